@@ -1,0 +1,471 @@
+/*
+ * medgp_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * FP64 CPU restatement ("oracle B") of MedGP's per-patient
+ * exact-inference hot path: SM-LMC covariance, NLML, hyper-parameter gradient,
+ * prior adjustment and one-step prediction.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference leg may load this library; the
+ * product (libmedgp_cuda.so and the host classes above it) never does.
+ *
+ * Parity pin: the reference ships NO golden vectors or tests for this path
+ * (SURVEY.md section 4), so this restatement is pinned against the reference itself
+ * compiled in this container (oracle/ref/build_ref.sh -> oracle/_ref/ref_eval):
+ * tests/golden/ holds outputs of that binary (float arithmetic) and
+ * tests/test_oracle_pin.py checks this file against them at the reference's own
+ * float noise floor (~1e-6 relative), plus central finite differences at FP64.
+ *
+ * Every function cites the reference file:line (relative to /root/reference) it
+ * restates.  Deliberate differences from the reference, all stated in DESIGN.md:
+ *   - all storage is double (the reference stores K, L, L^-1, W, alpha in float:
+ *     medgpc/src/inference/c_inference_exact.cpp:66-68,98,125,130,168-172);
+ *   - distances are exact double differences of the float32 times (the reference
+ *     rounds (x_i-x_j)^2 to float: medgpc/src/kernel/c_kernel.cpp:57);
+ *   - PI is the reference's truncated constant 3.14159265 passed in by the caller
+ *     (medgpc/src/util/global_settings.h:6).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORACLE_API __attribute__((visibility("default")))
+
+/* hyper-parameter layout, flat theta = [lik (D) | cov (Q(DR+2+D))]
+ * (medgpc/src/core/c_hyperparam.cpp:99-121); cov = [A raw (Q*D*R) | log mu (Q) |
+ * log v (Q) | log kappa (Q*D)] (medgpc/src/kernel/c_kernel_LMC_SM.cpp:51-62,88-89,175-176) */
+typedef struct {
+    int Q, D, R;
+    double pi;
+    double *sigma;  /* D      exp(theta_d)                c_likelihood.cpp:38-43 */
+    double *A;      /* Q*D*R  raw                         c_kernel_LMC_SM.cpp:92-96 */
+    double *mu;     /* Q      exp                         c_kernel_LMC_SM.cpp:57-59 */
+    double *v;      /* Q      exp */
+    double *kappa;  /* Q*D    exp */
+    double *B;      /* Q*D*D  A_q A_q^T + diag(kappa_q)   c_kernel_LMC_SM.cpp:72-115 */
+} hyp_t;
+
+static int hyp_count_cov(int Q, int D, int R) { return Q * (D * R + 2 + D); }
+
+static hyp_t *hyp_unpack(int Q, int D, int R, double pi, const double *theta)
+{
+    hyp_t *h = (hyp_t *)calloc(1, sizeof(hyp_t));
+    h->Q = Q; h->D = D; h->R = R; h->pi = pi;
+    h->sigma = (double *)malloc(sizeof(double) * D);
+    h->A = (double *)malloc(sizeof(double) * Q * D * R);
+    h->mu = (double *)malloc(sizeof(double) * Q);
+    h->v = (double *)malloc(sizeof(double) * Q);
+    h->kappa = (double *)malloc(sizeof(double) * Q * D);
+    h->B = (double *)malloc(sizeof(double) * Q * D * D);
+    const double *cov = theta + D;
+    for (int d = 0; d < D; d++) h->sigma[d] = exp(theta[d]);
+    for (int i = 0; i < Q * D * R; i++) h->A[i] = cov[i];
+    for (int q = 0; q < Q; q++) {
+        h->mu[q] = exp(cov[Q * D * R + q]);
+        h->v[q] = exp(cov[Q * (D * R + 1) + q]);
+        for (int d = 0; d < D; d++) h->kappa[q * D + d] = exp(cov[Q * (D * R + 2) + q * D + d]);
+    }
+    for (int q = 0; q < Q; q++)
+        for (int i = 0; i < D; i++)
+            for (int j = 0; j < D; j++) {
+                double s = 0.0;
+                for (int r = 0; r < R; r++)
+                    s += h->A[q * D * R + i * R + r] * h->A[q * D * R + j * R + r];
+                if (i == j) s += h->kappa[q * D + i];
+                h->B[(q * D + i) * D + j] = s;
+            }
+    return h;
+}
+
+static void hyp_free(hyp_t *h)
+{
+    free(h->sigma); free(h->A); free(h->mu); free(h->v); free(h->kappa); free(h->B); free(h);
+}
+
+/* spectral-mixture base kernel and its derivatives w.r.t. log mu and log v
+ * (medgpc/src/kernel/c_kernel_LMC_SM.cpp:374-391), tau = |t_i - t_j| */
+static double sm_k(double pi, double tau, double mu, double v)
+{
+    return cos(2.0 * pi * tau * mu) * exp(-2.0 * (pi * v) * (pi * v) * tau * tau);
+}
+static double sm_km(double pi, double tau, double mu, double v)
+{
+    double phi = 2.0 * pi * tau * mu;
+    return -phi * sin(phi) * exp(-2.0 * (pi * v) * (pi * v) * tau * tau);
+}
+static double sm_kv(double pi, double tau, double mu, double v)
+{
+    double d2piv = (pi * v) * (pi * v) * tau * tau;
+    return -4.0 * d2piv * cos(2.0 * pi * tau * mu) * exp(-2.0 * d2piv);
+}
+
+/* Gram matrix K (n x n, row-major, full symmetric), WITHOUT the noise diagonal
+ * (medgpc/src/kernel/c_kernel_LMC_SM.cpp:152-196) */
+static void gram_self(const hyp_t *h, int n, const int32_t *meta, const float *x, double *K)
+{
+    int D = h->D;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j <= i; j++) {
+            double tau = fabs((double)x[i] - (double)x[j]);
+            double s = 0.0;
+            for (int q = 0; q < h->Q; q++)
+                s += h->B[(q * D + meta[i]) * D + meta[j]] * sm_k(h->pi, tau, h->mu[q], h->v[q]);
+            K[(size_t)i * n + j] = s;
+            K[(size_t)j * n + i] = s;
+        }
+}
+
+/* unblocked lower Cholesky in place on a row-major matrix; returns 0 or the
+ * 1-based index of the first non-positive pivot (LAPACK potrf convention,
+ * called at medgpc/src/inference/c_inference_exact.cpp:98) */
+static int chol_lower(int n, double *a)
+{
+    for (int j = 0; j < n; j++) {
+        double *aj = a + (size_t)j * n;
+        double d = aj[j];
+        for (int k = 0; k < j; k++) d -= aj[k] * aj[k];
+        if (!(d > 0.0)) return j + 1;
+        d = sqrt(d);
+        aj[j] = d;
+        for (int i = j + 1; i < n; i++) {
+            double *ai = a + (size_t)i * n;
+            double s = ai[j];
+            for (int k = 0; k < j; k++) s -= ai[k] * aj[k];
+            ai[j] = s / d;
+        }
+    }
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++) a[(size_t)i * n + j] = 0.0;
+    return 0;
+}
+
+/* X = L^-1 (lower, row-major) (c_inference_exact.cpp:130 LAPACKE_strtri) */
+static void tri_inverse_lower(int n, const double *L, double *X)
+{
+    memset(X, 0, sizeof(double) * (size_t)n * n);
+    for (int j = 0; j < n; j++) {
+        X[(size_t)j * n + j] = 1.0 / L[(size_t)j * n + j];
+        for (int i = j + 1; i < n; i++) {
+            double s = 0.0;
+            for (int k = j; k < i; k++) s += L[(size_t)i * n + k] * X[(size_t)k * n + j];
+            X[(size_t)i * n + j] = -s / L[(size_t)i * n + i];
+        }
+    }
+}
+
+typedef struct {
+    int n;
+    int jitter;     /* number of extra sigma^2 additions that were needed */
+    double *L;      /* n*n lower Cholesky factor of K + noise (+ jitter)   */
+    double *alpha;  /* n   (K+noise)^-1 y                                   */
+    double logdet;  /* sum log L_ii                                         */
+    double quad;    /* y^T alpha                                            */
+} fit_t;
+
+static void fit_free(fit_t *f) { if (f) { free(f->L); free(f->alpha); free(f); } }
+
+/* K + noise -> L, alpha, with the reference's jitter loop
+ * (medgpc/src/inference/c_inference_exact.cpp:76-125) */
+static fit_t *fit_series(const hyp_t *h, int n, const int32_t *meta, const float *x, const float *y)
+{
+    fit_t *f = (fit_t *)calloc(1, sizeof(fit_t));
+    f->n = n;
+    double *K = (double *)malloc(sizeof(double) * (size_t)n * n);
+    f->L = (double *)malloc(sizeof(double) * (size_t)n * n);
+    f->alpha = (double *)malloc(sizeof(double) * n);
+    gram_self(h, n, meta, x, K);
+    for (int i = 0; i < n; i++) K[(size_t)i * n + i] += h->sigma[meta[i]] * h->sigma[meta[i]];
+    memcpy(f->L, K, sizeof(double) * (size_t)n * n);
+    int info = chol_lower(n, f->L);
+    int count = 0;
+    while (info != 0 && count < 10) {
+        for (int i = 0; i < n; i++) K[(size_t)i * n + i] += h->sigma[meta[i]] * h->sigma[meta[i]];
+        memcpy(f->L, K, sizeof(double) * (size_t)n * n);
+        info = chol_lower(n, f->L);
+        count++;
+    }
+    free(K);
+    if (info != 0) { fit_free(f); return NULL; }
+    f->jitter = count;
+    f->logdet = 0.0;
+    for (int i = 0; i < n; i++) f->logdet += log(f->L[(size_t)i * n + i]);
+    /* alpha: forward then backward substitution (zero mean: r = y, c_inference_exact.cpp:78-80) */
+    double *z = f->alpha;
+    for (int i = 0; i < n; i++) {
+        double s = (double)y[i];
+        for (int k = 0; k < i; k++) s -= f->L[(size_t)i * n + k] * z[k];
+        z[i] = s / f->L[(size_t)i * n + i];
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        double s = z[i];
+        for (int k = i + 1; k < n; k++) s -= f->L[(size_t)k * n + i] * z[k];
+        z[i] = s / f->L[(size_t)i * n + i];
+    }
+    f->quad = 0.0;
+    for (int i = 0; i < n; i++) f->quad += (double)y[i] * f->alpha[i];
+    return f;
+}
+
+/* W = K^-1 - alpha alpha^T (c_inference_exact.cpp:168-172), row-major full */
+static double *build_W(const fit_t *f)
+{
+    int n = f->n;
+    double *X = (double *)malloc(sizeof(double) * (size_t)n * n);
+    double *W = (double *)malloc(sizeof(double) * (size_t)n * n);
+    tri_inverse_lower(n, f->L, X);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j <= i; j++) {
+            double s = 0.0;
+            for (int k = i; k < n; k++) s += X[(size_t)k * n + i] * X[(size_t)k * n + j];
+            s -= f->alpha[i] * f->alpha[j];
+            W[(size_t)i * n + j] = s;
+            W[(size_t)j * n + i] = s;
+        }
+    free(X);
+    return W;
+}
+
+/* Gradient, LITERAL form: one dense dK per covariance hyper-parameter, g = 1/2 sum(W o dK)
+ * (medgpc/src/kernel/c_kernel_LMC_SM.cpp:198-327).  k/km/kv per q are tabulated once. */
+static void grad_direct(const hyp_t *h, int n, const int32_t *meta, const float *x,
+                        const double *W, double *gcov)
+{
+    int Q = h->Q, D = h->D, R = h->R;
+    size_t nn = (size_t)n * n;
+    double *kk = (double *)malloc(sizeof(double) * nn);
+    double *map = (double *)malloc(sizeof(double) * D * D);
+    for (int q = 0; q < Q; q++) {
+        /* which = 0: k (A and kappa entries), 1: km (mu), 2: kv (v) */
+        for (int which = 0; which < 3; which++) {
+            for (int i = 0; i < n; i++)
+                for (int j = 0; j < n; j++) {
+                    double tau = fabs((double)x[i] - (double)x[j]);
+                    double val = which == 0 ? sm_k(h->pi, tau, h->mu[q], h->v[q])
+                               : which == 1 ? sm_km(h->pi, tau, h->mu[q], h->v[q])
+                                            : sm_kv(h->pi, tau, h->mu[q], h->v[q]);
+                    kk[(size_t)i * n + j] = W[(size_t)i * n + j] * val;
+                }
+            if (which == 0) {
+                for (int d = 0; d < D; d++)
+                    for (int r = 0; r < R; r++) {
+                        /* dB/dA[d,r] = e_d a_r^T + a_r e_d^T (c_kernel_LMC_SM.cpp:238-244) */
+                        memset(map, 0, sizeof(double) * D * D);
+                        for (int i = 0; i < D; i++) map[i * D + d] += h->A[q * D * R + i * R + r];
+                        for (int i = 0; i < D; i++) map[d * D + i] += h->A[q * D * R + i * R + r];
+                        double s = 0.0;
+                        for (int i = 0; i < n; i++)
+                            for (int j = 0; j < n; j++)
+                                s += map[meta[i] * D + meta[j]] * kk[(size_t)i * n + j];
+                        gcov[q * D * R + d * R + r] = 0.5 * s;
+                    }
+                for (int d = 0; d < D; d++) {
+                    /* d/dlog kappa_q[d]: kappa on (d,d) only (c_kernel_LMC_SM.cpp:294-320) */
+                    double s = 0.0;
+                    for (int i = 0; i < n; i++) if (meta[i] == d)
+                        for (int j = 0; j < n; j++) if (meta[j] == d) s += kk[(size_t)i * n + j];
+                    gcov[Q * (D * R + 2) + q * D + d] = 0.5 * h->kappa[q * D + d] * s;
+                }
+            } else {
+                double s = 0.0;
+                for (int i = 0; i < n; i++)
+                    for (int j = 0; j < n; j++)
+                        s += h->B[(q * D + meta[i]) * D + meta[j]] * kk[(size_t)i * n + j];
+                gcov[Q * D * R + (which == 1 ? 0 : Q) + q] = 0.5 * s;
+            }
+        }
+    }
+    free(kk); free(map);
+}
+
+/* Gradient, COLLAPSED form: one pass over W into 3Q block sums */
+static void grad_collapsed(const hyp_t *h, int n, const int32_t *meta, const float *x,
+                           const double *W, double *gcov)
+{
+    int Q = h->Q, D = h->D, R = h->R;
+    double *S = (double *)calloc((size_t)3 * Q * D * D, sizeof(double));
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            double tau = fabs((double)x[i] - (double)x[j]);
+            double w = W[(size_t)i * n + j];
+            size_t de = (size_t)meta[i] * D + meta[j];
+            for (int q = 0; q < Q; q++) {
+                S[(size_t)(0 * Q + q) * D * D + de] += w * sm_k(h->pi, tau, h->mu[q], h->v[q]);
+                S[(size_t)(1 * Q + q) * D * D + de] += w * sm_km(h->pi, tau, h->mu[q], h->v[q]);
+                S[(size_t)(2 * Q + q) * D * D + de] += w * sm_kv(h->pi, tau, h->mu[q], h->v[q]);
+            }
+        }
+    for (int q = 0; q < Q; q++) {
+        const double *Sk = S + (size_t)(0 * Q + q) * D * D;
+        const double *Sm = S + (size_t)(1 * Q + q) * D * D;
+        const double *Sv = S + (size_t)(2 * Q + q) * D * D;
+        for (int d = 0; d < D; d++)
+            for (int r = 0; r < R; r++) {
+                double s = 0.0;
+                for (int e = 0; e < D; e++) s += Sk[d * D + e] * h->A[q * D * R + e * R + r];
+                gcov[q * D * R + d * R + r] = s;
+            }
+        double gm = 0.0, gv = 0.0;
+        for (int d = 0; d < D; d++)
+            for (int e = 0; e < D; e++) {
+                gm += h->B[(q * D + d) * D + e] * Sm[d * D + e];
+                gv += h->B[(q * D + d) * D + e] * Sv[d * D + e];
+            }
+        gcov[Q * D * R + q] = 0.5 * gm;
+        gcov[Q * (D * R + 1) + q] = 0.5 * gv;
+        for (int d = 0; d < D; d++)
+            gcov[Q * (D * R + 2) + q * D + d] = 0.5 * h->kappa[q * D + d] * Sk[d * D + d];
+    }
+    free(S);
+}
+
+/* ------------------------------------------------------------------ public API */
+
+/* One NLML (+gradient) evaluation, WITHOUT prior terms: the unit of work
+ * c_objective_one::compute_objective -> c_inference_exact::compute_nlml
+ * (medgpc/src/util/c_objective_one.cpp:40-81; c_inference_exact.cpp:29-244).
+ * grad_mode: 0 = collapsed block sums, 1 = literal per-hyper-parameter dK.
+ * status: 0 ok, k>0 = k jitter additions were needed, -1 = not positive definite.
+ * Returns 0, or -1 on failure (nlml/grad untouched). */
+ORACLE_API int medgp_oracle_nlml_grad(int Q, int D, int R, double pi, int n,
+                                      const int32_t *meta, const float *x, const float *y,
+                                      const double *theta, int want_grad, int grad_mode,
+                                      double *nlml, double *grad, int *status)
+{
+    hyp_t *h = hyp_unpack(Q, D, R, pi, theta);
+    fit_t *f = fit_series(h, n, meta, x, y);
+    if (!f) { *status = -1; hyp_free(h); return -1; }
+    *status = f->jitter;
+    /* c_inference_exact.cpp:146-152 */
+    *nlml = 0.5 * f->quad + f->logdet + n * log(2.0 * pi) / 2.0;
+    if (want_grad) {
+        double *W = build_W(f);
+        /* noise: sigma_d^2 * sum_{i in d} W_ii (c_inference_exact.cpp:191-203) */
+        for (int d = 0; d < D; d++) {
+            double s = 0.0;
+            for (int i = 0; i < n; i++) if (meta[i] == d) s += W[(size_t)i * n + i];
+            grad[d] = h->sigma[d] * h->sigma[d] * s;
+        }
+        if (grad_mode == 1) grad_direct(h, n, meta, x, W, grad + D);
+        else grad_collapsed(h, n, meta, x, W, grad + D);
+        free(W);
+    }
+    fit_free(f);
+    hyp_free(h);
+    return 0;
+}
+
+/* Gram matrix with noise diagonal, row-major n*n, for kernel (1) parity tests
+ * (c_kernel_LMC_SM.cpp:152-196 + c_inference_exact.cpp:88-92). */
+ORACLE_API int medgp_oracle_gram(int Q, int D, int R, double pi, int n, const int32_t *meta,
+                                 const float *x, const double *theta, int add_noise, double *K)
+{
+    hyp_t *h = hyp_unpack(Q, D, R, pi, theta);
+    gram_self(h, n, meta, x, K);
+    if (add_noise)
+        for (int i = 0; i < n; i++) K[(size_t)i * n + i] += h->sigma[meta[i]] * h->sigma[meta[i]];
+    hyp_free(h);
+    return 0;
+}
+
+/* alpha = (K+noise)^-1 y and lower Cholesky factor (row-major) for solver parity tests */
+ORACLE_API int medgp_oracle_fit(int Q, int D, int R, double pi, int n, const int32_t *meta,
+                                const float *x, const float *y, const double *theta,
+                                double *alpha, double *L, double *logdet)
+{
+    hyp_t *h = hyp_unpack(Q, D, R, pi, theta);
+    fit_t *f = fit_series(h, n, meta, x, y);
+    hyp_free(h);
+    if (!f) return -1;
+    if (alpha) memcpy(alpha, f->alpha, sizeof(double) * n);
+    if (L) memcpy(L, f->L, sizeof(double) * (size_t)n * n);
+    if (logdet) *logdet = f->logdet;
+    fit_free(f);
+    return 0;
+}
+
+/* Prediction at m test points from n training points
+ * (medgpc/src/core/gp_regression.cpp:128-214; cross-cov c_kernel_LMC_SM.cpp:329-372;
+ * prior variance c_kernel_LMC_SM.cpp:122-150):
+ *   mean = k*^T alpha ; var = sum_q B_q[f*,f*] - |L^-1 k*|^2 + sigma_{f*}^2 */
+ORACLE_API int medgp_oracle_predict(int Q, int D, int R, double pi, int n, const int32_t *meta,
+                                    const float *x, const float *y, const double *theta, int m,
+                                    const int32_t *meta_star, const float *x_star,
+                                    double *mean, double *var, int *status)
+{
+    hyp_t *h = hyp_unpack(Q, D, R, pi, theta);
+    fit_t *f = fit_series(h, n, meta, x, y);
+    if (!f) { *status = -1; hyp_free(h); return -1; }
+    *status = f->jitter;
+    double *ks = (double *)malloc(sizeof(double) * n);
+    for (int t = 0; t < m; t++) {
+        int fs = meta_star[t];
+        for (int i = 0; i < n; i++) {
+            double tau = fabs((double)x[i] - (double)x_star[t]);
+            double s = 0.0;
+            for (int q = 0; q < Q; q++)
+                s += h->B[(q * D + meta[i]) * D + fs] * sm_k(pi, tau, h->mu[q], h->v[q]);
+            ks[i] = s;
+        }
+        double mu = 0.0;
+        for (int i = 0; i < n; i++) mu += ks[i] * f->alpha[i];
+        /* v = L^-1 k* by forward substitution, in place */
+        double vv = 0.0;
+        for (int i = 0; i < n; i++) {
+            double s = ks[i];
+            for (int k = 0; k < i; k++) s -= f->L[(size_t)i * n + k] * ks[k];
+            ks[i] = s / f->L[(size_t)i * n + i];
+            vv += ks[i] * ks[i];
+        }
+        double kss = 0.0;
+        for (int q = 0; q < Q; q++) kss += h->B[(q * D + fs) * D + fs];
+        mean[t] = mu;
+        var[t] = kss - vv + h->sigma[fs] * h->sigma[fs];
+    }
+    free(ks);
+    fit_free(f);
+    hyp_free(h);
+    return 0;
+}
+
+/* Prior log-densities and derivatives (medgpc/src/prior/c_prior.cpp:383-421).
+ * type 1 = normal(mean p0, VARIANCE p1), type 2 = laplace(loc p0, scale p1).
+ * params are float in the reference (vector<float>), so they are rounded here too. */
+ORACLE_API int medgp_oracle_prior(int type, double xval, float p0, float p1, double pi,
+                                  double *lp, double *dlp)
+{
+    if (type == 1) {
+        *lp = -1.0 * (xval - p0) * (xval - p0) / (2.0 * p1) - log(2 * pi * p1) / 2.0;
+        *dlp = -1.0 * (xval - p0) / p1;
+        return 0;
+    }
+    if (type == 2) {
+        *lp = (-1.0 * fabs(xval - p0) / p1) - log(2 * p1);
+        if (xval == p0) *dlp = 0.0;
+        else *dlp = -1.0 * (xval > p0 ? 1.0 : -1.0) / p1;
+        return 0;
+    }
+    *lp = 0.0; *dlp = 0.0;
+    return 0;
+}
+
+/* Prior adjustment of (nlml, grad) for the covariance block, as
+ * c_inference_prior::compute_nlml applies it (medgpc/src/inference/c_inference_prior.cpp:94-121):
+ * flag[i] active; type 0 clamp -> g=0; type -1 none; else nlml -= lp, g -= (x*)dlp.
+ * xval is the TRANSFORMED hyper-parameter (A raw, others after exp). */
+ORACLE_API int medgp_oracle_prior_adjust(int Q, int D, int R, double pi, const double *theta,
+                                         const int *flag_cov, const int *type_cov,
+                                         const int *exp_cov, const float *p0, const float *p1,
+                                         int want_grad, double *nlml, double *grad)
+{
+    int ncov = hyp_count_cov(Q, D, R);
+    for (int i = 0; i < ncov; i++) {
+        if (!flag_cov[i]) continue;
+        if (type_cov[i] == 0) { if (want_grad) grad[D + i] = 0.0; continue; }
+        if (type_cov[i] == -1) continue;
+        double xval = i < Q * D * R ? theta[D + i] : exp(theta[D + i]);
+        double lp, dlp;
+        medgp_oracle_prior(type_cov[i], xval, p0[i], p1[i], pi, &lp, &dlp);
+        *nlml -= lp;
+        if (want_grad) grad[D + i] -= exp_cov[i] ? xval * dlp : dlp;
+    }
+    return 0;
+}
