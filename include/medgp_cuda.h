@@ -1,0 +1,135 @@
+/*
+ * medgp_cuda.h -- C ABI of libmedgp_cuda.so, the B200 (sm_100a) backend for MedGP's
+ * per-patient exact-inference hot path.
+ *
+ * The reference (bee-hive/MedGP) has no FFI; its seam is C++ virtual dispatch.  Each entry
+ * point below names the reference interface it replaces (paths relative to the reference
+ * root, medgpc/src/...).  All pointers are HOST pointers unless the name starts with d_;
+ * the library owns all device memory; no exception crosses the boundary; every function
+ * returns MEDGP_OK (0) or a negative medgp_status.  One context drives ONE GPU (one process
+ * or host thread per GPU; contexts are independent, so a cohort shards over GPUs with no
+ * collective).  A context is thread-compatible, not thread-safe.
+ *
+ * Hyper-parameter vector theta (length P = D + Q*(D*R+2+D), doubles), exactly the
+ * reference's flat order (core/c_hyperparam.cpp:99-121, kernel/c_kernel_LMC_SM.cpp:51-62):
+ *   [ log sigma_d (D) | A_q[d][r] raw (Q*D*R, index q*D*R+d*R+r) | log mu_q (Q) |
+ *     log v_q (Q) | log kappa_q[d] (Q*D, index q*D+d) ]
+ * Gradients come back in the same order, w.r.t. the stored (log or raw) values, WITHOUT
+ * prior terms (those stay on the host: inference/c_inference_prior.cpp:59-150).
+ */
+#ifndef MEDGP_CUDA_H
+#define MEDGP_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct medgp_ctx medgp_ctx;
+
+typedef enum {
+    MEDGP_OK = 0,
+    MEDGP_ERR_ARG = -1,      /* bad argument (NULL, out of range, model not set) */
+    MEDGP_ERR_CUDA = -2,     /* a CUDA call failed; see medgp_cuda_last_error   */
+    MEDGP_ERR_NOMEM = -3,    /* workspace too small for even one evaluation      */
+    MEDGP_ERR_NODEVICE = -4  /* no usable sm_100 device                          */
+} medgp_status;
+
+/* Per-evaluation status written to the `status` arrays:
+ *   0   success, no jitter;  k>0  success after k extra noise additions to the diagonal
+ *   -1  still not positive definite after 10 additions (the reference returns false:
+ *       inference/c_inference_exact.cpp:99-111) -- nlml/grad/mean/var are then NaN. */
+
+/* Stages for which device time is accumulated (CUDA events on the library's stream). */
+enum {
+    MEDGP_STAGE_PREP = 0,     /* theta -> B_q, sigma^2, per-point cos/sin tables          */
+    MEDGP_STAGE_ASSEMBLE,     /* kernel (1): covariance assembly                           */
+    MEDGP_STAGE_POTRF,        /* kernel (2): blocked FP64 Cholesky (DMMA)                  */
+    MEDGP_STAGE_SOLVE,        /* kernel (2): triangular solves, log-det, NLML              */
+    MEDGP_STAGE_TRTRI,        /* kernel (2): L^-1                                          */
+    MEDGP_STAGE_LAUUM,        /* kernel (2): K^-1 = L^-T L^-1                              */
+    MEDGP_STAGE_GRAD,         /* kernel (3): fused gradient reduction                      */
+    MEDGP_STAGE_PREDICT,      /* kernel (4): cross-covariance, predictive mean/variance    */
+    MEDGP_STAGE_COUNT
+};
+
+typedef struct {
+    double ms[MEDGP_STAGE_COUNT];        /* accumulated device milliseconds per stage        */
+    long long launches[MEDGP_STAGE_COUNT]; /* kernel launches per stage                      */
+    double flops[MEDGP_STAGE_COUNT];     /* algorithmic FP64 flop     */
+    double bytes[MEDGP_STAGE_COUNT];     /* algorithmic HBM bytes                            */
+    long long evals;                     /* evaluations completed                            */
+} medgp_stage_times;
+
+/* Create a context on CUDA device `device`.  workspace_bytes = 0 picks 70% of free HBM.
+ * Fails with MEDGP_ERR_NODEVICE when there is no GPU: there is NO CPU fallback. */
+int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_bytes);
+void medgp_cuda_destroy(medgp_ctx *ctx);
+const char *medgp_cuda_last_error(const medgp_ctx *ctx);
+
+/* Kernel shape.  Replaces c_kernel_LMC_SM::set_kernel_param (kernel/c_kernel_LMC_SM.cpp:64-70)
+ * and c_likelihood_gaussianMO's output count (likelihoods/c_likelihood_gaussianMO.cpp:25-29).
+ * pi_const is the reference's truncated PI, 3.14159265 (util/global_settings.h:6). */
+int medgp_cuda_model(medgp_ctx *ctx, int Q, int D, int R, double pi_const);
+int medgp_cuda_num_hyp(const medgp_ctx *ctx);  /* P, or negative status */
+
+/* Upload one series (a patient, or one sliding-window training set) once.  Replaces the
+ * data copies c_objective_one keeps (util/c_objective_one.cpp:23-36).  meta[i] in [0,D) is
+ * the feature slot of point i (dataio/c_experiment.cpp:298), x hours, y z-scored value.
+ * Any point order is accepted; results do not depend on it. */
+int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, const float *x,
+                          const float *y, int *out_series_id);
+int medgp_cuda_free_series(medgp_ctx *ctx, int series_id);
+int medgp_cuda_clear_series(medgp_ctx *ctx);
+
+/* batch NLML (+ gradient) evaluations: evaluation b uses series_id[b] and theta[b*P..].
+ * Replaces c_objective_one::compute_objective -> GP_Regression::train ->
+ * c_inference_exact::compute_nlml (util/c_objective_one.cpp:40-81, core/gp_regression.cpp:102-126,
+ * inference/c_inference_exact.cpp:29-244) including kernel/c_kernel_LMC_SM.cpp:152-327.
+ * grad may be NULL when want_grad == 0. */
+int medgp_cuda_nlml_grad(medgp_ctx *ctx, int batch, const int *series_id, const double *theta,
+                         int want_grad, double *nlml, double *grad, int *status);
+
+/* Same work with theta already resident in HBM and results left there (d_theta: batch*P,
+ * d_nlml: batch, d_grad: batch*P or NULL, d_status: batch ints); asynchronous on the
+ * context's stream -- call medgp_cuda_sync before reading.  Evaluations that fail the
+ * Cholesky are NOT retried with jitter on this path (status -1). */
+int medgp_cuda_nlml_grad_device(medgp_ctx *ctx, int batch, const int *series_id,
+                                const double *d_theta, int want_grad, double *d_nlml,
+                                double *d_grad, int *d_status);
+int medgp_cuda_sync(medgp_ctx *ctx);
+
+/* batch predictions: evaluation b trains on series_id[b] with theta[b*P..] and predicts the
+ * n_star[b] points meta_star/x_star[star_offset[b] ..].  Replaces GP_Regression::train(false)
+ * + GP_Regression::predict (core/gp_regression.cpp:102-214; cross-covariance
+ * kernel/c_kernel_LMC_SM.cpp:329-372, prior variance :122-150).  mean/var are indexed like
+ * x_star.  star_offset has batch+1 entries. */
+int medgp_cuda_predict(medgp_ctx *ctx, int batch, const int *series_id, const double *theta,
+                       const int *star_offset, const int32_t *meta_star, const float *x_star,
+                       double *mean, double *var, int *status);
+
+/* Debug/parity taps (tests only; one evaluation): the assembled K+noise (n*n, row-major,
+ * full symmetric) for kernel (1); the Cholesky factor L (n*n row-major lower) and
+ * alpha = K^-1 y for kernel (2); K^-1 (n*n row-major full) after want_grad.
+ * All in the caller's original point order. */
+int medgp_cuda_debug_matrices(medgp_ctx *ctx, int series_id, const double *theta,
+                              double *K, double *L, double *alpha, double *Kinv);
+
+/* Per-stage device timings and algorithmic work counters since the last reset. */
+int medgp_cuda_profile(medgp_ctx *ctx, int enable);  /* enabling adds event records */
+int medgp_cuda_stage_times(medgp_ctx *ctx, medgp_stage_times *out, int reset);
+
+/* Raw device helpers so callers (bench, Python) can stage theta/results without torch. */
+int medgp_cuda_malloc(medgp_ctx *ctx, size_t bytes, void **d_ptr);
+int medgp_cuda_free(medgp_ctx *ctx, void *d_ptr);
+int medgp_cuda_memcpy_h2d(medgp_ctx *ctx, void *d_dst, const void *src, size_t bytes);
+int medgp_cuda_memcpy_d2h(medgp_ctx *ctx, void *dst, const void *d_src, size_t bytes);
+/* The context's stream as a cudaStream_t (for event timing by the caller). */
+void *medgp_cuda_stream(medgp_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEDGP_CUDA_H */

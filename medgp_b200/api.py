@@ -1,0 +1,224 @@
+"""ctypes binding of libmedgp_cuda.so (include/medgp_cuda.h) used by tests/ and bench.py.
+
+This is plumbing only: every numerical result comes from the CUDA library.  There is no CPU
+path -- loading fails loudly when the shared library is missing, and ``Context`` raises when
+no sm_100 GPU is present.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmedgp_cuda.so")
+PI_REF = 3.14159265  # medgpc/src/util/global_settings.h:6
+
+STAGES = ["prep", "assemble", "potrf", "solve", "trtri", "lauum", "grad", "predict"]
+
+# every symbol include/medgp_cuda.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "medgp_cuda_create", "medgp_cuda_destroy", "medgp_cuda_last_error", "medgp_cuda_model",
+    "medgp_cuda_num_hyp", "medgp_cuda_add_series", "medgp_cuda_free_series",
+    "medgp_cuda_clear_series", "medgp_cuda_nlml_grad", "medgp_cuda_nlml_grad_device",
+    "medgp_cuda_sync", "medgp_cuda_predict", "medgp_cuda_debug_matrices", "medgp_cuda_profile",
+    "medgp_cuda_stage_times", "medgp_cuda_malloc", "medgp_cuda_free", "medgp_cuda_memcpy_h2d",
+    "medgp_cuda_memcpy_d2h", "medgp_cuda_stream",
+]
+
+
+class StageTimes(ctypes.Structure):
+    _fields_ = [("ms", ctypes.c_double * 8), ("launches", ctypes.c_longlong * 8),
+                ("flops", ctypes.c_double * 8), ("bytes", ctypes.c_double * 8),
+                ("evals", ctypes.c_longlong)]
+
+
+class MedgpError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def build_library():
+    """Compile the CUDA library in-tree (nvcc cross-compiles sm_100a without a GPU)."""
+    subprocess.run(["make", "-C", os.path.join(HERE, "csrc")], check=True)
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MedgpError(f"{LIB_PATH} is missing: build it with `make -C medgp_b200/csrc` "
+                         "(there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i, dp, ip = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.medgp_cuda_create.argtypes = [ctypes.POINTER(vp), i, ctypes.c_size_t]
+    lib.medgp_cuda_destroy.argtypes = [vp]
+    lib.medgp_cuda_destroy.restype = None
+    lib.medgp_cuda_last_error.argtypes = [vp]
+    lib.medgp_cuda_last_error.restype = ctypes.c_char_p
+    lib.medgp_cuda_model.argtypes = [vp, i, i, i, ctypes.c_double]
+    lib.medgp_cuda_num_hyp.argtypes = [vp]
+    lib.medgp_cuda_add_series.argtypes = [vp, i, ip, fp, fp, ip]
+    lib.medgp_cuda_free_series.argtypes = [vp, i]
+    lib.medgp_cuda_clear_series.argtypes = [vp]
+    lib.medgp_cuda_nlml_grad.argtypes = [vp, i, ip, dp, i, dp, dp, ip]
+    lib.medgp_cuda_nlml_grad_device.argtypes = [vp, i, ip, vp, i, vp, vp, vp]
+    lib.medgp_cuda_sync.argtypes = [vp]
+    lib.medgp_cuda_predict.argtypes = [vp, i, ip, dp, ip, ip, fp, dp, dp, ip]
+    lib.medgp_cuda_debug_matrices.argtypes = [vp, i, dp, dp, dp, dp, dp]
+    lib.medgp_cuda_profile.argtypes = [vp, i]
+    lib.medgp_cuda_stage_times.argtypes = [vp, ctypes.POINTER(StageTimes), i]
+    lib.medgp_cuda_malloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp)]
+    lib.medgp_cuda_free.argtypes = [vp, vp]
+    lib.medgp_cuda_memcpy_h2d.argtypes = [vp, vp, vp, ctypes.c_size_t]
+    lib.medgp_cuda_memcpy_d2h.argtypes = [vp, vp, vp, ctypes.c_size_t]
+    lib.medgp_cuda_stream.argtypes = [vp]
+    lib.medgp_cuda_stream.restype = vp
+    _lib = lib
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+
+
+def _fp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+class Context:
+    """One GPU, one model shape (Q, D, R), many uploaded series."""
+
+    def __init__(self, Q, D, R, device=0, workspace_bytes=0, pi=PI_REF):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p()
+        rc = self.lib.medgp_cuda_create(ctypes.byref(self.h), int(device), int(workspace_bytes))
+        if rc != 0:
+            self.h = None
+            raise MedgpError(f"medgp_cuda_create failed with status {rc} "
+                             "(no sm_100 GPU? there is no CPU fallback)")
+        self.Q, self.D, self.R = Q, D, R
+        self._check(self.lib.medgp_cuda_model(self.h, Q, D, R, float(pi)))
+        self.P = self.lib.medgp_cuda_num_hyp(self.h)
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.medgp_cuda_last_error(self.h)
+            raise MedgpError(f"medgp_cuda status {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self.h:
+            self.lib.medgp_cuda_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ series
+    def add_series(self, meta, x, y):
+        meta = np.ascontiguousarray(meta, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        sid = ctypes.c_int(-1)
+        self._check(self.lib.medgp_cuda_add_series(self.h, len(x), _ip(meta), _fp(x), _fp(y),
+                                                   ctypes.byref(sid)))
+        return sid.value
+
+    def free_series(self, sid):
+        self._check(self.lib.medgp_cuda_free_series(self.h, int(sid)))
+
+    def clear_series(self):
+        self._check(self.lib.medgp_cuda_clear_series(self.h))
+
+    # ------------------------------------------------------------------ hot path, host buffers
+    def nlml_grad(self, series_ids, theta, want_grad=True):
+        """theta: (batch, P).  Returns (nlml[batch], grad[batch,P] or None, status[batch])."""
+        sids = np.ascontiguousarray(series_ids, dtype=np.int32)
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(len(sids), self.P)
+        nlml = np.empty(len(sids))
+        grad = np.empty((len(sids), self.P)) if want_grad else None
+        status = np.empty(len(sids), dtype=np.int32)
+        self._check(self.lib.medgp_cuda_nlml_grad(
+            self.h, len(sids), _ip(sids), _dp(theta), int(want_grad), _dp(nlml),
+            _dp(grad) if want_grad else None, _ip(status)))
+        return nlml, grad, status
+
+    def predict(self, series_ids, theta, star_offset, meta_star, x_star):
+        sids = np.ascontiguousarray(series_ids, dtype=np.int32)
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(len(sids), self.P)
+        star_offset = np.ascontiguousarray(star_offset, dtype=np.int32)
+        meta_star = np.ascontiguousarray(meta_star, dtype=np.int32)
+        x_star = np.ascontiguousarray(x_star, dtype=np.float32)
+        m = int(star_offset[-1])
+        mean, var = np.empty(m), np.empty(m)
+        status = np.empty(len(sids), dtype=np.int32)
+        self._check(self.lib.medgp_cuda_predict(
+            self.h, len(sids), _ip(sids), _dp(theta), _ip(star_offset), _ip(meta_star),
+            _fp(x_star), _dp(mean), _dp(var), _ip(status)))
+        return mean, var, status
+
+    # ------------------------------------------------------------------ device-resident variant
+    def malloc(self, nbytes):
+        p = ctypes.c_void_p()
+        self._check(self.lib.medgp_cuda_malloc(self.h, int(nbytes), ctypes.byref(p)))
+        return p
+
+    def free(self, p):
+        self._check(self.lib.medgp_cuda_free(self.h, p))
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._check(self.lib.medgp_cuda_memcpy_h2d(self.h, dptr, arr.ctypes.data_as(ctypes.c_void_p), arr.nbytes))
+
+    def d2h(self, arr, dptr):
+        self._check(self.lib.medgp_cuda_memcpy_d2h(self.h, arr.ctypes.data_as(ctypes.c_void_p), dptr, arr.nbytes))
+
+    def nlml_grad_device(self, series_ids, d_theta, want_grad, d_nlml, d_grad, d_status):
+        sids = np.ascontiguousarray(series_ids, dtype=np.int32)
+        self._check(self.lib.medgp_cuda_nlml_grad_device(
+            self.h, len(sids), _ip(sids), d_theta, int(want_grad), d_nlml, d_grad, d_status))
+
+    def sync(self):
+        self._check(self.lib.medgp_cuda_sync(self.h))
+
+    def stream(self):
+        return self.lib.medgp_cuda_stream(self.h)
+
+    # ------------------------------------------------------------------ taps and timings
+    def debug_matrices(self, sid, theta, n, want=("K", "L", "alpha", "Kinv")):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        out = {}
+        K = np.zeros((n, n)) if "K" in want else None
+        L = np.zeros((n, n)) if "L" in want else None
+        a = np.zeros(n) if "alpha" in want else None
+        Ki = np.zeros((n, n)) if "Kinv" in want else None
+        self._check(self.lib.medgp_cuda_debug_matrices(
+            self.h, int(sid), _dp(theta), _dp(K) if K is not None else None,
+            _dp(L) if L is not None else None, _dp(a) if a is not None else None,
+            _dp(Ki) if Ki is not None else None))
+        for k, v in (("K", K), ("L", L), ("alpha", a), ("Kinv", Ki)):
+            if v is not None:
+                out[k] = v
+        return out
+
+    def profile(self, enable=True):
+        self._check(self.lib.medgp_cuda_profile(self.h, int(enable)))
+
+    def stage_times(self, reset=False):
+        st = StageTimes()
+        self._check(self.lib.medgp_cuda_stage_times(self.h, ctypes.byref(st), int(reset)))
+        return {name: dict(ms=st.ms[i], launches=st.launches[i], flops=st.flops[i], bytes=st.bytes[i])
+                for i, name in enumerate(STAGES)} | {"evals": st.evals}

@@ -1,0 +1,299 @@
+// common.cuh -- shared definitions for libmedgp_cuda.so (sm_100a only).
+//
+// HBM layout of one in-flight evaluation (all FP64):
+//   M      npad x npad column-major square, ld = npad (npad = n rounded up to 64, padded with
+//          the identity).  Lower tiles hold K -> L -> K^-1 in place; strictly-upper tiles hold
+//          U = (L^-1)^T once the triangular inverse ran.
+//   dinv   T = npad/64 blocks of 64x64 column-major: X_kk = inv(L_kk) (lower, zeros above)
+//   dinvT  the same blocks transposed (X_kk^T, upper)
+//   rhs    nrhs x npad: row 0 = y -> z = L^-1 y ; rows 1.. = k* -> L^-1 k* (prediction)
+//   alpha  npad: K^-1 y
+//   cs     Q x npad x (cos, sin)(2 PI mu_q t_i)
+//   par    derived hyper-parameters (ParLayout below)
+//   part   gradient partial sums, one row of (3Q+1) doubles per work item
+//   blk    T per-block partial log-determinants
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MEDGP_NB 64        // tile edge (rows/cols of a tile, depth of one tile product)
+#define MEDGP_SLD 68       // shared-memory pitch of a 64-row tile column (== 4 mod 16: DMMA fragment loads are bank-conflict free)
+#define MEDGP_KC 16        // k-depth of one pipeline stage
+#define MEDGP_NSTAGE 4     // pipeline stages
+#define MEDGP_QMAX 8       // compile-time bound on mixture components
+#define MEDGP_GEMM_THREADS 128
+
+struct ModelDims {
+    int Q, D, R, P;
+    double pi;
+    // offsets (in doubles) inside the per-evaluation parameter block
+    int oB, oSig2, oW, oC, oA, oKappa, oBdiag, parLen;
+};
+
+struct __align__(16) EvalDesc {
+    double *M, *dinv, *dinvT, *rhs, *alpha, *cs, *par, *part, *blk;
+    const double *t, *y;
+    const int *meta, *off;
+    const int4 *items;
+    const int *pair_start;
+    const double *star_t;    // prediction points of this evaluation (device), or null
+    const int *star_meta;
+    int n, npad, T, nitems;
+    int jitter, nrhs, nstar, out_index;
+    int star_out;            // offset of this evaluation's predictions in the output arrays
+    int pad0, pad1, pad2;
+};
+
+// ---------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk async copy (TMA engine, UBLKCP) + FP64 tensor-core MMA (DMMA)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// 1-D bulk copy global -> shared through the TMA engine; completion is signalled on `bar`.
+// src, dst 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor core (SASS: DMMA.8x8x4)
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------
+// Tile GEMM core:  C(64x64) = sum_l A_l * B_l^T,  A_l, B_l 64x64 column-major tiles in HBM.
+// One CTA of 4 warps; warp (wm, wn) owns the 32x32 quadrant, as 4x4 DMMA 8x8 sub-tiles:
+//   acc[a][b][e] = C[32wm + 8a + lane/4][32wn + 8b + 2(lane%4) + e]
+// Operands are staged column-by-column (512 B each) by cp.async.bulk into a 4-stage ring of
+// [k][m] / [k][n] panels with pitch MEDGP_SLD, guarded by full/empty mbarriers.
+// ---------------------------------------------------------------------------------------
+constexpr int kPanelElems = MEDGP_KC * MEDGP_SLD;            // one operand panel of a stage
+constexpr int kStageElems = 2 * kPanelElems;                 // A panel + B panel
+constexpr int kTileElems = MEDGP_NB * MEDGP_SLD;             // a full 64x64 tile with pitch
+constexpr int kGemmSmemBytes = MEDGP_NSTAGE * kStageElems * 8; // 69632 B == 2 full tiles
+
+struct GemmBars {
+    uint64_t full[MEDGP_NSTAGE];
+    uint64_t empty[MEDGP_NSTAGE];
+};
+
+__device__ __forceinline__ void gemm_bars_init(GemmBars *bars)
+{
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MEDGP_NSTAGE; s++) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], MEDGP_GEMM_THREADS / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void acc_zero(double (&acc)[4][4][2])
+{
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+}
+
+// accumulate `depth4` k-steps of 4 from panels sA ([k][m], pitch SLD) and sB ([k][n])
+__device__ __forceinline__ void mma_panels(double (&acc)[4][4][2], const double *sA,
+                                           const double *sB, int depth4, int wm, int wn, int lane)
+{
+    const int r = lane >> 2, kq = lane & 3;
+    const double *pa = sA + kq * MEDGP_SLD + wm * 32 + r;
+    const double *pb = sB + kq * MEDGP_SLD + wn * 32 + r;
+#pragma unroll 4
+    for (int kk = 0; kk < depth4; kk++) {
+        double a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            a[u] = pa[8 * u];
+            b[u] = pb[8 * u];
+        }
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+#pragma unroll
+            for (int y = 0; y < 4; y++) dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+        pa += 4 * MEDGP_SLD;
+        pb += 4 * MEDGP_SLD;
+    }
+}
+
+// TileFn: void operator()(int l, const double*& A, int& lda, const double*& B, int& ldb)
+template <class TileFn>
+__device__ __forceinline__ void gemm_nt_tiles(double (&acc)[4][4][2], int nl, TileFn tiles,
+                                              double *smem, GemmBars *bars)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp & 1, wn = warp >> 1;
+    const int nch = nl * (MEDGP_NB / MEDGP_KC);
+    constexpr uint32_t kStageBytes = 2 * MEDGP_KC * MEDGP_NB * 8;  // bytes landing per stage
+
+    auto issue = [&](int ch) {
+        const int s = ch % MEDGP_NSTAGE;
+        const int l = ch / (MEDGP_NB / MEDGP_KC), cc = ch % (MEDGP_NB / MEDGP_KC);
+        const double *A, *B;
+        int lda, ldb;
+        tiles(l, A, lda, B, ldb);
+        if (lane == 0) mbar_arrive_expect_tx(&bars->full[s], kStageBytes);
+        __syncwarp();
+        double *stage = smem + s * kStageElems;
+        if (lane < MEDGP_KC)
+            bulk_g2s(stage + lane * MEDGP_SLD, A + (size_t)(cc * MEDGP_KC + lane) * lda,
+                     MEDGP_NB * 8, &bars->full[s]);
+        else
+            bulk_g2s(stage + kPanelElems + (lane - MEDGP_KC) * MEDGP_SLD,
+                     B + (size_t)(cc * MEDGP_KC + lane - MEDGP_KC) * ldb, MEDGP_NB * 8,
+                     &bars->full[s]);
+    };
+
+    if (warp == 0)
+        for (int ch = 0; ch < MEDGP_NSTAGE - 1 && ch < nch; ch++) issue(ch);
+
+    for (int ch = 0; ch < nch; ch++) {
+        const int s = ch % MEDGP_NSTAGE;
+        if (warp == 0) {
+            const int nxt = ch + MEDGP_NSTAGE - 1;
+            if (nxt < nch) {
+                if (nxt >= MEDGP_NSTAGE)
+                    mbar_wait(&bars->empty[nxt % MEDGP_NSTAGE], ((nxt / MEDGP_NSTAGE) - 1) & 1);
+                issue(nxt);
+            }
+        }
+        mbar_wait(&bars->full[s], (ch / MEDGP_NSTAGE) & 1);
+        const double *stage = smem + s * kStageElems;
+        mma_panels(acc, stage, stage + kPanelElems, MEDGP_KC / 4, wm, wn, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->empty[s]);
+    }
+}
+
+// write the accumulator tile (times sign) into a pitch-SLD column-major shared tile
+__device__ __forceinline__ void acc_to_smem(const double (&acc)[4][4][2], double *sT, double sign)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp & 1, wn = warp >> 1, r = lane >> 2, kq = lane & 3;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int row = wm * 32 + 8 * a + r, col = wn * 32 + 8 * b + 2 * kq;
+            sT[col * MEDGP_SLD + row] = sign * acc[a][b][0];
+            sT[(col + 1) * MEDGP_SLD + row] = sign * acc[a][b][1];
+        }
+}
+
+// acc = base - acc, base a column-major HBM tile
+__device__ __forceinline__ void acc_rsub_global(double (&acc)[4][4][2], const double *G, int ldg)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp & 1, wn = warp >> 1, r = lane >> 2, kq = lane & 3;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int row = wm * 32 + 8 * a + r, col = wn * 32 + 8 * b + 2 * kq;
+            acc[a][b][0] = G[(size_t)col * ldg + row] - acc[a][b][0];
+            acc[a][b][1] = G[(size_t)(col + 1) * ldg + row] - acc[a][b][1];
+        }
+}
+
+__device__ __forceinline__ void acc_to_global(const double (&acc)[4][4][2], double *G, int ldg)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp & 1, wn = warp >> 1, r = lane >> 2, kq = lane & 3;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int row = wm * 32 + 8 * a + r, col = wn * 32 + 8 * b + 2 * kq;
+            G[(size_t)col * ldg + row] = acc[a][b][0];
+            G[(size_t)(col + 1) * ldg + row] = acc[a][b][1];
+        }
+}
+
+// copy a dense 64x64 column-major HBM tile (ld = ldg) into a pitch-SLD shared tile
+__device__ __forceinline__ void tile_g2s_plain(double *sT, const double *G, int ldg)
+{
+    for (int idx = threadIdx.x; idx < MEDGP_NB * MEDGP_NB / 2; idx += blockDim.x) {
+        const int c = idx >> 5, r2 = (idx & 31) * 2;
+        const double2 v = *reinterpret_cast<const double2 *>(G + (size_t)c * ldg + r2);
+        *reinterpret_cast<double2 *>(sT + c * MEDGP_SLD + r2) = v;
+    }
+}
+
+// block-wide sum of `NV` doubles per thread; result valid in thread 0.  scratch: NV*32 doubles.
+template <int NV>
+__device__ __forceinline__ void block_reduce_sum(double (&v)[NV], double *scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        v[i] = x;
+    }
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < NV; i++) scratch[i * 32 + warp] = v[i];
+    __syncthreads();
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            double s = 0.0;
+            for (int w = 0; w < nwarp; w++) s += scratch[i * 32 + w];
+            v[i] = s;
+        }
+    __syncthreads();
+}

@@ -1,0 +1,315 @@
+// cov.cuh -- kernels (1), (3), (4) of the hot path: SM-LMC covariance assembly, the fused
+// gradient reduction and the test-time cross-covariance / predictive moments.
+//
+//   k_q(tau)  = cos(2 PI mu_q tau) exp(-2 (PI v_q)^2 tau^2)        kernel/c_kernel_LMC_SM.cpp:374-378
+//   K_ij      = sum_q B_q[f_i,f_j] k_q(t_i - t_j) + delta_ij sigma^2_{f_i}
+//                                                  kernel/c_kernel_LMC_SM.cpp:152-196,
+//                                                  inference/c_inference_exact.cpp:88-92
+// cos(w(t_i - t_j)) is formed from per-point tables (cos, sin)(w_q t_i) by angle addition, so
+// each pair costs one exp per mixture component and no trig.
+#pragma once
+#include "common.cuh"
+#include "linalg.cuh"
+
+// ------------------------------------------------------------------ parameters + trig tables
+// theta -> sigma^2, w_q = 2 PI mu_q, c_q = 2 (PI v_q)^2, A, kappa, B_q = A_q A_q^T + diag(kappa_q)
+// (likelihoods/c_likelihood.cpp:38-43, kernel/c_kernel_LMC_SM.cpp:51-62,72-115), then the
+// per-point (cos, sin)(w_q t_i) tables.
+__global__ void __launch_bounds__(256)
+k_prep(const EvalDesc *__restrict__ descs, ModelDims md, const double *__restrict__ thetas)
+{
+    const EvalDesc &e = descs[blockIdx.x];
+    const int Q = md.Q, D = md.D, R = md.R, tid = threadIdx.x;
+    const double *th = thetas + (size_t)e.out_index * md.P;
+    const double *cov = th + D;
+    double *par = e.par;
+    for (int d = tid; d < D; d += blockDim.x) {
+        const double s = exp(th[d]);
+        par[md.oSig2 + d] = s * s;
+    }
+    for (int i = tid; i < Q * D * R; i += blockDim.x) par[md.oA + i] = cov[i];
+    for (int q = tid; q < Q; q += blockDim.x) {
+        const double mu = exp(cov[Q * D * R + q]);
+        const double v = exp(cov[Q * (D * R + 1) + q]);
+        par[md.oW + q] = 2.0 * md.pi * mu;
+        par[md.oC + q] = 2.0 * (md.pi * v) * (md.pi * v);
+    }
+    for (int i = tid; i < Q * D; i += blockDim.x)
+        par[md.oKappa + i] = exp(cov[Q * (D * R + 2) + i]);
+    __syncthreads();
+    for (int idx = tid; idx < Q * D * D; idx += blockDim.x) {
+        const int q = idx / (D * D), rem = idx - q * D * D, i = rem / D, j = rem - i * D;
+        double s = 0.0;
+        for (int r = 0; r < R; r++) s += par[md.oA + q * D * R + i * R + r] * par[md.oA + q * D * R + j * R + r];
+        if (i == j) s += par[md.oKappa + q * D + i];
+        par[md.oB + idx] = s;
+    }
+    __syncthreads();
+    for (int d = tid; d < D; d += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < Q; q++) s += par[md.oB + (q * D + d) * D + d];
+        par[md.oBdiag + d] = s;  // prior variance of feature d (kernel/c_kernel_LMC_SM.cpp:137-144)
+    }
+    const int npad = e.npad;
+    for (int idx = tid; idx < Q * npad; idx += blockDim.x) {
+        const int q = idx / npad, i = idx - q * npad;
+        double sn = 0.0, cs = 1.0;
+        if (i < e.n) sincos(par[md.oW + q] * e.t[i], &sn, &cs);
+        reinterpret_cast<double2 *>(e.cs)[idx] = make_double2(cs, sn);
+    }
+}
+
+// ------------------------------------------------------------------ kernel (1): assembly
+// grid (lower tiles, evaluations), 256 threads, one 64x64 tile of K + noise per CTA, written
+// column-major (lanes along rows: coalesced 512 B column segments).  Rows/cols >= n are the
+// identity.  dynamic smem: B (Q*D*D) + c (Q) doubles.
+__global__ void __launch_bounds__(256)
+k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double s_tr[MEDGP_NB], s_tc[MEDGP_NB];
+    __shared__ int s_mr[MEDGP_NB], s_mc[MEDGP_NB];
+    __shared__ double2 s_csr[MEDGP_QMAX][MEDGP_NB], s_csc[MEDGP_QMAX][MEDGP_NB];
+    const EvalDesc &e = descs[blockIdx.y];
+    int ti, tj;
+    tri_index(blockIdx.x, ti, tj);
+    if (ti >= e.T) return;
+    const int Q = md.Q, D = md.D, tid = threadIdx.x, n = e.n, ld = e.npad;
+    double *sB = sm, *sC = sm + Q * D * D;
+    for (int i = tid; i < Q * D * D; i += blockDim.x) sB[i] = e.par[md.oB + i];
+    if (tid < Q) sC[tid] = e.par[md.oC + tid];
+    if (tid < MEDGP_NB) {
+        const int gi = ti * MEDGP_NB + tid;
+        s_tr[tid] = gi < n ? e.t[gi] : 0.0;
+        s_mr[tid] = gi < n ? e.meta[gi] : 0;
+    } else if (tid < 2 * MEDGP_NB) {
+        const int u = tid - MEDGP_NB, gj = tj * MEDGP_NB + u;
+        s_tc[u] = gj < n ? e.t[gj] : 0.0;
+        s_mc[u] = gj < n ? e.meta[gj] : 0;
+    }
+    const double2 *cs = reinterpret_cast<const double2 *>(e.cs);
+    for (int idx = tid; idx < Q * MEDGP_NB; idx += blockDim.x) {
+        const int q = idx >> 6, u = idx & 63;
+        s_csr[q][u] = cs[(size_t)q * ld + ti * MEDGP_NB + u];
+        s_csc[q][u] = cs[(size_t)q * ld + tj * MEDGP_NB + u];
+    }
+    __syncthreads();
+    const int r = tid & 63, g = tid >> 6;
+    const int gi = ti * MEDGP_NB + r;
+    const double tr = s_tr[r];
+    const int mr = s_mr[r];
+    const double jit = 1.0 + (double)e.jitter;
+    double *out = e.M + (size_t)(tj * MEDGP_NB) * ld + gi;
+#pragma unroll 2
+    for (int u = 0; u < 16; u++) {
+        const int c = g * 16 + u, gj = tj * MEDGP_NB + c;
+        if (gj > gi) continue;  // strictly upper part of a diagonal tile: not needed
+        double val;
+        if (gi >= n || gj >= n) {
+            val = (gi == gj) ? 1.0 : 0.0;
+        } else {
+            const double tau = tr - s_tc[c], tau2 = tau * tau;
+            const int mc = s_mc[c];
+            val = 0.0;
+            for (int q = 0; q < Q; q++) {
+                const double2 a = s_csr[q][r], b = s_csc[q][c];
+                const double cosphi = a.x * b.x + a.y * b.y;
+                val += sB[(q * D + mr) * D + mc] * cosphi * exp(-sC[q] * tau2);
+            }
+            if (gi == gj) val += jit * e.par[md.oSig2 + mr];
+        }
+        out[(size_t)c * ld] = val;
+    }
+}
+
+// ------------------------------------------------------------------ kernel (3): fused gradient
+// g = 1/2 sum_ij W_ij dK_ij/dtheta over the FULL matrix, W = K^-1 - alpha alpha^T
+// (inference/c_inference_exact.cpp:168-172, kernel/c_kernel_LMC_SM.cpp:198-327), collapsed to
+// block sums per feature pair.  Points are feature-major inside the
+// library, so a work item is a rectangle rows [i0,i1) of feature d  x  all columns of feature
+// e <= d; every element of an item belongs to the same (d, e) and is reduced in registers:
+//   part[item] = [ sum W k_q (Q) | sum W km_q (Q) | sum W kv_q (Q) | sum_{i} W_ii ]
+// For d == e only j <= i is visited and off-diagonal elements count twice, so the sums are
+// those of the full square block.  K^-1 is read once (lower triangle), dK is never stored.
+__global__ void __launch_bounds__(128)
+k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
+{
+    __shared__ double scratch[(3 * MEDGP_QMAX + 1) * 32];
+    __shared__ double s_w[MEDGP_QMAX], s_c[MEDGP_QMAX];
+    const EvalDesc &e = descs[blockIdx.y];
+    if ((int)blockIdx.x >= e.nitems) return;
+    const int4 it = e.items[blockIdx.x];
+    const int Q = md.Q, tid = threadIdx.x, ld = e.npad;
+    if (tid < Q) {
+        s_w[tid] = e.par[md.oW + tid];
+        s_c[tid] = e.par[md.oC + tid];
+    }
+    __syncthreads();
+    const int d = it.x, f = it.y, i0 = it.z, nr = it.w - it.z;
+    const int j0 = e.off[f], nc = e.off[f + 1] - j0;
+    const bool diagblk = (d == f);
+    const double2 *cs = reinterpret_cast<const double2 *>(e.cs);
+    double acc[3 * MEDGP_QMAX + 1];
+#pragma unroll
+    for (int u = 0; u < 3 * MEDGP_QMAX + 1; u++) acc[u] = 0.0;
+    const int total = nr * nc;
+    for (int idx = tid; idx < total; idx += blockDim.x) {
+        const int jj = idx / nr, ii = idx - jj * nr;
+        const int i = i0 + ii, j = j0 + jj;
+        if (diagblk && j > i) continue;
+        const double ai = e.alpha[i], aj = e.alpha[j];
+        double w = e.M[(size_t)j * ld + i] - ai * aj;
+        if (i == j) acc[3 * MEDGP_QMAX] += w;
+        else if (diagblk) w *= 2.0;
+        const double tau = e.t[i] - e.t[j], tau2 = tau * tau;
+#pragma unroll
+        for (int q = 0; q < MEDGP_QMAX; q++) {
+            if (q < Q) {
+                const double2 a = cs[(size_t)q * ld + i], b = cs[(size_t)q * ld + j];
+                const double cosphi = a.x * b.x + a.y * b.y;
+                const double sinphi = a.y * b.x - a.x * b.y;
+                const double ex = exp(-s_c[q] * tau2);
+                const double k = cosphi * ex;
+                const double phi = s_w[q] * tau;
+                acc[q] += w * k;
+                acc[MEDGP_QMAX + q] -= w * (phi * sinphi * ex);           // km: c_kernel_LMC_SM.cpp:379-384
+                acc[2 * MEDGP_QMAX + q] -= w * (2.0 * s_c[q] * tau2 * k); // kv: c_kernel_LMC_SM.cpp:385-391
+            }
+        }
+    }
+    block_reduce_sum<3 * MEDGP_QMAX + 1>(acc, scratch);
+    if (tid == 0) {
+        double *p = e.part + (size_t)blockIdx.x * (3 * Q + 1);
+        for (int q = 0; q < Q; q++) {
+            p[q] = acc[q];
+            p[Q + q] = acc[MEDGP_QMAX + q];
+            p[2 * Q + q] = acc[2 * MEDGP_QMAX + q];
+        }
+        p[3 * Q] = acc[3 * MEDGP_QMAX];
+    }
+}
+
+// Gradient epilogue, one CTA per evaluation (deterministic: fixed summation order):
+//   noise   g_d        = sigma_d^2 sum_{i in d} W_ii                inference/c_inference_exact.cpp:191-203
+//   A       g_A[q,d,r] = (S_q A_q)[d,r]                            kernel/c_kernel_LMC_SM.cpp:228-256
+//   mu, v   g          = 1/2 sum_{d,e} B_q[d,e] S{mu,v}_q[d,e]     :257-293
+//   kappa   g          = 1/2 kappa_q[d] S_q[d,d]                   :294-320
+// dynamic smem: S (Q*D*D) + gm, gv (npairs*Q each) + dg (D) doubles.
+__global__ void __launch_bounds__(256)
+k_grad_finish(const EvalDesc *__restrict__ descs, ModelDims md, double *__restrict__ out_grad,
+              const int *__restrict__ fail)
+{
+    extern __shared__ __align__(16) double sm[];
+    const EvalDesc &e = descs[blockIdx.x];
+    const int Q = md.Q, D = md.D, R = md.R, tid = threadIdx.x;
+    const int npairs = D * (D + 1) / 2, W = 3 * Q + 1;
+    double *S = sm, *gm = S + Q * D * D, *gv = gm + npairs * Q, *dg = gv + npairs * Q;
+    const double *par = e.par;
+    for (int idx = tid; idx < npairs * Q; idx += blockDim.x) {
+        const int p = idx / Q, q = idx - p * Q;
+        int d, f;
+        tri_index(p, d, f);
+        double sk = 0.0, smu = 0.0, sv = 0.0;
+        for (int itx = e.pair_start[p]; itx < e.pair_start[p + 1]; itx++) {
+            const double *row = e.part + (size_t)itx * W;
+            sk += row[q];
+            smu += row[Q + q];
+            sv += row[2 * Q + q];
+        }
+        S[(q * D + d) * D + f] = sk;
+        S[(q * D + f) * D + d] = sk;
+        const double b = par[md.oB + (q * D + d) * D + f] * (d == f ? 1.0 : 2.0);
+        gm[idx] = b * smu;
+        gv[idx] = b * sv;
+    }
+    for (int d = tid; d < D; d += blockDim.x) {
+        const int p = d * (d + 1) / 2 + d;
+        double s = 0.0;
+        for (int itx = e.pair_start[p]; itx < e.pair_start[p + 1]; itx++)
+            s += e.part[(size_t)itx * W + 3 * Q];
+        dg[d] = s;
+    }
+    __syncthreads();
+    double *g = out_grad + (size_t)e.out_index * md.P;
+    const bool bad = fail[e.out_index] != 0;
+    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+    for (int d = tid; d < D; d += blockDim.x) g[d] = bad ? nanv : par[md.oSig2 + d] * dg[d];
+    double *gc = g + D;
+    for (int idx = tid; idx < Q * D * R; idx += blockDim.x) {
+        const int q = idx / (D * R), rem = idx - q * D * R, d = rem / R, r = rem - d * R;
+        double s = 0.0;
+        for (int f = 0; f < D; f++) s += S[(q * D + d) * D + f] * par[md.oA + q * D * R + f * R + r];
+        gc[idx] = bad ? nanv : s;
+    }
+    if (tid < 2 * Q) {
+        const int q = tid % Q;
+        const double *src = tid < Q ? gm : gv;
+        double s = 0.0;
+        for (int p = 0; p < npairs; p++) s += src[p * Q + q];
+        gc[Q * D * R + tid] = bad ? nanv : 0.5 * s;  // [mu (Q) | v (Q)]
+    }
+    for (int idx = tid; idx < Q * D; idx += blockDim.x) {
+        const int q = idx / D, d = idx - q * D;
+        gc[Q * (D * R + 2) + idx] = bad ? nanv : 0.5 * par[md.oKappa + idx] * S[(q * D + d) * D + d];
+    }
+}
+
+// ------------------------------------------------------------------ kernel (4): prediction
+// cross-covariance columns k*(X, x*) into rhs rows 1..nstar
+// (kernel/c_kernel_LMC_SM.cpp:329-372); pad rows are 0.
+__global__ void __launch_bounds__(256)
+k_cross(const EvalDesc *__restrict__ descs, ModelDims md)
+{
+    const EvalDesc &e = descs[blockIdx.y];
+    const int s = blockIdx.x;
+    if (s >= e.nstar) return;
+    const int Q = md.Q, D = md.D, ld = e.npad;
+    const double ts = e.star_t[s];
+    const int ms = e.star_meta[s];
+    const double2 *cs = reinterpret_cast<const double2 *>(e.cs);
+    double *out = e.rhs + (size_t)(1 + s) * ld;
+    __shared__ double s_cs[MEDGP_QMAX], s_sn[MEDGP_QMAX];
+    if (threadIdx.x < Q) sincos(e.par[md.oW + threadIdx.x] * ts, &s_sn[threadIdx.x], &s_cs[threadIdx.x]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+        double val = 0.0;
+        if (i < e.n) {
+            const double tau = e.t[i] - ts, tau2 = tau * tau;
+            const int mi = e.meta[i];
+            for (int q = 0; q < Q; q++) {
+                const double2 a = cs[(size_t)q * ld + i];
+                const double cosphi = a.x * s_cs[q] + a.y * s_sn[q];
+                val += e.par[md.oB + (q * D + mi) * D + ms] * cosphi * exp(-e.par[md.oC + q] * tau2);
+            }
+        }
+        out[i] = val;
+    }
+}
+
+// mean = (L^-1 k*)^T (L^-1 y) = k*^T alpha ; var = sum_q B_q[f*,f*] - |L^-1 k*|^2 + sigma^2_{f*}
+// (core/gp_regression.cpp:180-196)
+__global__ void __launch_bounds__(256)
+k_pred_finish(const EvalDesc *__restrict__ descs, ModelDims md, double *__restrict__ out_mean,
+              double *__restrict__ out_var, const int *__restrict__ fail)
+{
+    __shared__ double scratch[64];
+    const EvalDesc &e = descs[blockIdx.y];
+    const int s = blockIdx.x;
+    if (s >= e.nstar) return;
+    const int ld = e.npad;
+    const double *z = e.rhs, *v = e.rhs + (size_t)(1 + s) * ld;
+    double acc[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+        const double vi = v[i];
+        acc[0] += vi * z[i];
+        acc[1] += vi * vi;
+    }
+    block_reduce_sum<2>(acc, scratch);
+    if (threadIdx.x == 0) {
+        const int ms = e.star_meta[s];
+        const bool bad = fail[e.out_index] != 0;
+        const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+        out_mean[e.star_out + s] = bad ? nanv : acc[0];
+        out_var[e.star_out + s] = bad ? nanv : e.par[md.oBdiag + ms] - acc[1] + e.par[md.oSig2 + ms];
+    }
+}

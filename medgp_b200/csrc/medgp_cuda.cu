@@ -1,0 +1,834 @@
+// medgp_cuda.cu -- C ABI (include/medgp_cuda.h) and host orchestration of libmedgp_cuda.so.
+//
+// One context = one GPU + one stream + one workspace arena.  A call receives a batch of
+// evaluations (series id, theta); they are sorted by padded size, cut into chunks that fit
+// the arena, and each chunk runs the stage sequence
+//   prep -> assemble -> potrf (diag + panel per block column) -> [cross] -> solve
+//        -> [trtri rows -> alpha -> lauum -> grad -> grad_finish]      (want_grad)
+//        -> [pred_finish]                                              (prediction)
+// with grid.y (or grid.x) indexing the evaluations of the chunk.  No CPU fallback exists:
+// without a device medgp_cuda_create fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/medgp_cuda.h"
+#include "common.cuh"
+#include "cov.cuh"
+#include "linalg.cuh"
+
+#define MEDGP_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+constexpr int kGradRows = 128;  // rows per gradient work item
+constexpr int kMaxJitter = 10;  // inference/c_inference_exact.cpp:99
+
+struct Series {
+    bool alive = false;
+    int n = 0, npad = 0, T = 0, nitems = 0;
+    double *d_t = nullptr, *d_y = nullptr;
+    int *d_meta = nullptr, *d_off = nullptr, *d_pair_start = nullptr;
+    int4 *d_items = nullptr;
+    std::vector<int> perm;  // internal position -> caller position
+};
+
+struct Request {
+    int series, out_index, jitter, nstar, star_off;
+};
+
+struct StageMark {
+    int stage;
+    cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct medgp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool model_set = false;
+    ModelDims md{};
+    char *arena = nullptr;
+    size_t arena_bytes = 0;
+    std::vector<Series> series;
+    std::string err;
+    // staging owned by the context (grown on demand)
+    EvalDesc *h_descs = nullptr, *d_descs = nullptr;
+    size_t desc_cap = 0;
+    double *h_theta = nullptr, *d_theta = nullptr, *h_out = nullptr, *d_out = nullptr;
+    size_t theta_cap = 0, out_cap = 0;
+    int *h_status = nullptr, *d_status = nullptr, *d_fail = nullptr;
+    size_t status_cap = 0, fail_cap = 0;
+    double *d_star_t = nullptr;
+    int *d_star_meta = nullptr;
+    size_t star_cap = 0;
+    // profiling
+    bool profile = false;
+    std::vector<StageMark> marks;
+    std::vector<cudaEvent_t> event_pool;
+    medgp_stage_times times{};
+};
+
+namespace {
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e);                    \
+            return MEDGP_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void fill_dims(ModelDims &md, int Q, int D, int R, double pi)
+{
+    md.Q = Q; md.D = D; md.R = R; md.pi = pi;
+    md.P = D + Q * (D * R + 2 + D);
+    int o = 0;
+    md.oB = o; o += Q * D * D;
+    md.oSig2 = o; o += D;
+    md.oW = o; o += Q;
+    md.oC = o; o += Q;
+    md.oA = o; o += Q * D * R;
+    md.oKappa = o; o += Q * D;
+    md.oBdiag = o; o += D;
+    md.parLen = (o + 1) & ~1;
+}
+
+// bytes of arena one evaluation needs
+size_t eval_bytes(const ModelDims &md, const Series &s, int nrhs, bool grad)
+{
+    const size_t np = s.npad;
+    size_t b = 0;
+    b += align_up(np * np * 8, 256);                       // M
+    b += 2 * align_up(np * MEDGP_NB * 8, 256);             // dinv, dinvT
+    b += align_up(np * (size_t)nrhs * 8, 256);             // rhs
+    b += align_up(np * 8, 256);                            // alpha
+    b += align_up(np * (size_t)md.Q * 16, 256);            // cs
+    b += align_up((size_t)md.parLen * 8, 256);             // par
+    b += align_up((size_t)s.T * 8, 256);                   // blk
+    if (grad) b += align_up((size_t)s.nitems * (3 * md.Q + 1) * 8, 256);
+    return b;
+}
+
+int ensure_staging(medgp_ctx *ctx, size_t nreq, size_t nstar)
+{
+    const size_t P = ctx->md.P;
+    if (nreq > ctx->desc_cap) {
+        if (ctx->h_descs) cudaFreeHost(ctx->h_descs);
+        if (ctx->d_descs) cudaFree(ctx->d_descs);
+        ctx->desc_cap = std::max(nreq, 2 * ctx->desc_cap);
+        CU(cudaMallocHost(&ctx->h_descs, ctx->desc_cap * sizeof(EvalDesc)));
+        CU(cudaMalloc(&ctx->d_descs, ctx->desc_cap * sizeof(EvalDesc)));
+    }
+    if (nreq * P > ctx->theta_cap) {
+        if (ctx->h_theta) cudaFreeHost(ctx->h_theta);
+        if (ctx->d_theta) cudaFree(ctx->d_theta);
+        ctx->theta_cap = std::max(nreq * P, 2 * ctx->theta_cap);
+        CU(cudaMallocHost(&ctx->h_theta, ctx->theta_cap * 8));
+        CU(cudaMalloc(&ctx->d_theta, ctx->theta_cap * 8));
+    }
+    // results: nlml (nreq) + grad (nreq*P) + mean/var (2*nstar)
+    const size_t need_out = nreq * (P + 1) + 2 * nstar;
+    if (need_out > ctx->out_cap) {
+        if (ctx->h_out) cudaFreeHost(ctx->h_out);
+        if (ctx->d_out) cudaFree(ctx->d_out);
+        ctx->out_cap = std::max(need_out, 2 * ctx->out_cap);
+        CU(cudaMallocHost(&ctx->h_out, ctx->out_cap * 8));
+        CU(cudaMalloc(&ctx->d_out, ctx->out_cap * 8));
+    }
+    if (nreq > ctx->status_cap) {
+        if (ctx->h_status) cudaFreeHost(ctx->h_status);
+        if (ctx->d_status) cudaFree(ctx->d_status);
+        ctx->status_cap = std::max(nreq, 2 * ctx->status_cap);
+        CU(cudaMallocHost(&ctx->h_status, ctx->status_cap * sizeof(int)));
+        CU(cudaMalloc(&ctx->d_status, ctx->status_cap * sizeof(int)));
+    }
+    if (nreq > ctx->fail_cap) {
+        if (ctx->d_fail) cudaFree(ctx->d_fail);
+        ctx->fail_cap = std::max(nreq, 2 * ctx->fail_cap);
+        CU(cudaMalloc(&ctx->d_fail, ctx->fail_cap * sizeof(int)));
+    }
+    if (nstar > ctx->star_cap) {
+        if (ctx->d_star_t) cudaFree(ctx->d_star_t);
+        if (ctx->d_star_meta) cudaFree(ctx->d_star_meta);
+        ctx->star_cap = std::max(nstar, 2 * ctx->star_cap);
+        CU(cudaMalloc(&ctx->d_star_t, ctx->star_cap * 8));
+        CU(cudaMalloc(&ctx->d_star_meta, ctx->star_cap * sizeof(int)));
+    }
+    return MEDGP_OK;
+}
+
+cudaEvent_t get_event(medgp_ctx *ctx)
+{
+    if (!ctx->event_pool.empty()) {
+        cudaEvent_t e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct StageScope {
+    medgp_ctx *ctx;
+    int stage;
+    cudaEvent_t a = nullptr;
+    StageScope(medgp_ctx *c, int s) : ctx(c), stage(s)
+    {
+        if (ctx->profile) {
+            a = get_event(ctx);
+            cudaEventRecord(a, ctx->stream);
+        }
+    }
+    ~StageScope()
+    {
+        if (ctx->profile) {
+            cudaEvent_t b = get_event(ctx);
+            cudaEventRecord(b, ctx->stream);
+            ctx->marks.push_back({stage, a, b});
+        }
+    }
+};
+
+void resolve_marks(medgp_ctx *ctx)
+{
+    for (auto &m : ctx->marks) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, m.a, m.b) == cudaSuccess) ctx->times.ms[m.stage] += ms;
+        ctx->event_pool.push_back(m.a);
+        ctx->event_pool.push_back(m.b);
+    }
+    ctx->marks.clear();
+}
+
+// The core: run `reqs` (any sizes) through the stage sequence.  d_theta is indexed by
+// out_index.  mode: 0 = NLML only, 1 = NLML + gradient, 2 = prediction.
+int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, int mode,
+              double *d_nlml, double *d_grad, int *d_status, double *d_mean, double *d_var,
+              size_t desc_base)
+{
+    const ModelDims &md = ctx->md;
+    cudaStream_t st = ctx->stream;
+    const bool grad = (mode == 1), pred = (mode == 2);
+    std::stable_sort(reqs.begin(), reqs.end(), [&](const Request &a, const Request &b) {
+        return ctx->series[a.series].npad > ctx->series[b.series].npad;
+    });
+    const int gemm_smem = kGemmSmemBytes;
+    const int asm_smem = (md.Q * md.D * md.D + md.Q) * 8;
+    const int npairs = md.D * (md.D + 1) / 2;
+    const int fin_smem = (md.Q * md.D * md.D + 2 * npairs * md.Q + md.D) * 8;
+
+    size_t pos = 0, dpos = desc_base;
+    while (pos < reqs.size()) {
+        // ---- form a chunk
+        size_t used = 0, cnt = 0;
+        const size_t first = pos;
+        while (pos < reqs.size() && cnt < 65535) {
+            const Series &s = ctx->series[reqs[pos].series];
+            const size_t b = eval_bytes(md, s, 1 + reqs[pos].nstar, grad);
+            if (used + b > ctx->arena_bytes) break;
+            used += b;
+            pos++;
+            cnt++;
+        }
+        if (cnt == 0) {
+            ctx->err = "workspace too small for one evaluation";
+            return MEDGP_ERR_NOMEM;
+        }
+        // ---- carve the arena and fill descriptors
+        char *p = ctx->arena;
+        auto take = [&](size_t bytes) {
+            char *r = p;
+            p += align_up(bytes, 256);
+            return r;
+        };
+        int Tmax = 0, items_max = 0, nstar_max = 0;
+        for (size_t c = 0; c < cnt; c++) {
+            const Request &rq = reqs[first + c];
+            const Series &s = ctx->series[rq.series];
+            EvalDesc &e = ctx->h_descs[dpos + c];
+            const size_t np = s.npad;
+            e.M = (double *)take(np * np * 8);
+            e.dinv = (double *)take(np * MEDGP_NB * 8);
+            e.dinvT = (double *)take(np * MEDGP_NB * 8);
+            e.rhs = (double *)take(np * (size_t)(1 + rq.nstar) * 8);
+            e.alpha = (double *)take(np * 8);
+            e.cs = (double *)take(np * (size_t)md.Q * 16);
+            e.par = (double *)take((size_t)md.parLen * 8);
+            e.blk = (double *)take((size_t)s.T * 8);
+            e.part = grad ? (double *)take((size_t)s.nitems * (3 * md.Q + 1) * 8) : nullptr;
+            e.t = s.d_t; e.y = s.d_y; e.meta = s.d_meta; e.off = s.d_off;
+            e.items = s.d_items; e.pair_start = s.d_pair_start;
+            e.star_t = pred ? ctx->d_star_t + rq.star_off : nullptr;
+            e.star_meta = pred ? ctx->d_star_meta + rq.star_off : nullptr;
+            e.n = s.n; e.npad = s.npad; e.T = s.T; e.nitems = s.nitems;
+            e.jitter = rq.jitter; e.nrhs = 1 + rq.nstar; e.nstar = rq.nstar;
+            e.out_index = rq.out_index; e.star_out = rq.star_off;
+            e.pad0 = e.pad1 = e.pad2 = 0;
+            Tmax = std::max(Tmax, s.T);
+            items_max = std::max(items_max, s.nitems);
+            nstar_max = std::max(nstar_max, rq.nstar);
+            // algorithmic work
+            const double n = s.n;
+            ctx->times.flops[MEDGP_STAGE_POTRF] += n * n * n / 3.0;
+            ctx->times.flops[MEDGP_STAGE_SOLVE] += n * n * (1 + rq.nstar);
+            ctx->times.bytes[MEDGP_STAGE_ASSEMBLE] += 8.0 * n * (n + 1) / 2 + 12.0 * n;
+            if (grad) {
+                ctx->times.flops[MEDGP_STAGE_TRTRI] += n * n * n / 3.0;
+                ctx->times.flops[MEDGP_STAGE_LAUUM] += n * n * n / 3.0;
+                ctx->times.bytes[MEDGP_STAGE_GRAD] += 8.0 * n * (n + 1) / 2 + 8.0 * md.P;
+            }
+            if (pred) ctx->times.bytes[MEDGP_STAGE_PREDICT] += rq.nstar * (8.0 * n * (n + 1) / 2 + 8.0 * n);
+            ctx->times.evals++;
+        }
+        const EvalDesc *dd = ctx->d_descs + dpos;
+        CU(cudaMemcpyAsync(ctx->d_descs + dpos, ctx->h_descs + dpos, cnt * sizeof(EvalDesc),
+                           cudaMemcpyHostToDevice, st));
+        // evaluations are sorted by T descending: the first act(k) of them have T > k
+        auto act = [&](int k) {
+            size_t lo = 0, hi = cnt;
+            while (lo < hi) {
+                const size_t mid = (lo + hi) / 2;
+                if (ctx->series[reqs[first + mid].series].T > k) lo = mid + 1; else hi = mid;
+            }
+            return (unsigned)lo;
+        };
+        const unsigned ncta = (unsigned)cnt;
+        const int ntri = Tmax * (Tmax + 1) / 2;
+        {
+            StageScope sc(ctx, MEDGP_STAGE_PREP);
+            k_prep<<<ncta, 256, 0, st>>>(dd, md, d_theta);
+            ctx->times.launches[MEDGP_STAGE_PREP]++;
+        }
+        {
+            StageScope sc(ctx, MEDGP_STAGE_ASSEMBLE);
+            k_assemble<<<dim3(ntri, ncta), 256, asm_smem, st>>>(dd, md);
+            ctx->times.launches[MEDGP_STAGE_ASSEMBLE]++;
+        }
+        {
+            StageScope sc(ctx, MEDGP_STAGE_POTRF);
+            for (int k = 0; k < Tmax; k++) {
+                k_potrf_diag<<<act(k), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, ctx->d_fail);
+                ctx->times.launches[MEDGP_STAGE_POTRF]++;
+                if (k + 1 < Tmax) {
+                    k_potrf_panel<<<dim3(Tmax - k - 1, act(k + 1)), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k);
+                    ctx->times.launches[MEDGP_STAGE_POTRF]++;
+                }
+            }
+        }
+        if (pred && nstar_max > 0) {
+            StageScope sc(ctx, MEDGP_STAGE_PREDICT);
+            k_cross<<<dim3(nstar_max, ncta), 256, 0, st>>>(dd, md);
+            ctx->times.launches[MEDGP_STAGE_PREDICT]++;
+        }
+        {
+            StageScope sc(ctx, MEDGP_STAGE_SOLVE);
+            k_solve<<<ncta, 256, 0, st>>>(dd, md, d_nlml, d_status, ctx->d_fail);
+            ctx->times.launches[MEDGP_STAGE_SOLVE]++;
+        }
+        if (grad) {
+            {
+                StageScope sc(ctx, MEDGP_STAGE_TRTRI);
+                for (int i = 1; i < Tmax; i++) {
+                    k_trtri_row<<<dim3(i, act(i)), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, i);
+                    ctx->times.launches[MEDGP_STAGE_TRTRI]++;
+                }
+                k_alpha<<<dim3(Tmax, ncta), 256, 0, st>>>(dd);
+                ctx->times.launches[MEDGP_STAGE_TRTRI]++;
+            }
+            {
+                StageScope sc(ctx, MEDGP_STAGE_LAUUM);
+                k_lauum<<<dim3(ntri, ncta), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd);
+                ctx->times.launches[MEDGP_STAGE_LAUUM]++;
+            }
+            {
+                StageScope sc(ctx, MEDGP_STAGE_GRAD);
+                k_grad<<<dim3(items_max, ncta), 128, 0, st>>>(dd, md);
+                k_grad_finish<<<ncta, 256, fin_smem, st>>>(dd, md, d_grad, ctx->d_fail);
+                ctx->times.launches[MEDGP_STAGE_GRAD] += 2;
+            }
+        }
+        if (pred && nstar_max > 0) {
+            StageScope sc(ctx, MEDGP_STAGE_PREDICT);
+            k_pred_finish<<<dim3(nstar_max, ncta), 256, 0, st>>>(dd, md, d_mean, d_var, ctx->d_fail);
+            ctx->times.launches[MEDGP_STAGE_PREDICT]++;
+        }
+        CU(cudaGetLastError());
+        dpos += cnt;
+    }
+    return MEDGP_OK;
+}
+
+int check_series_ids(medgp_ctx *ctx, int batch, const int *series_id)
+{
+    for (int b = 0; b < batch; b++) {
+        const int s = series_id[b];
+        if (s < 0 || s >= (int)ctx->series.size() || !ctx->series[s].alive) {
+            ctx->err = "unknown series id";
+            return MEDGP_ERR_ARG;
+        }
+    }
+    return MEDGP_OK;
+}
+
+void free_series_mem(Series &s)
+{
+    cudaFree(s.d_t); cudaFree(s.d_y); cudaFree(s.d_meta); cudaFree(s.d_off);
+    cudaFree(s.d_items); cudaFree(s.d_pair_start);
+    s = Series();
+}
+
+}  // namespace
+
+// ======================================================================================= API
+
+MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_bytes)
+{
+    if (!out) return MEDGP_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
+        return MEDGP_ERR_NODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+        return MEDGP_ERR_NODEVICE;  // the fatbin holds sm_100a code only
+    medgp_ctx *ctx = new medgp_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return MEDGP_ERR_CUDA;
+    }
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (workspace_bytes == 0)
+        workspace_bytes = std::min<size_t>((size_t)(0.7 * (double)free_b), (size_t)64 << 30);
+    if (cudaMalloc(&ctx->arena, workspace_bytes) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return MEDGP_ERR_NOMEM;
+    }
+    ctx->arena_bytes = workspace_bytes;
+    cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    cudaFuncSetAttribute(k_potrf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    cudaFuncSetAttribute(k_trtri_row, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    cudaFuncSetAttribute(k_lauum, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    *out = ctx;
+    return MEDGP_OK;
+}
+
+MEDGP_API void medgp_cuda_destroy(medgp_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &s : ctx->series)
+        if (s.alive) free_series_mem(s);
+    resolve_marks(ctx);
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    cudaFree(ctx->arena);
+    cudaFreeHost(ctx->h_descs); cudaFree(ctx->d_descs);
+    cudaFreeHost(ctx->h_theta); cudaFree(ctx->d_theta);
+    cudaFreeHost(ctx->h_out); cudaFree(ctx->d_out);
+    cudaFreeHost(ctx->h_status); cudaFree(ctx->d_status); cudaFree(ctx->d_fail);
+    cudaFree(ctx->d_star_t); cudaFree(ctx->d_star_meta);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+MEDGP_API const char *medgp_cuda_last_error(const medgp_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : "null context";
+}
+
+MEDGP_API int medgp_cuda_model(medgp_ctx *ctx, int Q, int D, int R, double pi_const)
+{
+    if (!ctx) return MEDGP_ERR_ARG;
+    if (Q < 1 || Q > MEDGP_QMAX || D < 1 || R < 1 || Q * D * D > 8192 || !(pi_const > 0)) {
+        ctx->err = "model shape out of range (1<=Q<=8, Q*D*D<=8192)";
+        return MEDGP_ERR_ARG;
+    }
+    for (auto &s : ctx->series)
+        if (s.alive) {
+            ctx->err = "clear the series before changing the model";
+            return MEDGP_ERR_ARG;
+        }
+    cudaSetDevice(ctx->device);
+    fill_dims(ctx->md, Q, D, R, pi_const);
+    const int asm_smem = (Q * D * D + Q) * 8;
+    const int npairs = D * (D + 1) / 2;
+    const int fin_smem = (Q * D * D + 2 * npairs * Q + D) * 8;
+    CU(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(asm_smem, 1024)));
+    CU(cudaFuncSetAttribute(k_grad_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(fin_smem, 1024)));
+    ctx->model_set = true;
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_num_hyp(const medgp_ctx *ctx)
+{
+    return (ctx && ctx->model_set) ? ctx->md.P : (int)MEDGP_ERR_ARG;
+}
+
+MEDGP_API int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, const float *x,
+                                    const float *y, int *out_series_id)
+{
+    if (!ctx || !ctx->model_set || n < 1 || !meta || !x || !y || !out_series_id) {
+        if (ctx) ctx->err = "add_series: bad argument or model not set";
+        return MEDGP_ERR_ARG;
+    }
+    const int D = ctx->md.D;
+    for (int i = 0; i < n; i++)
+        if (meta[i] < 0 || meta[i] >= D) {
+            ctx->err = "add_series: meta out of range";
+            return MEDGP_ERR_ARG;
+        }
+    cudaSetDevice(ctx->device);
+    Series s;
+    s.alive = true;
+    s.n = n;
+    s.npad = (n + MEDGP_NB - 1) / MEDGP_NB * MEDGP_NB;
+    s.T = s.npad / MEDGP_NB;
+    // feature-major internal order (stable): results are order independent, and the gradient
+    // kernel's work items need every feature contiguous.
+    s.perm.resize(n);
+    std::iota(s.perm.begin(), s.perm.end(), 0);
+    std::stable_sort(s.perm.begin(), s.perm.end(), [&](int a, int b) { return meta[a] < meta[b]; });
+    std::vector<double> ht(s.npad, 0.0), hy(s.npad, 0.0);
+    std::vector<int> hm(s.npad, 0), off(D + 1, 0);
+    for (int i = 0; i < n; i++) {
+        const int src = s.perm[i];
+        ht[i] = (double)x[src];
+        hy[i] = (double)y[src];
+        hm[i] = meta[src];
+        off[meta[src] + 1]++;
+    }
+    for (int d = 0; d < D; d++) off[d + 1] += off[d];
+    std::vector<int4> items;
+    std::vector<int> pair_start(D * (D + 1) / 2 + 1, 0);
+    for (int d = 0; d < D; d++)
+        for (int f = 0; f <= d; f++) {
+            const int p = d * (d + 1) / 2 + f;
+            pair_start[p] = (int)items.size();
+            if (off[f + 1] > off[f])
+                for (int i0 = off[d]; i0 < off[d + 1]; i0 += kGradRows)
+                    items.push_back(make_int4(d, f, i0, std::min(i0 + kGradRows, off[d + 1])));
+        }
+    pair_start.back() = (int)items.size();
+    s.nitems = (int)items.size();
+    CU(cudaMalloc(&s.d_t, s.npad * 8));
+    CU(cudaMalloc(&s.d_y, s.npad * 8));
+    CU(cudaMalloc(&s.d_meta, s.npad * sizeof(int)));
+    CU(cudaMalloc(&s.d_off, (D + 1) * sizeof(int)));
+    CU(cudaMalloc(&s.d_items, std::max<size_t>(1, items.size()) * sizeof(int4)));
+    CU(cudaMalloc(&s.d_pair_start, pair_start.size() * sizeof(int)));
+    CU(cudaMemcpy(s.d_t, ht.data(), s.npad * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s.d_y, hy.data(), s.npad * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s.d_meta, hm.data(), s.npad * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s.d_off, off.data(), (D + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    if (!items.empty())
+        CU(cudaMemcpy(s.d_items, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s.d_pair_start, pair_start.data(), pair_start.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // reuse a dead slot if there is one
+    int id = -1;
+    for (size_t i = 0; i < ctx->series.size(); i++)
+        if (!ctx->series[i].alive) { id = (int)i; break; }
+    if (id < 0) { id = (int)ctx->series.size(); ctx->series.emplace_back(); }
+    ctx->series[id] = std::move(s);
+    *out_series_id = id;
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_free_series(medgp_ctx *ctx, int series_id)
+{
+    if (!ctx || series_id < 0 || series_id >= (int)ctx->series.size() || !ctx->series[series_id].alive)
+        return MEDGP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_series_mem(ctx->series[series_id]);
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_clear_series(medgp_ctx *ctx)
+{
+    if (!ctx) return MEDGP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &s : ctx->series)
+        if (s.alive) free_series_mem(s);
+    ctx->series.clear();
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_sync(medgp_ctx *ctx)
+{
+    if (!ctx) return MEDGP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    resolve_marks(ctx);
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_nlml_grad_device(medgp_ctx *ctx, int batch, const int *series_id,
+                                          const double *d_theta, int want_grad, double *d_nlml,
+                                          double *d_grad, int *d_status)
+{
+    if (!ctx || !ctx->model_set || batch < 0 || !series_id || !d_theta || !d_nlml || !d_status ||
+        (want_grad && !d_grad)) {
+        if (ctx) ctx->err = "nlml_grad_device: bad argument";
+        return MEDGP_ERR_ARG;
+    }
+    if (batch == 0) return MEDGP_OK;
+    cudaSetDevice(ctx->device);
+    int rc = check_series_ids(ctx, batch, series_id);
+    if (rc) return rc;
+    // the descriptor staging buffer is reused: the previous call must have drained
+    CU(cudaStreamSynchronize(ctx->stream));
+    resolve_marks(ctx);
+    rc = ensure_staging(ctx, batch, 0);
+    if (rc) return rc;
+    std::vector<Request> reqs(batch);
+    for (int b = 0; b < batch; b++) reqs[b] = {series_id[b], b, 0, 0, 0};
+    CU(cudaMemsetAsync(ctx->d_fail, 0, batch * sizeof(int), ctx->stream));
+    return run_batch(ctx, std::move(reqs), d_theta, want_grad ? 1 : 0, d_nlml, d_grad, d_status,
+                     nullptr, nullptr, 0);
+}
+
+MEDGP_API int medgp_cuda_nlml_grad(medgp_ctx *ctx, int batch, const int *series_id,
+                                   const double *theta, int want_grad, double *nlml, double *grad,
+                                   int *status)
+{
+    if (!ctx || !ctx->model_set || batch < 0 || !series_id || !theta || !nlml || !status ||
+        (want_grad && !grad)) {
+        if (ctx) ctx->err = "nlml_grad: bad argument";
+        return MEDGP_ERR_ARG;
+    }
+    if (batch == 0) return MEDGP_OK;
+    cudaSetDevice(ctx->device);
+    int rc = check_series_ids(ctx, batch, series_id);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    rc = ensure_staging(ctx, batch, 0);
+    if (rc) return rc;
+    const size_t P = ctx->md.P;
+    cudaStream_t st = ctx->stream;
+    memcpy(ctx->h_theta, theta, (size_t)batch * P * 8);
+    CU(cudaMemcpyAsync(ctx->d_theta, ctx->h_theta, (size_t)batch * P * 8, cudaMemcpyHostToDevice, st));
+    double *d_nlml = ctx->d_out, *d_grad = ctx->d_out + batch;
+    std::vector<Request> reqs(batch);
+    for (int b = 0; b < batch; b++) reqs[b] = {series_id[b], b, 0, 0, 0};
+    for (int round = 0; round <= kMaxJitter && !reqs.empty(); round++) {
+        CU(cudaMemsetAsync(ctx->d_fail, 0, batch * sizeof(int), st));
+        rc = run_batch(ctx, reqs, ctx->d_theta, want_grad ? 1 : 0, d_nlml, d_grad, ctx->d_status,
+                       nullptr, nullptr, 0);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        resolve_marks(ctx);
+        // jitter: add sigma^2 to the diagonal again and refactor (c_inference_exact.cpp:99-108)
+        std::vector<Request> again;
+        for (auto &rq : reqs)
+            if (ctx->h_status[rq.out_index] < 0 && rq.jitter < kMaxJitter) {
+                Request r2 = rq;
+                r2.jitter++;
+                again.push_back(r2);
+            }
+        reqs.swap(again);
+    }
+    const size_t nout = want_grad ? (size_t)batch * (P + 1) : (size_t)batch;
+    CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, nout * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(nlml, ctx->h_out, (size_t)batch * 8);
+    if (want_grad) memcpy(grad, ctx->h_out + batch, (size_t)batch * P * 8);
+    memcpy(status, ctx->h_status, (size_t)batch * sizeof(int));
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_predict(medgp_ctx *ctx, int batch, const int *series_id,
+                                 const double *theta, const int *star_offset,
+                                 const int32_t *meta_star, const float *x_star, double *mean,
+                                 double *var, int *status)
+{
+    if (!ctx || !ctx->model_set || batch < 0 || !series_id || !theta || !star_offset ||
+        !meta_star || !x_star || !mean || !var || !status) {
+        if (ctx) ctx->err = "predict: bad argument";
+        return MEDGP_ERR_ARG;
+    }
+    if (batch == 0) return MEDGP_OK;
+    cudaSetDevice(ctx->device);
+    int rc = check_series_ids(ctx, batch, series_id);
+    if (rc) return rc;
+    const int nstar = star_offset[batch];
+    for (int b = 0; b < batch; b++)
+        if (star_offset[b + 1] < star_offset[b]) { ctx->err = "predict: star_offset not monotone"; return MEDGP_ERR_ARG; }
+    for (int i = 0; i < nstar; i++)
+        if (meta_star[i] < 0 || meta_star[i] >= ctx->md.D) { ctx->err = "predict: meta_star out of range"; return MEDGP_ERR_ARG; }
+    CU(cudaStreamSynchronize(ctx->stream));
+    rc = ensure_staging(ctx, batch, nstar);
+    if (rc) return rc;
+    const size_t P = ctx->md.P;
+    cudaStream_t st = ctx->stream;
+    memcpy(ctx->h_theta, theta, (size_t)batch * P * 8);
+    CU(cudaMemcpyAsync(ctx->d_theta, ctx->h_theta, (size_t)batch * P * 8, cudaMemcpyHostToDevice, st));
+    if (nstar > 0) {
+        std::vector<double> ts(nstar);
+        for (int i = 0; i < nstar; i++) ts[i] = (double)x_star[i];
+        CU(cudaMemcpyAsync(ctx->d_star_t, ts.data(), nstar * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_star_meta, meta_star, nstar * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));  // ts is a pageable temporary
+    }
+    double *d_nlml = ctx->d_out, *d_mean = ctx->d_out + batch, *d_var = d_mean + nstar;
+    std::vector<Request> reqs(batch);
+    for (int b = 0; b < batch; b++)
+        reqs[b] = {series_id[b], b, 0, star_offset[b + 1] - star_offset[b], star_offset[b]};
+    for (int round = 0; round <= kMaxJitter && !reqs.empty(); round++) {
+        CU(cudaMemsetAsync(ctx->d_fail, 0, batch * sizeof(int), st));
+        rc = run_batch(ctx, reqs, ctx->d_theta, 2, d_nlml, nullptr, ctx->d_status, d_mean, d_var, 0);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        resolve_marks(ctx);
+        std::vector<Request> again;
+        for (auto &rq : reqs)
+            if (ctx->h_status[rq.out_index] < 0 && rq.jitter < kMaxJitter) {
+                Request r2 = rq;
+                r2.jitter++;
+                again.push_back(r2);
+            }
+        reqs.swap(again);
+    }
+    CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, ((size_t)batch + 2 * (size_t)nstar) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(mean, ctx->h_out + batch, (size_t)nstar * 8);
+    memcpy(var, ctx->h_out + batch + nstar, (size_t)nstar * 8);
+    memcpy(status, ctx->h_status, (size_t)batch * sizeof(int));
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_debug_matrices(medgp_ctx *ctx, int series_id, const double *theta,
+                                        double *K, double *L, double *alpha, double *Kinv)
+{
+    if (!ctx || !ctx->model_set || !theta) return MEDGP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    int rc = check_series_ids(ctx, 1, &series_id);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    rc = ensure_staging(ctx, 1, 0);
+    if (rc) return rc;
+    const Series &s = ctx->series[series_id];
+    const ModelDims &md = ctx->md;
+    cudaStream_t st = ctx->stream;
+    const size_t np = s.npad, n = s.n;
+    CU(cudaMemcpyAsync(ctx->d_theta, theta, (size_t)md.P * 8, cudaMemcpyHostToDevice, st));
+    std::vector<double> hM(np * np), ha(np);
+    auto fetch = [&]() -> int {
+        // the single evaluation's M is the first arena allocation
+        CU(cudaMemcpyAsync(hM.data(), ctx->arena, np * np * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return MEDGP_OK;
+    };
+    std::vector<Request> one = {{series_id, 0, 0, 0, 0}};
+    if (K) {
+        // a full NLML pass sets up descriptors and parameters ...
+        rc = run_batch(ctx, one, ctx->d_theta, 0, ctx->d_out, nullptr, ctx->d_status, nullptr, nullptr, 0);
+        if (rc) return rc;
+        // ... then assembly alone is re-run into the same buffer (potrf overwrote it)
+        const int asm_smem = (md.Q * md.D * md.D + md.Q) * 8;
+        k_assemble<<<dim3(s.T * (s.T + 1) / 2, 1), 256, asm_smem, st>>>(ctx->d_descs, md);
+        if ((rc = fetch())) return rc;
+        for (size_t i = 0; i < n; i++)
+            for (size_t j = 0; j <= i; j++) {
+                const double v = hM[j * np + i];
+                K[(size_t)s.perm[i] * n + s.perm[j]] = v;
+                K[(size_t)s.perm[j] * n + s.perm[i]] = v;
+            }
+    }
+    if (L) {
+        CU(cudaMemsetAsync(ctx->d_fail, 0, sizeof(int), st));
+        rc = run_batch(ctx, one, ctx->d_theta, 0, ctx->d_out, nullptr, ctx->d_status, nullptr, nullptr, 0);
+        if (rc) return rc;
+        if ((rc = fetch())) return rc;
+        for (size_t i = 0; i < n; i++)
+            for (size_t j = 0; j < n; j++) L[i * n + j] = (j <= i) ? hM[j * np + i] : 0.0;
+    }
+    if (alpha || Kinv) {
+        CU(cudaMemsetAsync(ctx->d_fail, 0, sizeof(int), st));
+        rc = run_batch(ctx, one, ctx->d_theta, 1, ctx->d_out, ctx->d_out + 1, ctx->d_status, nullptr, nullptr, 0);
+        if (rc) return rc;
+        if ((rc = fetch())) return rc;
+        if (Kinv)
+            for (size_t i = 0; i < n; i++)
+                for (size_t j = 0; j <= i; j++) {
+                    const double v = hM[j * np + i];
+                    Kinv[(size_t)s.perm[i] * n + s.perm[j]] = v;
+                    Kinv[(size_t)s.perm[j] * n + s.perm[i]] = v;
+                }
+        if (alpha) {
+            CU(cudaMemcpy(ha.data(), ctx->h_descs[0].alpha, np * 8, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n; i++) alpha[s.perm[i]] = ha[i];
+        }
+    }
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_profile(medgp_ctx *ctx, int enable)
+{
+    if (!ctx) return MEDGP_ERR_ARG;
+    ctx->profile = enable != 0;
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_stage_times(medgp_ctx *ctx, medgp_stage_times *out, int reset)
+{
+    if (!ctx || !out) return MEDGP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    resolve_marks(ctx);
+    *out = ctx->times;
+    if (reset) ctx->times = medgp_stage_times{};
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_malloc(medgp_ctx *ctx, size_t bytes, void **d_ptr)
+{
+    if (!ctx || !d_ptr) return MEDGP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CU(cudaMalloc(d_ptr, bytes));
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_free(medgp_ctx *ctx, void *d_ptr)
+{
+    if (!ctx) return MEDGP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CU(cudaFree(d_ptr));
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_memcpy_h2d(medgp_ctx *ctx, void *d_dst, const void *src, size_t bytes)
+{
+    if (!ctx) return MEDGP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CU(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_memcpy_d2h(medgp_ctx *ctx, void *dst, const void *d_src, size_t bytes)
+{
+    if (!ctx) return MEDGP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CU(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MEDGP_OK;
+}
+
+MEDGP_API void *medgp_cuda_stream(medgp_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }

@@ -1,0 +1,144 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the FP64 oracle on the
+same seeded inputs.  Tolerances are relative and stated per test (north_star: <= 1e-9)."""
+import numpy as np
+import pytest
+
+from medgp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9          # north_star tolerance for NLML / gradients / predictions
+RTOL_K = 1e-12       # covariance entries
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def api():
+    from medgp_b200 import api as a
+    return a
+
+
+CASES = [
+    # Q, D, R, n, seed
+    (2, 2, 2, 80, 1),      # C1-like, one partial tile
+    (2, 2, 1, 64, 2),      # exactly one tile
+    (1, 1, 1, 37, 3),      # degenerate single output / single component
+    (3, 4, 2, 130, 4),     # two tiles + 2 rows
+    (5, 24, 8, 300, 5),    # C2 shape, small n
+    (5, 24, 8, 500, 6),    # C2
+]
+
+
+@pytest.mark.parametrize("Q,D,R,n,seed", CASES)
+def test_matrices_nlml_grad(api, oracle, Q, D, R, n, seed):
+    meta, x, y = synth.make_patient(D, n, seed)
+    theta = synth.init_hyp_lmc_sm(Q, D, R, 2, seed=718 + seed)[1]
+    ctx = api.Context(Q, D, R, workspace_bytes=1 << 30)
+    sid = ctx.add_series(meta, x, y)
+    dbg = ctx.debug_matrices(sid, theta, n)
+    K = oracle.gram(Q, D, R, meta, x, theta)
+    assert rel(dbg["K"], K) <= RTOL_K
+    alpha, L, logdet = oracle.fit(Q, D, R, meta, x, y, theta)
+    assert rel(dbg["L"], L) <= 1e-10
+    assert rel(dbg["alpha"], alpha) <= RTOL
+    assert rel(dbg["Kinv"], np.linalg.inv(K)) <= RTOL
+    f, g, st = ctx.nlml_grad([sid], theta[None, :], want_grad=True)
+    f0, g0, st0 = oracle.nlml_grad(Q, D, R, meta, x, y, theta)
+    assert st[0] == st0 == 0
+    assert abs(f[0] - f0) <= RTOL * abs(f0)
+    assert rel(g[0], g0) <= RTOL
+    f2, _, _ = ctx.nlml_grad([sid], theta[None, :], want_grad=False)
+    assert f2[0] == f[0]
+    ctx.close()
+
+
+def test_ragged_batch_and_order_invariance(api, oracle):
+    Q, D, R = 3, 5, 2
+    ctx = api.Context(Q, D, R, workspace_bytes=1 << 30)
+    rng = np.random.default_rng(0)
+    sizes = [20, 64, 65, 200, 333, 129, 12, 500]
+    thetas = synth.init_hyp_lmc_sm(Q, D, R, len(sizes), seed=11)
+    sids, ref = [], []
+    for k, n in enumerate(sizes):
+        meta, x, y = synth.make_patient(D, n, 100 + k)
+        perm = rng.permutation(n)          # arbitrary point order must not matter
+        sids.append(ctx.add_series(meta[perm], x[perm], y[perm]))
+        ref.append(oracle.nlml_grad(Q, D, R, meta, x, y, thetas[k]))
+    f, g, st = ctx.nlml_grad(sids, thetas, want_grad=True)
+    for k in range(len(sizes)):
+        assert st[k] == 0
+        assert abs(f[k] - ref[k][0]) <= RTOL * abs(ref[k][0])
+        assert rel(g[k], ref[k][1]) <= RTOL
+    # same series evaluated with several thetas in one call (random inits of one patient)
+    f2, g2, _ = ctx.nlml_grad([sids[3]] * len(sizes), thetas, want_grad=True)
+    meta, x, y = synth.make_patient(D, sizes[3], 103)
+    for k in range(len(sizes)):
+        f0, g0, _ = oracle.nlml_grad(Q, D, R, meta, x, y, thetas[k])
+        assert abs(f2[k] - f0) <= RTOL * abs(f0)
+        assert rel(g2[k], g0) <= RTOL
+    ctx.close()
+
+
+def test_duplicate_timestamps_and_two_point_features(api, oracle):
+    Q, D, R = 2, 3, 2
+    meta = np.array([0, 0, 1, 1, 1, 2, 2], dtype=np.int32)
+    x = np.array([1.0, 5.0, 1.0, 5.0, 9.5, 5.0, 9.5], dtype=np.float32)   # r = 0 pairs across features
+    y = np.array([0.3, -0.2, 1.0, 0.1, -0.7, 0.4, 0.0], dtype=np.float32)
+    theta = synth.init_hyp_lmc_sm(Q, D, R, 1, seed=5)[0]
+    ctx = api.Context(Q, D, R, workspace_bytes=1 << 28)
+    sid = ctx.add_series(meta, x, y)
+    f, g, st = ctx.nlml_grad([sid], theta[None], True)
+    f0, g0, _ = oracle.nlml_grad(Q, D, R, meta, x, y, theta)
+    assert abs(f[0] - f0) <= RTOL * abs(f0)
+    assert rel(g[0], g0) <= RTOL
+    ctx.close()
+
+
+def test_jitter_path(api, oracle):
+    """Tiny noise + duplicated points make K numerically singular: the reference adds sigma^2
+    again and refactors (c_inference_exact.cpp:99-108); status counts the additions."""
+    Q, D, R = 1, 1, 1
+    n = 40
+    meta = np.zeros(n, dtype=np.int32)
+    x = np.repeat(np.linspace(1, 10, n // 2), 2).astype(np.float32)
+    y = np.random.default_rng(3).standard_normal(n).astype(np.float32)
+    theta = np.array([np.log(1e-9), 1.0, np.log(1 / 24.0), np.log(1 / (2 * 3.14159265 * 48.0)), np.log(1e-12)])
+    ctx = api.Context(Q, D, R, workspace_bytes=1 << 28)
+    sid = ctx.add_series(meta, x, y)
+    f, g, st = ctx.nlml_grad([sid], theta[None], True)
+    f0, g0, st0 = oracle.nlml_grad(Q, D, R, meta, x, y, theta)
+    assert st[0] == st0
+    if st0 >= 0:
+        assert np.isfinite(f[0])
+    else:
+        assert np.isnan(f[0])
+    ctx.close()
+
+
+def test_predict(api, oracle):
+    Q, D, R = 3, 4, 2
+    ctx = api.Context(Q, D, R, workspace_bytes=1 << 30)
+    thetas = synth.init_hyp_lmc_sm(Q, D, R, 3, seed=21)
+    sids, offs, ms, xs, ref_m, ref_v = [], [0], [], [], [], []
+    for k, (n, m) in enumerate([(50, 1), (200, 3), (131, 6)]):
+        meta, x, y = synth.make_patient(D, n, 300 + k)
+        rng = np.random.default_rng(k)
+        mstar = rng.integers(0, D, m).astype(np.int32)
+        xstar = rng.uniform(0.5, 260.0, m).astype(np.float32)
+        xstar[0] = x[3]   # a test time that coincides with a training time
+        sids.append(ctx.add_series(meta, x, y))
+        offs.append(offs[-1] + m)
+        ms.append(mstar)
+        xs.append(xstar)
+        mu, var, _ = oracle.predict(Q, D, R, meta, x, y, thetas[k], mstar, xstar)
+        ref_m.append(mu)
+        ref_v.append(var)
+    mean, var, st = ctx.predict(sids, thetas, offs, np.concatenate(ms), np.concatenate(xs))
+    assert (st == 0).all()
+    assert rel(mean, np.concatenate(ref_m)) <= RTOL
+    assert rel(var, np.concatenate(ref_v)) <= RTOL
+    ctx.close()
