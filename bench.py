@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- cohort NLML+gradient evaluations per second (BASELINE.json metric).
+
+Workload at every N (weak scaling, per-GPU work fixed): configs[1] of BASELINE.json --
+24-feature SM-LMC (D=24, Q=5, R=8, P=1114), 256 synthetic patients of n=500 points per GPU,
+one theta per patient drawn from the reference's initialisation distribution.  One "step" is
+one NLML+gradient evaluation of every patient of the shard (256 evaluations per GPU).
+
+  value  evaluations/s, theta resident in HBM, CUDA events on the library's stream
+  e2e    evaluations/s through medgp_cuda_nlml_grad with HOST buffers (theta H2D and
+         nlml/grad/status D2H inside the timed region)
+  --impl reference   the reference's own CPU implementation (oracle/_ref/ref_eval, the
+         unmodified reference compiled against OpenBLAS) on the box's host cores, one
+         single-thread process per core as the reference is deployed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from medgp_b200 import synth  # noqa: E402
+
+Q, D, R, N_POINTS, PATIENTS_PER_GPU = 5, 24, 8, 500, 256
+METRIC = "cohort NLML+gradient evals/sec"
+UNIT = "evals/s"
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "C2: 24-feature SM-LMC (feature_all.json shape), Q=5 R=8 P=1114, "
+                    f"{PATIENTS_PER_GPU} synthetic patients x n={N_POINTS} per GPU, "
+                    "1 NLML+gradient eval per patient per step",
+        "patients_per_gpu": PATIENTS_PER_GPU, "n_points": N_POINTS, "Q": Q, "D": D, "R": R,
+        "sharding": f"patients sharded over {n_gpus} GPU(s), no collective on the data path",
+        "l2": "inputs_exceed_l2 (256 x 2 MiB matrices per step vs 126 MB L2)",
+    }
+
+
+def make_shard(rank):
+    """Patients rank*256 .. rank*256+255 of the synthetic cohort and their thetas."""
+    patients = [synth.make_patient(D, N_POINTS, seed=rank * PATIENTS_PER_GPU + i)
+                for i in range(PATIENTS_PER_GPU)]
+    thetas = synth.init_hyp_lmc_sm(Q, D, R, PATIENTS_PER_GPU, seed=718 + rank)
+    return patients, thetas
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measure_fp64_peak(torch, device):
+    """cuBLAS DGEMM 8192^3 through torch.matmul: the FP64 yardstick (MEASURED_PEAKS.json has
+    no FP64 entry).  Returns TFLOP/s (best of 5)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=device)
+    b = torch.randn(n, n, dtype=torch.float64, device=device)
+    torch.matmul(a, b)
+    torch.cuda.synchronize(device)
+    best = 0.0
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize(device)
+        best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    del a, b
+    return best
+
+
+def reference_sample(n_evals, want_grad=True):
+    """Times `n_evals` evaluations of the workload with the compiled reference, one
+    single-thread process per evaluation, all concurrently.  Returns (evals/s, cores, text)."""
+    from oracle import oracle
+    if not oracle.have_ref():
+        return None, 0, "oracle/_ref/ref_eval missing"
+    patients, thetas = make_shard(0)
+    tmp = tempfile.mkdtemp(prefix="medgp_ref_")
+    paths = []
+    for i in range(n_evals):
+        meta, x, y = patients[i % PATIENTS_PER_GPU]
+        p = os.path.join(tmp, f"case{i}.txt")
+        oracle.write_case(p, Q, D, R, meta, x, y, thetas[i % PATIENTS_PER_GPU])
+        paths.append(p)
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([oracle.REF_EVAL, p, "1" if want_grad else "0", "1", "1"],
+                              stdout=subprocess.DEVNULL, env=oracle.ref_env()) for p in paths]
+    for pr in procs:
+        pr.wait()
+    dt = time.perf_counter() - t0
+    for p in paths:
+        os.unlink(p)
+    os.rmdir(tmp)
+    return n_evals / dt, n_evals, (f"{n_evals} concurrent single-thread ref_eval processes, one "
+                                  f"NLML+grad eval each (n={N_POINTS}, D={D}, Q={Q}, R={R}), "
+                                  f"{dt:.1f} s wall")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        reference_sample(cores)
+    t0 = time.perf_counter()
+    total = 0
+    sample = ""
+    for _ in range(args.steps):
+        v, used, sample = reference_sample(cores)
+        if v is None:
+            print(json.dumps({"impl": "reference", "unavailable": sample}))
+            return 0
+        total += used
+    dt = time.perf_counter() - t0
+    value = total / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": sample + "; reference built with g++ -O2 + OpenBLAS (not icpc/MKL)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from medgp_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    patients, thetas = make_shard(rank)
+    ctx = api.Context(Q, D, R, device=local, workspace_bytes=8 << 30)
+    sids = np.array([ctx.add_series(*p) for p in patients], dtype=np.int32)
+    P, B = ctx.P, len(sids)
+    d_theta, d_nlml = ctx.malloc(B * P * 8), ctx.malloc(B * 8)
+    d_grad, d_status = ctx.malloc(B * P * 8), ctx.malloc(B * 4)
+    ctx.h2d(d_theta, thetas)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+
+    def step_device():
+        ctx.nlml_grad_device(sids, d_theta, True, d_nlml, d_grad, d_status)
+
+    for _ in range(args.warmup):
+        step_device()
+    ctx.sync()
+    ctx.stage_times(reset=True)
+    ctx.profile(True)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    ctx.sync()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    stages = ctx.stage_times(reset=True)
+    ctx.profile(False)
+    status = np.empty(B, dtype=np.int32)
+    ctx.d2h(status, d_status)
+    nlml_dev = np.empty(B)
+    ctx.d2h(nlml_dev, d_nlml)
+    assert (status == 0).all() and np.isfinite(nlml_dev).all(), "device path produced failures"
+
+    # ---- e2e: host buffers through the public C ABI call, copies inside the timed region
+    for _ in range(2):
+        ctx.nlml_grad(sids, thetas, True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        nlml_h, grad_h, st_h = ctx.nlml_grad(sids, thetas, True)
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    assert np.allclose(nlml_h, nlml_dev, rtol=1e-12, atol=0)
+
+    t = torch.tensor([ms, t_e2e * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    total_evals = world * B * args.steps
+    value = total_evals / (ms_max * 1e-3)
+    e2e_value = total_evals / (e2e_ms_max * 1e-3)
+
+    if rank == 0:
+        # ---- roofline of the dominant stage (by device time inside the timed region)
+        names = [k for k in stages if k != "evals"]
+        dom = max(names, key=lambda k: stages[k]["ms"])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        st = stages[dom]
+        launches = max(1, st["launches"])
+        avg_s = st["ms"] * 1e-3 / launches
+        if dom in ("potrf", "trtri", "lauum", "solve"):
+            fp64_peak = measure_fp64_peak(torch, dev)
+            achieved = st["flops"] / launches / avg_s / 1e12
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": fp64_peak,
+                        "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                        "peak_source": "FP64: cuBLAS DGEMM 8192^3 measured in this run "
+                                       "(MEASURED_PEAKS.json has no FP64 entry)"}
+        else:
+            hbm = peaks.get("hbm_gbs", 6650.0)
+            achieved = st["bytes"] / launches / avg_s / 1e9
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm,
+                        "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}
+        roofline["stage_ms_per_step"] = {k: stages[k]["ms"] / args.steps for k in names}
+        roofline["stage_launches_per_step"] = {k: stages[k]["launches"] / args.steps for k in names}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, used, sample = reference_sample(os.cpu_count() or 1)
+            if v is not None:
+                cpu = {"value": v, "unit": UNIT, "cores": used, "kind": "reference",
+                       "sample": sample + "; reference built with g++ -O2 + OpenBLAS (not icpc/MKL)"}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * P * 8),
+                    "d2h_bytes_per_step": int(B * (P + 1) * 8 + B * 4)},
+            "gpu_launches": int(sum(stages[k]["launches"] for k in names)),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    for p in (d_theta, d_nlml, d_grad, d_status):
+        ctx.free(p)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -131,61 +131,76 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
 //   part[item] = [ sum W k_q (Q) | sum W km_q (Q) | sum W kv_q (Q) | sum_{i} W_ii ]
 // For d == e only j <= i is visited and off-diagonal elements count twice, so the sums are
 // those of the full square block.  K^-1 is read once (lower triangle), dK is never stored.
+template <int QT>
 __global__ void __launch_bounds__(128)
 k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
 {
-    __shared__ double scratch[(3 * MEDGP_QMAX + 1) * 32];
-    __shared__ double s_w[MEDGP_QMAX], s_c[MEDGP_QMAX];
+    // one WARP per work item (4 items per CTA): the 3Q+1 partial sums stay in registers and
+    // are combined with shuffles only -- no shared memory, no block barrier.
     const EvalDesc &e = descs[blockIdx.y];
-    if ((int)blockIdx.x >= e.nitems) return;
-    const int4 it = e.items[blockIdx.x];
-    const int Q = md.Q, tid = threadIdx.x, ld = e.npad;
-    if (tid < Q) {
-        s_w[tid] = e.par[md.oW + tid];
-        s_c[tid] = e.par[md.oC + tid];
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (item >= e.nitems) return;
+    const int4 it = e.items[item];
+    const int ld = e.npad;
+    double wq[QT], cq[QT];
+#pragma unroll
+    for (int q = 0; q < QT; q++) {
+        wq[q] = __ldg(e.par + md.oW + q);
+        cq[q] = __ldg(e.par + md.oC + q);
     }
-    __syncthreads();
     const int d = it.x, f = it.y, i0 = it.z, nr = it.w - it.z;
-    const int j0 = e.off[f], nc = e.off[f + 1] - j0;
+    const int j0 = __ldg(e.off + f), nc = __ldg(e.off + f + 1) - j0;
     const bool diagblk = (d == f);
-    const double2 *cs = reinterpret_cast<const double2 *>(e.cs);
-    double acc[3 * MEDGP_QMAX + 1];
+    const double2 *__restrict__ cs = reinterpret_cast<const double2 *>(e.cs);
+    const double *__restrict__ M = e.M;
+    const double *__restrict__ tt = e.t;
+    const double *__restrict__ al = e.alpha;
+    double sk[QT], sm[QT], sv[QT], sdiag = 0.0;
 #pragma unroll
-    for (int u = 0; u < 3 * MEDGP_QMAX + 1; u++) acc[u] = 0.0;
-    const int total = nr * nc;
-    for (int idx = tid; idx < total; idx += blockDim.x) {
-        const int jj = idx / nr, ii = idx - jj * nr;
+    for (int q = 0; q < QT; q++) sk[q] = sm[q] = sv[q] = 0.0;
+    int jj = lane / nr, ii = lane - jj * nr;
+    while (jj < nc) {
         const int i = i0 + ii, j = j0 + jj;
-        if (diagblk && j > i) continue;
-        const double ai = e.alpha[i], aj = e.alpha[j];
-        double w = e.M[(size_t)j * ld + i] - ai * aj;
-        if (i == j) acc[3 * MEDGP_QMAX] += w;
-        else if (diagblk) w *= 2.0;
-        const double tau = e.t[i] - e.t[j], tau2 = tau * tau;
+        if (!(diagblk && j > i)) {
+            double w = M[(size_t)j * ld + i] - al[i] * al[j];
+            if (i == j) sdiag += w;
+            else if (diagblk) w *= 2.0;
+            const double tau = tt[i] - tt[j], tau2 = tau * tau;
 #pragma unroll
-        for (int q = 0; q < MEDGP_QMAX; q++) {
-            if (q < Q) {
+            for (int q = 0; q < QT; q++) {
                 const double2 a = cs[(size_t)q * ld + i], b = cs[(size_t)q * ld + j];
                 const double cosphi = a.x * b.x + a.y * b.y;
                 const double sinphi = a.y * b.x - a.x * b.y;
-                const double ex = exp(-s_c[q] * tau2);
-                const double k = cosphi * ex;
-                const double phi = s_w[q] * tau;
-                acc[q] += w * k;
-                acc[MEDGP_QMAX + q] -= w * (phi * sinphi * ex);           // km: c_kernel_LMC_SM.cpp:379-384
-                acc[2 * MEDGP_QMAX + q] -= w * (2.0 * s_c[q] * tau2 * k); // kv: c_kernel_LMC_SM.cpp:385-391
+                const double wex = w * exp(-cq[q] * tau2);
+                const double wk = wex * cosphi;
+                sk[q] += wk;
+                sm[q] -= wex * (wq[q] * tau) * sinphi;   // km: c_kernel_LMC_SM.cpp:379-384
+                sv[q] -= (2.0 * cq[q] * tau2) * wk;      // kv: c_kernel_LMC_SM.cpp:385-391
             }
         }
+        ii += 32;
+        while (ii >= nr) { ii -= nr; jj++; }
     }
-    block_reduce_sum<3 * MEDGP_QMAX + 1>(acc, scratch);
-    if (tid == 0) {
-        double *p = e.part + (size_t)blockIdx.x * (3 * Q + 1);
-        for (int q = 0; q < Q; q++) {
-            p[q] = acc[q];
-            p[Q + q] = acc[MEDGP_QMAX + q];
-            p[2 * Q + q] = acc[2 * MEDGP_QMAX + q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < QT; q++) {
+            sk[q] += __shfl_xor_sync(0xffffffffu, sk[q], o);
+            sm[q] += __shfl_xor_sync(0xffffffffu, sm[q], o);
+            sv[q] += __shfl_xor_sync(0xffffffffu, sv[q], o);
         }
-        p[3 * Q] = acc[3 * MEDGP_QMAX];
+        sdiag += __shfl_xor_sync(0xffffffffu, sdiag, o);
+    }
+    if (lane == 0) {
+        double *p = e.part + (size_t)item * (3 * QT + 1);
+#pragma unroll
+        for (int q = 0; q < QT; q++) {
+            p[q] = sk[q];
+            p[QT + q] = sm[q];
+            p[2 * QT + q] = sv[q];
+        }
+        p[3 * QT] = sdiag;
     }
 }
 

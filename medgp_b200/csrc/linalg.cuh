@@ -28,85 +28,106 @@ __device__ __forceinline__ void gemm2_smem(double (&acc)[4][4][2], const double 
 }
 
 // ------------------------------------------------------------------ potrf: diagonal block k
+// Fused Cholesky + triangular inverse of one 64x64 block by Gauss-Jordan-style elimination on
+// the augmented matrix [D | I], entirely in registers.  256 threads: thread (r, g) (r = tid&63,
+// g = tid>>6, warp-uniform) owns row r, columns c = 4s+g, s = 0..15, in W[s].
+// Step j (pivot d = D_jj after earlier updates, a_r = D_rj):
+//      L_rj = a_r / sqrt(d)                       (saved to sL by the owner of column j)
+//      W_rc -= (a_r / d) * row_j[c]    for every r > j, c <= r, c != j
+//      W_rj  = -a_r / d
+// where row_j[c] = D_cj for c > j (symmetry) and the running Y_jc for c < j, Y = rows of
+// L^-1 before the final scaling X_rc = Y_rc / L_rr.  One block barrier per step; row_j travels
+// through a double-buffered 64-entry shared vector laid out by column group.
+#define MEDGP_DIAG_THREADS 256
+
+__device__ __forceinline__ void potf2_inv_gj(double (&W)[16], int r, int g, double *rowbuf /*2x64*/,
+                                             double *sL /*pitch SLD*/, int *s_fail)
+{
+#pragma unroll
+    for (int j = 0; j < MEDGP_NB; j++) {
+        const int gj = j & 3, sj = j >> 2;
+        double *rb = rowbuf + (j & 1) * MEDGP_NB;
+        // publish row j: column-j owners write D_rj (r >= j) at the slot of column r ...
+        if (g == gj && r >= j) rb[(r & 3) * 16 + (r >> 2)] = W[sj];
+        // ... and the four owners of row j write Y_jc, c < j
+        if (r == j) {
+#pragma unroll
+            for (int s = 0; s < 16; s++)
+                if (4 * s + g < j) rb[g * 16 + s] = W[s];
+        }
+        __syncthreads();
+        if (r >= j) {
+            double d = rb[gj * 16 + sj];
+            if (!(d > 0.0)) {  // LAPACK potrf: info > 0 (also catches NaN)
+                *s_fail = 1;
+                d = 1.0;
+            }
+            const double ar = rb[(r & 3) * 16 + (r >> 2)];
+            if (g == gj) sL[j * MEDGP_SLD + r] = ar * rsqrt(d);  // L_rj (r == j: sqrt(d))
+            if (r > j) {
+                const double ard = ar / d;
+#pragma unroll
+                for (int s = 0; s < 16; s++) {
+                    const int c = 4 * s + g;
+                    if (c <= r) {
+                        if (s == sj && g == gj) W[s] = -ard;
+                        else W[s] = fma(-ard, rb[g * 16 + s], W[s]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // One CTA per evaluation: D = K_kk - sum_{l<k} L_kl L_kl^T ; L_kk = chol(D) ; X_kk = inv(L_kk).
 // Writes L_kk (lower part of the tile), dinv[k], dinvT[k], blk[k] = sum log diag(L_kk) and
-// raises *fail when a pivot is not positive (LAPACK potrf info > 0).
-__global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
+// raises fail[] when a pivot is not positive.
+__global__ void __launch_bounds__(MEDGP_DIAG_THREADS, 2)
 k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail)
 {
     extern __shared__ __align__(128) double smem[];
     __shared__ GemmBars bars;
+    __shared__ double rowbuf[2 * MEDGP_NB];
     __shared__ int s_fail;
     const EvalDesc &e = descs[blockIdx.x];
     if (k >= e.T) return;
     const int ld = e.npad, tid = threadIdx.x;
     gemm_bars_init(&bars);
     if (tid == 0) s_fail = 0;
-
-    double acc[4][4][2];
-    acc_zero(acc);
     double *M = e.M;
-    gemm_nt_tiles(acc, k,
-                  [&](int l, const double *&A, int &lda, const double *&B, int &ldb) {
-                      A = tile_ptr(M, ld, k, l);
-                      B = A;
-                      lda = ldb = ld;
-                  },
-                  smem, &bars);
-    __syncthreads();
     double *sD = smem, *sL = smem + kTileElems;
-    acc_to_smem(acc, sD, 1.0);
+    if (tid < MEDGP_GEMM_THREADS) {
+        double acc[4][4][2];
+        acc_zero(acc);
+        gemm_nt_tiles(acc, k,
+                      [&](int l, const double *&A, int &lda, const double *&B, int &ldb) {
+                          A = tile_ptr(M, ld, k, l);
+                          B = A;
+                          lda = ldb = ld;
+                      },
+                      smem, &bars);
+        // the 4 GEMM warps must all be done with the ring before it is reused as sD
+        asm volatile("bar.sync 1, %0;" ::"n"(MEDGP_GEMM_THREADS));
+        acc_to_smem(acc, sD, 1.0);
+    }
     __syncthreads();
-    // D = sym(K_kk) - C, lower part (sD is symmetric; only r >= c is used below)
+    const int r = tid & 63, g = tid >> 6;
     const double *Kkk = tile_ptr(M, ld, k, k);
-    for (int idx = tid; idx < MEDGP_NB * MEDGP_NB; idx += blockDim.x) {
-        const int c = idx >> 6, r = idx & 63;
-        if (r >= c) sD[c * MEDGP_SLD + r] = Kkk[(size_t)c * ld + r] - sD[c * MEDGP_SLD + r];
+    double W[16];
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        const int c = 4 * s + g;
+        W[s] = (c <= r) ? Kkk[(size_t)c * ld + r] - sD[c * MEDGP_SLD + r] : 0.0;
     }
-    // unblocked right-looking Cholesky, one barrier per column.  Column j of sD is frozen once
-    // it becomes the pivot column (a_r = D_rj after all earlier updates); the trailing update
-    // uses a_r a_c / d, and L(:,j) = a / sqrt(d) is formed afterwards from the frozen columns.
-    const int r = tid & 63, half = tid >> 6;
-    for (int j = 0; j < MEDGP_NB; j++) {
-        __syncthreads();
-        double d = sD[j * MEDGP_SLD + j];
-        if (!(d > 0.0)) {  // also catches NaN (LAPACK potrf: info > 0)
-            if (tid == 0) s_fail = 1;
-            d = 1.0;
-        }
-        const double ard = (r > j) ? sD[j * MEDGP_SLD + r] / d : 0.0;
-#pragma unroll 4
-        for (int c = j + 1 + half; c <= r; c += 2)
-            sD[c * MEDGP_SLD + r] -= ard * sD[j * MEDGP_SLD + c];
-    }
+    __syncthreads();  // sD is dead from here on: it becomes the staging tile for X
+    potf2_inv_gj(W, r, g, rowbuf, sL, &s_fail);
     __syncthreads();
-    for (int idx = tid; idx < MEDGP_NB * MEDGP_NB; idx += blockDim.x) {
-        const int c = idx >> 6, rr = idx & 63;
-        double d = sD[c * MEDGP_SLD + c];
-        if (!(d > 0.0)) d = 1.0;
-        sL[c * MEDGP_SLD + rr] = (rr >= c) ? sD[c * MEDGP_SLD + rr] / sqrt(d) : 0.0;
-    }
-    __syncthreads();
-    // X = inv(L): two adjacent lanes share column c of X (even / odd terms of each dot
-    // product).  X is stored transposed in sD (sD[k][c] = X(k,c)); sD is dead as input.
-    {
-        const int c = tid >> 1, par = tid & 1;
-        for (int rr = 0; rr < MEDGP_NB; rr++) {
-            double s = 0.0;
-            if (rr > c) {
-#pragma unroll 4
-                for (int kk = c + par; kk < rr; kk += 2)
-                    s += sL[kk * MEDGP_SLD + rr] * sD[kk * MEDGP_SLD + c];
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (par == 0) {
-                double x = 0.0;
-                if (rr == c) x = 1.0 / sL[rr * MEDGP_SLD + rr];
-                else if (rr > c) x = -s / sL[rr * MEDGP_SLD + rr];
-                sD[rr * MEDGP_SLD + c] = x;
-            }
-            __syncwarp();
-        }
+    const double lrr_inv = 1.0 / sL[r * MEDGP_SLD + r];
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        const int c = 4 * s + g;
+        const double x = (c < r) ? W[s] * lrr_inv : (c == r ? lrr_inv : 0.0);
+        sD[c * MEDGP_SLD + r] = x;  // X(r, c)
     }
     __syncthreads();
     // write back: L_kk (lower), dinv (X column-major), dinvT (X^T column-major)
@@ -116,8 +137,8 @@ k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail)
     for (int idx = tid; idx < MEDGP_NB * MEDGP_NB; idx += blockDim.x) {
         const int c = idx >> 6, rr = idx & 63;
         if (rr >= c) Lkk[(size_t)c * ld + rr] = sL[c * MEDGP_SLD + rr];
-        Xk[c * MEDGP_NB + rr] = sD[rr * MEDGP_SLD + c];   // X(rr, c)
-        XTk[c * MEDGP_NB + rr] = sD[c * MEDGP_SLD + rr];  // X^T(rr, c) = X(c, rr)
+        Xk[c * MEDGP_NB + rr] = sD[c * MEDGP_SLD + rr];   // X(rr, c)
+        XTk[c * MEDGP_NB + rr] = sD[rr * MEDGP_SLD + c];  // X^T(rr, c) = X(c, rr)
     }
     if (tid < 32) {
         double s = log(sL[tid * MEDGP_SLD + tid]) + log(sL[(tid + 32) * MEDGP_SLD + tid + 32]);

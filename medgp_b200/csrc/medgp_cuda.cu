@@ -25,7 +25,7 @@
 
 namespace {
 
-constexpr int kGradRows = 128;  // rows per gradient work item
+constexpr int kGradRows = 32;   // rows per gradient work item
 constexpr int kMaxJitter = 10;  // inference/c_inference_exact.cpp:99
 
 struct Series {
@@ -317,7 +317,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         {
             StageScope sc(ctx, MEDGP_STAGE_POTRF);
             for (int k = 0; k < Tmax; k++) {
-                k_potrf_diag<<<act(k), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, ctx->d_fail);
+                k_potrf_diag<<<act(k), MEDGP_DIAG_THREADS, gemm_smem, st>>>(dd, k, ctx->d_fail);
                 ctx->times.launches[MEDGP_STAGE_POTRF]++;
                 if (k + 1 < Tmax) {
                     k_potrf_panel<<<dim3(Tmax - k - 1, act(k + 1)), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k);
@@ -352,7 +352,17 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
             }
             {
                 StageScope sc(ctx, MEDGP_STAGE_GRAD);
-                k_grad<<<dim3(items_max, ncta), 128, 0, st>>>(dd, md);
+                const dim3 gg((items_max + 3) / 4, ncta);
+                switch (md.Q) {
+                    case 1: k_grad<1><<<gg, 128, 0, st>>>(dd, md); break;
+                    case 2: k_grad<2><<<gg, 128, 0, st>>>(dd, md); break;
+                    case 3: k_grad<3><<<gg, 128, 0, st>>>(dd, md); break;
+                    case 4: k_grad<4><<<gg, 128, 0, st>>>(dd, md); break;
+                    case 5: k_grad<5><<<gg, 128, 0, st>>>(dd, md); break;
+                    case 6: k_grad<6><<<gg, 128, 0, st>>>(dd, md); break;
+                    case 7: k_grad<7><<<gg, 128, 0, st>>>(dd, md); break;
+                    default: k_grad<8><<<gg, 128, 0, st>>>(dd, md); break;
+                }
                 k_grad_finish<<<ncta, 256, fin_smem, st>>>(dd, md, d_grad, ctx->d_fail);
                 ctx->times.launches[MEDGP_STAGE_GRAD] += 2;
             }
