@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmedgp_cuda.so")
+LIB_PATH = os.environ.get("MEDGP_LIB", os.path.join(HERE, "libmedgp_cuda.so"))  # MEDGP_LIB: experiments only
 PI_REF = 3.14159265  # medgpc/src/util/global_settings.h:6
 
 STAGES = ["prep", "assemble", "potrf", "solve", "trtri", "lauum", "grad", "predict"]

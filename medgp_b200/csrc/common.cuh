@@ -1,10 +1,13 @@
 // common.cuh -- shared definitions for libmedgp_cuda.so (sm_100a only).
 //
 // HBM layout of one in-flight evaluation (all FP64):
-//   M      npad x npad column-major square, ld = npad (npad = n rounded up to 64, padded with
-//          the identity).  Lower tiles hold K -> L -> K^-1 in place; strictly-upper tiles hold
-//          U = (L^-1)^T once the triangular inverse ran.
-//   dinv   T = npad/64 blocks of 64x64 column-major: X_kk = inv(L_kk) (lower, zeros above)
+//   M      T x T tiles (T = npad/64, npad = n rounded up to 64, padded with the identity), stored
+//          TILE-MAJOR: tile (ti, tj) is the contiguous block number tj*T + ti of 64 columns x
+//          pitch 68 doubles (34816 B).  The pitch is the bank-conflict-free shared-memory pitch
+//          of the DMMA fragment loads, so a 16-column k-panel of a tile is ONE contiguous
+//          8704 B bulk copy straight into its pipeline stage.  Lower tiles hold K -> L -> K^-1
+//          in place; strictly-upper tiles hold U = (L^-1)^T once the triangular inverse ran.
+//   dinv   T tiles (same 64 x pitch-68 format): X_kk = inv(L_kk) (lower, zeros above)
 //   dinvT  the same blocks transposed (X_kk^T, upper)
 //   rhs    nrhs x npad: row 0 = y -> z = L^-1 y ; rows 1.. = k* -> L^-1 k* (prediction)
 //   alpha  npad: K^-1 y
@@ -43,6 +46,16 @@ struct __align__(16) EvalDesc {
     int star_out;            // offset of this evaluation's predictions in the output arrays
     int pad0, pad1, pad2;
 };
+
+// tile-major addressing (kTileElems doubles per tile, column pitch MEDGP_SLD)
+__host__ __device__ __forceinline__ size_t tile_off(int T, int ti, int tj)
+{
+    return ((size_t)tj * T + ti) * (size_t)(MEDGP_NB * MEDGP_SLD);
+}
+__host__ __device__ __forceinline__ size_t elem_off(int T, int i, int j)
+{
+    return tile_off(T, i >> 6, j >> 6) + (size_t)((j & 63) * MEDGP_SLD + (i & 63));
+}
 
 // ---------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + bulk async copy (TMA engine, UBLKCP) + FP64 tensor-core MMA (DMMA)
@@ -112,8 +125,9 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 // Tile GEMM core:  C(64x64) = sum_l A_l * B_l^T,  A_l, B_l 64x64 column-major tiles in HBM.
 // One CTA of 4 warps; warp (wm, wn) owns the 32x32 quadrant, as 4x4 DMMA 8x8 sub-tiles:
 //   acc[a][b][e] = C[32wm + 8a + lane/4][32wn + 8b + 2(lane%4) + e]
-// Operands are staged column-by-column (512 B each) by cp.async.bulk into a 4-stage ring of
-// [k][m] / [k][n] panels with pitch MEDGP_SLD, guarded by full/empty mbarriers.
+// Operands are staged one 16-column panel (8704 B, contiguous in the tile-major HBM layout) per
+// cp.async.bulk into a 4-stage ring of [k][m] / [k][n] panels with pitch MEDGP_SLD, guarded by
+// full/empty mbarriers.
 // ---------------------------------------------------------------------------------------
 constexpr int kPanelElems = MEDGP_KC * MEDGP_SLD;            // one operand panel of a stage
 constexpr int kStageElems = 2 * kPanelElems;                 // A panel + B panel
@@ -169,7 +183,7 @@ __device__ __forceinline__ void mma_panels(double (&acc)[4][4][2], const double 
     }
 }
 
-// TileFn: void operator()(int l, const double*& A, int& lda, const double*& B, int& ldb)
+// TileFn: void operator()(int l, const double*& A, const double*& B) -> tile base pointers
 template <class TileFn>
 __device__ __forceinline__ void gemm_nt_tiles(double (&acc)[4][4][2], int nl, TileFn tiles,
                                               double *smem, GemmBars *bars)
@@ -177,24 +191,20 @@ __device__ __forceinline__ void gemm_nt_tiles(double (&acc)[4][4][2], int nl, Ti
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wm = warp & 1, wn = warp >> 1;
     const int nch = nl * (MEDGP_NB / MEDGP_KC);
-    constexpr uint32_t kStageBytes = 2 * MEDGP_KC * MEDGP_NB * 8;  // bytes landing per stage
+    constexpr uint32_t kPanelBytes = kPanelElems * 8;  // 8704 B, one bulk copy
 
     auto issue = [&](int ch) {
-        const int s = ch % MEDGP_NSTAGE;
-        const int l = ch / (MEDGP_NB / MEDGP_KC), cc = ch % (MEDGP_NB / MEDGP_KC);
-        const double *A, *B;
-        int lda, ldb;
-        tiles(l, A, lda, B, ldb);
-        if (lane == 0) mbar_arrive_expect_tx(&bars->full[s], kStageBytes);
+        if (lane == 0) {
+            const int s = ch % MEDGP_NSTAGE;
+            const int l = ch / (MEDGP_NB / MEDGP_KC), cc = ch % (MEDGP_NB / MEDGP_KC);
+            const double *A, *B;
+            tiles(l, A, B);
+            mbar_arrive_expect_tx(&bars->full[s], 2 * kPanelBytes);
+            double *stage = smem + s * kStageElems;
+            bulk_g2s(stage, A + cc * kPanelElems, kPanelBytes, &bars->full[s]);
+            bulk_g2s(stage + kPanelElems, B + cc * kPanelElems, kPanelBytes, &bars->full[s]);
+        }
         __syncwarp();
-        double *stage = smem + s * kStageElems;
-        if (lane < MEDGP_KC)
-            bulk_g2s(stage + lane * MEDGP_SLD, A + (size_t)(cc * MEDGP_KC + lane) * lda,
-                     MEDGP_NB * 8, &bars->full[s]);
-        else
-            bulk_g2s(stage + kPanelElems + (lane - MEDGP_KC) * MEDGP_SLD,
-                     B + (size_t)(cc * MEDGP_KC + lane - MEDGP_KC) * ldb, MEDGP_NB * 8,
-                     &bars->full[s]);
     };
 
     if (warp == 0)
@@ -213,6 +223,10 @@ __device__ __forceinline__ void gemm_nt_tiles(double (&acc)[4][4][2], int nl, Ti
         mbar_wait(&bars->full[s], (ch / MEDGP_NSTAGE) & 1);
         const double *stage = smem + s * kStageElems;
         mma_panels(acc, stage, stage + kPanelElems, MEDGP_KC / 4, wm, wn, lane);
+        // The stage is about to be handed back to the async proxy (bulk copy): order this
+        // thread's generic-proxy reads before it.  Without the fence the refill was observed
+        // to race with the fragment loads under load (1e-3 errors, run-to-run differences).
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->empty[s]);
     }
@@ -233,8 +247,8 @@ __device__ __forceinline__ void acc_to_smem(const double (&acc)[4][4][2], double
         }
 }
 
-// acc = base - acc, base a column-major HBM tile
-__device__ __forceinline__ void acc_rsub_global(double (&acc)[4][4][2], const double *G, int ldg)
+// acc = base - acc, base a pitch-SLD HBM tile
+__device__ __forceinline__ void acc_rsub_global(double (&acc)[4][4][2], const double *G)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wm = warp & 1, wn = warp >> 1, r = lane >> 2, kq = lane & 3;
@@ -243,12 +257,12 @@ __device__ __forceinline__ void acc_rsub_global(double (&acc)[4][4][2], const do
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int row = wm * 32 + 8 * a + r, col = wn * 32 + 8 * b + 2 * kq;
-            acc[a][b][0] = G[(size_t)col * ldg + row] - acc[a][b][0];
-            acc[a][b][1] = G[(size_t)(col + 1) * ldg + row] - acc[a][b][1];
+            acc[a][b][0] = G[col * MEDGP_SLD + row] - acc[a][b][0];
+            acc[a][b][1] = G[(col + 1) * MEDGP_SLD + row] - acc[a][b][1];
         }
 }
 
-__device__ __forceinline__ void acc_to_global(const double (&acc)[4][4][2], double *G, int ldg)
+__device__ __forceinline__ void acc_to_global(const double (&acc)[4][4][2], double *G)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wm = warp & 1, wn = warp >> 1, r = lane >> 2, kq = lane & 3;
@@ -257,19 +271,16 @@ __device__ __forceinline__ void acc_to_global(const double (&acc)[4][4][2], doub
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int row = wm * 32 + 8 * a + r, col = wn * 32 + 8 * b + 2 * kq;
-            G[(size_t)col * ldg + row] = acc[a][b][0];
-            G[(size_t)(col + 1) * ldg + row] = acc[a][b][1];
+            G[col * MEDGP_SLD + row] = acc[a][b][0];
+            G[(col + 1) * MEDGP_SLD + row] = acc[a][b][1];
         }
 }
 
-// copy a dense 64x64 column-major HBM tile (ld = ldg) into a pitch-SLD shared tile
-__device__ __forceinline__ void tile_g2s_plain(double *sT, const double *G, int ldg)
+// copy a pitch-SLD HBM tile into a pitch-SLD shared tile (contiguous 34816 B)
+__device__ __forceinline__ void tile_g2s_plain(double *sT, const double *G)
 {
-    for (int idx = threadIdx.x; idx < MEDGP_NB * MEDGP_NB / 2; idx += blockDim.x) {
-        const int c = idx >> 5, r2 = (idx & 31) * 2;
-        const double2 v = *reinterpret_cast<const double2 *>(G + (size_t)c * ldg + r2);
-        *reinterpret_cast<double2 *>(sT + c * MEDGP_SLD + r2) = v;
-    }
+    for (int idx = threadIdx.x; idx < kTileElems / 2; idx += blockDim.x)
+        reinterpret_cast<double2 *>(sT)[idx] = reinterpret_cast<const double2 *>(G)[idx];
 }
 
 // block-wide sum of `NV` doubles per thread; result valid in thread 0.  scratch: NV*32 doubles.

@@ -99,7 +99,7 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
     const double tr = s_tr[r];
     const int mr = s_mr[r];
     const double jit = 1.0 + (double)e.jitter;
-    double *out = e.M + (size_t)(tj * MEDGP_NB) * ld + gi;
+    double *out = e.M + tile_off(e.T, ti, tj) + r;
 #pragma unroll 2
     for (int u = 0; u < 16; u++) {
         const int c = g * 16 + u, gj = tj * MEDGP_NB + c;
@@ -118,7 +118,7 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
             }
             if (gi == gj) val += jit * e.par[md.oSig2 + mr];
         }
-        out[(size_t)c * ld] = val;
+        out[c * MEDGP_SLD] = val;
     }
 }
 
@@ -142,7 +142,7 @@ k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
     const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (item >= e.nitems) return;
     const int4 it = e.items[item];
-    const int ld = e.npad;
+    const int ld = e.npad, T = e.T;
     double wq[QT], cq[QT];
 #pragma unroll
     for (int q = 0; q < QT; q++) {
@@ -163,7 +163,7 @@ k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
     while (jj < nc) {
         const int i = i0 + ii, j = j0 + jj;
         if (!(diagblk && j > i)) {
-            double w = M[(size_t)j * ld + i] - al[i] * al[j];
+            double w = M[elem_off(T, i, j)] - al[i] * al[j];
             if (i == j) sdiag += w;
             else if (diagblk) w *= 2.0;
             const double tau = tt[i] - tt[j], tau2 = tau * tau;

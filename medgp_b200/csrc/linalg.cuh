@@ -12,9 +12,9 @@
 #pragma once
 #include "common.cuh"
 
-__device__ __forceinline__ double *tile_ptr(double *M, int ld, int ti, int tj)
+__device__ __forceinline__ double *tile_ptr(double *M, int T, int ti, int tj)
 {
-    return M + (size_t)tj * MEDGP_NB * ld + (size_t)ti * MEDGP_NB;
+    return M + tile_off(T, ti, tj);
 }
 
 // second product of the panel kernels: acc = sP * X^T with sP, sX pitch-SLD tiles in smem,
@@ -29,116 +29,178 @@ __device__ __forceinline__ void gemm2_smem(double (&acc)[4][4][2], const double 
 
 // ------------------------------------------------------------------ potrf: diagonal block k
 // Fused Cholesky + triangular inverse of one 64x64 block by Gauss-Jordan-style elimination on
-// the augmented matrix [D | I], entirely in registers.  256 threads: thread (r, g) (r = tid&63,
-// g = tid>>6, warp-uniform) owns row r, columns c = 4s+g, s = 0..15, in W[s].
+// the augmented matrix [D | I], entirely in registers.  128 threads: thread (r, g) (r = tid&63,
+// g = tid>>6, warp-uniform) owns row r and the 32 columns of parity g.
 // Step j (pivot d = D_jj after earlier updates, a_r = D_rj):
 //      L_rj = a_r / sqrt(d)                       (saved to sL by the owner of column j)
-//      W_rc -= (a_r / d) * row_j[c]    for every r > j, c <= r, c != j
+//      W_rc -= (a_r / d) * row_j[c]    for every r > j, c != j   (c > r: dead slots, harmless)
 //      W_rj  = -a_r / d
 // where row_j[c] = D_cj for c > j (symmetry) and the running Y_jc for c < j, Y = rows of
 // L^-1 before the final scaling X_rc = Y_rc / L_rr.  One block barrier per step; row_j travels
-// through a double-buffered 64-entry shared vector laid out by column group.
-#define MEDGP_DIAG_THREADS 256
+// through a double-buffered 64-entry shared vector laid out by column parity (16-byte
+// broadcast reads).  To keep the code inside the instruction cache only 8 steps are unrolled:
+// after each panel of 8 columns the register file is rotated by 4 slots, so the pivot columns
+// always sit in W[0..3] and every register index stays static:
+//      during panel p, W[pos] holds column c = 2*((pos + 4p) mod 32) + g.
+#define MEDGP_DIAG_THREADS 128
 
-__device__ __forceinline__ void potf2_inv_gj(double (&W)[16], int r, int g, double *rowbuf /*2x64*/,
+// shared scratch: d[2][2*32] (column j of D by parity), y[2][2][64] (row j of Y in the rotated
+// slot coordinates of its owner, per parity), rs[2] = 1/sqrt(pivot)
+struct GjBufs {
+    double d[2][MEDGP_NB];
+    double y[2][2][MEDGP_NB];
+    double rs[2];
+};
+
+// 1/sqrt(d) of a pivot, flagging non-positive pivots (LAPACK potrf: info > 0; also NaN)
+__device__ __forceinline__ double pivot_rsqrt(double d, int *s_fail)
+{
+    if (!(d > 0.0)) {
+        *s_fail = 1;
+        d = 1.0;
+    }
+    return rsqrt(d);
+}
+
+__device__ __forceinline__ void potf2_inv_gj(double (&W)[32], int r, int g, GjBufs *gb,
                                              double *sL /*pitch SLD*/, int *s_fail)
 {
+    const int rslot = (r & 1) * 32 + (r >> 1);
+    // 1/sqrt of the NEXT pivot is computed by its owner during the previous update sweep, off
+    // the critical path; the first one here.
+    double rs_next = (r == 0 && g == 0) ? pivot_rsqrt(W[0], s_fail) : 0.0;
+#pragma unroll 1
+    for (int p = 0; p < 8; p++) {
+        const int base = 4 * p;  // W[pos] holds column 2*((pos + base) mod 32) + g
 #pragma unroll
-    for (int j = 0; j < MEDGP_NB; j++) {
-        const int gj = j & 3, sj = j >> 2;
-        double *rb = rowbuf + (j & 1) * MEDGP_NB;
-        // publish row j: column-j owners write D_rj (r >= j) at the slot of column r ...
-        if (g == gj && r >= j) rb[(r & 3) * 16 + (r >> 2)] = W[sj];
-        // ... and the four owners of row j write Y_jc, c < j
-        if (r == j) {
+        for (int jj = 0; jj < 8; jj++) {
+            const int j = 8 * p + jj;
+            const int gj = jj & 1, pj = jj >> 1;  // static: parity and register slot of column j
+            const int gn = (jj + 1) & 1, pn = (jj + 1) >> 1;  // ... and of column j + 1
+            double *db = gb->d[jj & 1];
+            double *yb = gb->y[jj & 1][g];
+            if (g == gj && r >= j) db[rslot] = W[pj];  // column j of D: D_rj, r >= j
+            if (r == j) {                              // row j of Y (all 32 slots, rotated coords)
+                if (g == gj) gb->rs[jj & 1] = rs_next;
 #pragma unroll
-            for (int s = 0; s < 16; s++)
-                if (4 * s + g < j) rb[g * 16 + s] = W[s];
-        }
-        __syncthreads();
-        if (r >= j) {
-            double d = rb[gj * 16 + sj];
-            if (!(d > 0.0)) {  // LAPACK potrf: info > 0 (also catches NaN)
-                *s_fail = 1;
-                d = 1.0;
+                for (int pos = 0; pos < 32; pos += 2)
+                    *reinterpret_cast<double2 *>(yb + base + pos) = make_double2(W[pos], W[pos + 1]);
             }
-            const double ar = rb[(r & 3) * 16 + (r >> 2)];
-            if (g == gj) sL[j * MEDGP_SLD + r] = ar * rsqrt(d);  // L_rj (r == j: sqrt(d))
-            if (r > j) {
-                const double ard = ar / d;
+            __syncthreads();
+            if (r >= j) {
+                const double rs = gb->rs[jj & 1];
+                const double l = db[rslot] * rs;  // L_rj = a_r / sqrt(d)   (r == j: sqrt(d))
+                if (g == gj) sL[j * MEDGP_SLD + r] = l;
+                if (r > j) {
+                    const double nard = -l * rs;  // -a_r / d
+                    const double *dsrc = db + g * 32 + base;  // future columns: D_cj
+                    const double *ysrc = yb + base;           // past columns:   Y_jc
+                    // slots 0..3: the current panel (columns 8p + 2 pos + g), per-slot choice
+                    {
+                        const double2 d0 = *reinterpret_cast<const double2 *>(dsrc);
+                        const double2 d1 = *reinterpret_cast<const double2 *>(dsrc + 2);
+                        const double2 y0 = *reinterpret_cast<const double2 *>(ysrc);
+                        const double2 y1 = *reinterpret_cast<const double2 *>(ysrc + 2);
+                        const double dv[4] = {d0.x, d0.y, d1.x, d1.y};
+                        const double yv[4] = {y0.x, y0.y, y1.x, y1.y};
 #pragma unroll
-                for (int s = 0; s < 16; s++) {
-                    const int c = 4 * s + g;
-                    if (c <= r) {
-                        if (s == sj && g == gj) W[s] = -ard;
-                        else W[s] = fma(-ard, rb[g * 16 + s], W[s]);
+                        for (int pos = 0; pos < 4; pos++) {
+                            const double v = (2 * pos + g < jj) ? yv[pos] : dv[pos];
+                            W[pos] = fma(nard, v, W[pos]);
+                        }
+                        if (g == gj) W[pj] = nard;
+                    }
+                    // slot group 1 first: for jj == 7 it holds the next pivot
+                    {
+                        const double *sp = (1 >= 8 - p) ? ysrc : dsrc;
+                        const double2 v0 = *reinterpret_cast<const double2 *>(sp + 4);
+                        const double2 v1 = *reinterpret_cast<const double2 *>(sp + 6);
+                        W[4] = fma(nard, v0.x, W[4]);
+                        W[5] = fma(nard, v0.y, W[5]);
+                        W[6] = fma(nard, v1.x, W[6]);
+                        W[7] = fma(nard, v1.y, W[7]);
+                    }
+                    // the owner of pivot j+1 starts its 1/sqrt now; the remaining updates hide it
+                    if (r == j + 1 && g == gn) rs_next = pivot_rsqrt(W[jj == 7 ? 4 : pn], s_fail);
+#pragma unroll
+                    for (int q = 2; q < 8; q++) {
+                        const double *sp = (q >= 8 - p) ? ysrc : dsrc;
+                        const double2 v0 = *reinterpret_cast<const double2 *>(sp + 4 * q);
+                        const double2 v1 = *reinterpret_cast<const double2 *>(sp + 4 * q + 2);
+                        W[4 * q] = fma(nard, v0.x, W[4 * q]);
+                        W[4 * q + 1] = fma(nard, v0.y, W[4 * q + 1]);
+                        W[4 * q + 2] = fma(nard, v1.x, W[4 * q + 2]);
+                        W[4 * q + 3] = fma(nard, v1.y, W[4 * q + 3]);
                     }
                 }
             }
         }
+        // rotate the register file by 4 slots
+        const double t0 = W[0], t1 = W[1], t2 = W[2], t3 = W[3];
+#pragma unroll
+        for (int pos = 0; pos < 28; pos++) W[pos] = W[pos + 4];
+        W[28] = t0; W[29] = t1; W[30] = t2; W[31] = t3;
     }
 }
 
 // One CTA per evaluation: D = K_kk - sum_{l<k} L_kl L_kl^T ; L_kk = chol(D) ; X_kk = inv(L_kk).
 // Writes L_kk (lower part of the tile), dinv[k], dinvT[k], blk[k] = sum log diag(L_kk) and
 // raises fail[] when a pivot is not positive.
-__global__ void __launch_bounds__(MEDGP_DIAG_THREADS, 2)
+__global__ void __launch_bounds__(MEDGP_DIAG_THREADS, 3)
 k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail)
 {
     extern __shared__ __align__(128) double smem[];
     __shared__ GemmBars bars;
-    __shared__ double rowbuf[2 * MEDGP_NB];
+    __shared__ __align__(16) GjBufs gjb;
     __shared__ int s_fail;
     const EvalDesc &e = descs[blockIdx.x];
     if (k >= e.T) return;
-    const int ld = e.npad, tid = threadIdx.x;
+    const int T = e.T, tid = threadIdx.x;
     gemm_bars_init(&bars);
     if (tid == 0) s_fail = 0;
     double *M = e.M;
     double *sD = smem, *sL = smem + kTileElems;
-    if (tid < MEDGP_GEMM_THREADS) {
+    {
         double acc[4][4][2];
         acc_zero(acc);
         gemm_nt_tiles(acc, k,
-                      [&](int l, const double *&A, int &lda, const double *&B, int &ldb) {
-                          A = tile_ptr(M, ld, k, l);
+                      [&](int l, const double *&A, const double *&B) {
+                          A = tile_ptr(M, T, k, l);
                           B = A;
-                          lda = ldb = ld;
                       },
                       smem, &bars);
-        // the 4 GEMM warps must all be done with the ring before it is reused as sD
-        asm volatile("bar.sync 1, %0;" ::"n"(MEDGP_GEMM_THREADS));
+        __syncthreads();  // all warps are done with the ring before it is reused as sD
         acc_to_smem(acc, sD, 1.0);
     }
     __syncthreads();
     const int r = tid & 63, g = tid >> 6;
-    const double *Kkk = tile_ptr(M, ld, k, k);
-    double W[16];
+    const double *Kkk = tile_ptr(M, T, k, k);
+    double W[32];
 #pragma unroll
-    for (int s = 0; s < 16; s++) {
-        const int c = 4 * s + g;
-        W[s] = (c <= r) ? Kkk[(size_t)c * ld + r] - sD[c * MEDGP_SLD + r] : 0.0;
+    for (int s = 0; s < 32; s++) {
+        const int c = 2 * s + g;
+        W[s] = (c <= r) ? Kkk[c * MEDGP_SLD + r] - sD[c * MEDGP_SLD + r] : 0.0;
     }
     __syncthreads();  // sD is dead from here on: it becomes the staging tile for X
-    potf2_inv_gj(W, r, g, rowbuf, sL, &s_fail);
+    potf2_inv_gj(W, r, g, &gjb, sL, &s_fail);
     __syncthreads();
     const double lrr_inv = 1.0 / sL[r * MEDGP_SLD + r];
 #pragma unroll
-    for (int s = 0; s < 16; s++) {
-        const int c = 4 * s + g;
+    for (int s = 0; s < 32; s++) {
+        const int c = 2 * s + g;
         const double x = (c < r) ? W[s] * lrr_inv : (c == r ? lrr_inv : 0.0);
         sD[c * MEDGP_SLD + r] = x;  // X(r, c)
     }
     __syncthreads();
     // write back: L_kk (lower), dinv (X column-major), dinvT (X^T column-major)
-    double *Lkk = tile_ptr(M, ld, k, k);
-    double *Xk = e.dinv + (size_t)k * MEDGP_NB * MEDGP_NB;
-    double *XTk = e.dinvT + (size_t)k * MEDGP_NB * MEDGP_NB;
+    double *Lkk = tile_ptr(M, T, k, k);
+    double *Xk = e.dinv + (size_t)k * kTileElems;
+    double *XTk = e.dinvT + (size_t)k * kTileElems;
     for (int idx = tid; idx < MEDGP_NB * MEDGP_NB; idx += blockDim.x) {
         const int c = idx >> 6, rr = idx & 63;
-        if (rr >= c) Lkk[(size_t)c * ld + rr] = sL[c * MEDGP_SLD + rr];
-        Xk[c * MEDGP_NB + rr] = sD[c * MEDGP_SLD + rr];   // X(rr, c)
-        XTk[c * MEDGP_NB + rr] = sD[rr * MEDGP_SLD + c];  // X^T(rr, c) = X(c, rr)
+        if (rr >= c) Lkk[c * MEDGP_SLD + rr] = sL[c * MEDGP_SLD + rr];
+        Xk[c * MEDGP_SLD + rr] = sD[c * MEDGP_SLD + rr];   // X(rr, c)
+        XTk[c * MEDGP_SLD + rr] = sD[rr * MEDGP_SLD + c];  // X^T(rr, c) = X(c, rr)
     }
     if (tid < 32) {
         double s = log(sL[tid * MEDGP_SLD + tid]) + log(sL[(tid + 32) * MEDGP_SLD + tid + 32]);
@@ -161,27 +223,26 @@ k_potrf_panel(const EvalDesc *__restrict__ descs, int k)
     const EvalDesc &e = descs[blockIdx.y];
     const int i = k + 1 + blockIdx.x;
     if (i >= e.T) return;
-    const int ld = e.npad;
+    const int T = e.T;
     gemm_bars_init(&bars);
     double acc[4][4][2];
     acc_zero(acc);
     double *M = e.M;
     gemm_nt_tiles(acc, k,
-                  [&](int l, const double *&A, int &lda, const double *&B, int &ldb) {
-                      A = tile_ptr(M, ld, i, l);
-                      B = tile_ptr(M, ld, k, l);
-                      lda = ldb = ld;
+                  [&](int l, const double *&A, const double *&B) {
+                      A = tile_ptr(M, T, i, l);
+                      B = tile_ptr(M, T, k, l);
                   },
                   smem, &bars);
-    double *Tik = tile_ptr(M, ld, i, k);
-    acc_rsub_global(acc, Tik, ld);
+    double *Tik = tile_ptr(M, T, i, k);
+    acc_rsub_global(acc, Tik);
     __syncthreads();  // every warp is done with the pipeline buffers
     double *sP = smem, *sX = smem + kTileElems;
     acc_to_smem(acc, sP, 1.0);
-    tile_g2s_plain(sX, e.dinv + (size_t)k * MEDGP_NB * MEDGP_NB, MEDGP_NB);
+    tile_g2s_plain(sX, e.dinv + (size_t)k * kTileElems);
     __syncthreads();
     gemm2_smem(acc, sP, sX);
-    acc_to_global(acc, Tik, ld);
+    acc_to_global(acc, Tik);
 }
 
 // ------------------------------------------------------------------ trtri: block row i of L^-1
@@ -194,28 +255,26 @@ k_trtri_row(const EvalDesc *__restrict__ descs, int i)
     const EvalDesc &e = descs[blockIdx.y];
     const int j = blockIdx.x;
     if (i >= e.T || j >= i) return;
-    const int ld = e.npad;
+    const int T = e.T;
     gemm_bars_init(&bars);
     double acc[4][4][2];
     acc_zero(acc);
     double *M = e.M;
-    const double *XTj = e.dinvT + (size_t)j * MEDGP_NB * MEDGP_NB;
+    const double *XTj = e.dinvT + (size_t)j * kTileElems;
     gemm_nt_tiles(acc, i - j,
-                  [&](int l0, const double *&A, int &lda, const double *&B, int &ldb) {
+                  [&](int l0, const double *&A, const double *&B) {
                       const int l = j + l0;
-                      if (l0 == 0) { A = XTj; lda = MEDGP_NB; }
-                      else { A = tile_ptr(M, ld, j, l); lda = ld; }
-                      B = tile_ptr(M, ld, i, l);
-                      ldb = ld;
+                      A = (l0 == 0) ? XTj : tile_ptr(M, T, j, l);
+                      B = tile_ptr(M, T, i, l);
                   },
                   smem, &bars);
     __syncthreads();
     double *sP = smem, *sX = smem + kTileElems;
     acc_to_smem(acc, sP, -1.0);
-    tile_g2s_plain(sX, e.dinv + (size_t)i * MEDGP_NB * MEDGP_NB, MEDGP_NB);
+    tile_g2s_plain(sX, e.dinv + (size_t)i * kTileElems);
     __syncthreads();
     gemm2_smem(acc, sP, sX);
-    acc_to_global(acc, tile_ptr(M, ld, j, i), ld);
+    acc_to_global(acc, tile_ptr(M, T, j, i));
 }
 
 // lower-triangle tile enumeration: p -> (ti, tj), ti >= tj, row by row
@@ -239,22 +298,20 @@ k_lauum(const EvalDesc *__restrict__ descs)
     int i, j;
     tri_index(blockIdx.x, i, j);
     if (i >= e.T) return;
-    const int ld = e.npad;
+    const int T = e.T;
     gemm_bars_init(&bars);
     double acc[4][4][2];
     acc_zero(acc);
     double *M = e.M;
-    const double *XTi = e.dinvT + (size_t)i * MEDGP_NB * MEDGP_NB;
-    gemm_nt_tiles(acc, e.T - i,
-                  [&](int l0, const double *&A, int &lda, const double *&B, int &ldb) {
+    const double *XTi = e.dinvT + (size_t)i * kTileElems;
+    gemm_nt_tiles(acc, T - i,
+                  [&](int l0, const double *&A, const double *&B) {
                       const int l = i + l0;
-                      if (l0 == 0) { A = XTi; lda = MEDGP_NB; }
-                      else { A = tile_ptr(M, ld, i, l); lda = ld; }
-                      if (l == j) { B = XTi; ldb = MEDGP_NB; }  // only when i == j == l
-                      else { B = tile_ptr(M, ld, j, l); ldb = ld; }
+                      A = (l0 == 0) ? XTi : tile_ptr(M, T, i, l);
+                      B = (l == j) ? XTi : tile_ptr(M, T, j, l);  // l == j only when i == j == l
                   },
                   smem, &bars);
-    acc_to_global(acc, tile_ptr(M, ld, i, j), ld);
+    acc_to_global(acc, tile_ptr(M, T, i, j));
 }
 
 // ------------------------------------------------------------------ forward solves + NLML
@@ -267,14 +324,14 @@ __device__ __forceinline__ void fwd_solve_group(const EvalDesc &e, double *rhs0,
     const int ld = e.npad, tid = threadIdx.x, T = e.T;
     for (int k = 0; k < T; k++) {
         // z_k = X_kk * rhs_k : 256 threads = 64 rows x 4 column slices
-        const double *Xk = e.dinv + (size_t)k * MEDGP_NB * MEDGP_NB;
+        const double *Xk = e.dinv + (size_t)k * kTileElems;
         const int r = tid & 63, sl = tid >> 6;
         double part[NR];
 #pragma unroll
         for (int q = 0; q < NR; q++) part[q] = 0.0;
         for (int c = sl * 16; c < sl * 16 + 16; c++) {
             if (c > r) break;
-            const double xv = Xk[c * MEDGP_NB + r];
+            const double xv = Xk[c * MEDGP_SLD + r];
 #pragma unroll
             for (int q = 0; q < NR; q++) part[q] += xv * rhs0[(size_t)q * ld + k * MEDGP_NB + c];
         }
@@ -292,14 +349,14 @@ __device__ __forceinline__ void fwd_solve_group(const EvalDesc &e, double *rhs0,
         }
         __syncthreads();
         // rows below: rhs_i -= sum_c L(i, 64k + c) z_c
-        const double *Lcol = e.M + (size_t)k * MEDGP_NB * ld;
         for (int i = (k + 1) * MEDGP_NB + tid; i < ld; i += blockDim.x) {
+            const double *Lrow = e.M + tile_off(T, i >> 6, k) + (i & 63);
             double s[NR];
 #pragma unroll
             for (int q = 0; q < NR; q++) s[q] = 0.0;
 #pragma unroll 8
             for (int c = 0; c < MEDGP_NB; c++) {
-                const double lv = Lcol[(size_t)c * ld + i];
+                const double lv = Lrow[c * MEDGP_SLD];
 #pragma unroll
                 for (int q = 0; q < NR; q++) s[q] += lv * sz[(NR * 4 + q) * MEDGP_NB + c];
             }
@@ -356,12 +413,12 @@ k_alpha(const EvalDesc *__restrict__ descs)
     const double *z = e.rhs;
     double s = 0.0;
     // diagonal block: U_jj = X_jj^T
-    const double *XT = e.dinvT + (size_t)j * MEDGP_NB * MEDGP_NB;
+    const double *XT = e.dinvT + (size_t)j * kTileElems;
     for (int c = sl * 16; c < sl * 16 + 16; c++)
-        if (c >= r) s += XT[c * MEDGP_NB + r] * z[j * MEDGP_NB + c];
+        if (c >= r) s += XT[c * MEDGP_SLD + r] * z[j * MEDGP_NB + c];
     // strictly upper tiles (j, l), l > j : columns split over the 4 slices
-    const double *Urow = e.M + (size_t)j * MEDGP_NB + r;
-    for (int c = (j + 1) * MEDGP_NB + sl; c < ld; c += 4) s += Urow[(size_t)c * ld] * z[c];
+    for (int c = (j + 1) * MEDGP_NB + sl; c < ld; c += 4)
+        s += e.M[tile_off(e.T, j, c >> 6) + (c & 63) * MEDGP_SLD + r] * z[c];
     sp[sl * MEDGP_NB + r] = s;
     __syncthreads();
     if (tid < MEDGP_NB)

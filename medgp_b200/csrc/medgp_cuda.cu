@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -67,6 +68,10 @@ struct medgp_ctx {
     double *d_star_t = nullptr;
     int *d_star_meta = nullptr;
     size_t star_cap = 0;
+    // sub-chunk streams (fork/join around the context's stream)
+    int max_streams = 1;
+    cudaStream_t sub_streams[8] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
     // profiling
     bool profile = false;
     std::vector<StageMark> marks;
@@ -107,8 +112,8 @@ size_t eval_bytes(const ModelDims &md, const Series &s, int nrhs, bool grad)
 {
     const size_t np = s.npad;
     size_t b = 0;
-    b += align_up(np * np * 8, 256);                       // M
-    b += 2 * align_up(np * MEDGP_NB * 8, 256);             // dinv, dinvT
+    b += align_up((size_t)s.T * s.T * kTileElems * 8, 256);   // M (tile-major)
+    b += 2 * align_up((size_t)s.T * kTileElems * 8, 256);     // dinv, dinvT
     b += align_up(np * (size_t)nrhs * 8, 256);             // rhs
     b += align_up(np * 8, 256);                            // alpha
     b += align_up(np * (size_t)md.Q * 16, 256);            // cs
@@ -182,18 +187,19 @@ struct StageScope {
     medgp_ctx *ctx;
     int stage;
     cudaEvent_t a = nullptr;
-    StageScope(medgp_ctx *c, int s) : ctx(c), stage(s)
+    cudaStream_t st;
+    StageScope(medgp_ctx *c, int s, cudaStream_t stream) : ctx(c), stage(s), st(stream)
     {
         if (ctx->profile) {
             a = get_event(ctx);
-            cudaEventRecord(a, ctx->stream);
+            cudaEventRecord(a, st);
         }
     }
     ~StageScope()
     {
         if (ctx->profile) {
             cudaEvent_t b = get_event(ctx);
-            cudaEventRecord(b, ctx->stream);
+            cudaEventRecord(b, st);
             ctx->marks.push_back({stage, a, b});
         }
     }
@@ -210,8 +216,122 @@ void resolve_marks(medgp_ctx *ctx)
     ctx->marks.clear();
 }
 
+// One sub-chunk = a contiguous descriptor range launched on one stream.
+struct SubChunk {
+    size_t base = 0, cnt = 0;
+    int Tmax = 0, items_max = 0, nstar_max = 0;
+    std::vector<int> T;  // per evaluation, descending
+    unsigned act(int k) const  // evaluations with T > k (a prefix: sorted descending)
+    {
+        size_t lo = 0, hi = cnt;
+        while (lo < hi) {
+            const size_t mid = (lo + hi) / 2;
+            if (T[mid] > k) lo = mid + 1; else hi = mid;
+        }
+        return (unsigned)lo;
+    }
+};
+
+template <int QT>
+void launch_grad_q(dim3 gg, cudaStream_t st, const EvalDesc *dd, const ModelDims &md)
+{
+    k_grad<QT><<<gg, 128, 0, st>>>(dd, md);
+}
+
+void launch_grad(int Q, dim3 gg, cudaStream_t st, const EvalDesc *dd, const ModelDims &md)
+{
+    switch (Q) {
+        case 1: launch_grad_q<1>(gg, st, dd, md); break;
+        case 2: launch_grad_q<2>(gg, st, dd, md); break;
+        case 3: launch_grad_q<3>(gg, st, dd, md); break;
+        case 4: launch_grad_q<4>(gg, st, dd, md); break;
+        case 5: launch_grad_q<5>(gg, st, dd, md); break;
+        case 6: launch_grad_q<6>(gg, st, dd, md); break;
+        case 7: launch_grad_q<7>(gg, st, dd, md); break;
+        default: launch_grad_q<8>(gg, st, dd, md); break;
+    }
+}
+
+// the stage sequence of one sub-chunk on stream st
+void launch_sub(medgp_ctx *ctx, const SubChunk &sc, cudaStream_t st, const double *d_theta, int mode,
+                double *d_nlml, double *d_grad, int *d_status, double *d_mean, double *d_var)
+{
+    const ModelDims &md = ctx->md;
+    const bool grad = (mode == 1), pred = (mode == 2);
+    const int gemm_smem = kGemmSmemBytes;
+    const int asm_smem = (md.Q * md.D * md.D + md.Q) * 8;
+    const int npairs = md.D * (md.D + 1) / 2;
+    const int fin_smem = (md.Q * md.D * md.D + 2 * npairs * md.Q + md.D) * 8;
+    const EvalDesc *dd = ctx->d_descs + sc.base;
+    const unsigned ncta = (unsigned)sc.cnt;
+    const int Tmax = sc.Tmax, ntri = Tmax * (Tmax + 1) / 2;
+    auto &L = ctx->times.launches;
+    {
+        StageScope sp(ctx, MEDGP_STAGE_PREP, st);
+        k_prep<<<ncta, 256, 0, st>>>(dd, md, d_theta);
+        L[MEDGP_STAGE_PREP]++;
+    }
+    {
+        StageScope sp(ctx, MEDGP_STAGE_ASSEMBLE, st);
+        k_assemble<<<dim3(ntri, ncta), 256, asm_smem, st>>>(dd, md);
+        L[MEDGP_STAGE_ASSEMBLE]++;
+    }
+    {
+        StageScope sp(ctx, MEDGP_STAGE_POTRF, st);
+        for (int k = 0; k < Tmax; k++) {
+            k_potrf_diag<<<sc.act(k), MEDGP_DIAG_THREADS, gemm_smem, st>>>(dd, k, ctx->d_fail);
+            L[MEDGP_STAGE_POTRF]++;
+            if (k + 1 < Tmax) {
+                k_potrf_panel<<<dim3(Tmax - k - 1, sc.act(k + 1)), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k);
+                L[MEDGP_STAGE_POTRF]++;
+            }
+        }
+    }
+    if (pred && sc.nstar_max > 0) {
+        StageScope sp(ctx, MEDGP_STAGE_PREDICT, st);
+        k_cross<<<dim3(sc.nstar_max, ncta), 256, 0, st>>>(dd, md);
+        L[MEDGP_STAGE_PREDICT]++;
+    }
+    {
+        StageScope sp(ctx, MEDGP_STAGE_SOLVE, st);
+        k_solve<<<ncta, 256, 0, st>>>(dd, md, d_nlml, d_status, ctx->d_fail);
+        L[MEDGP_STAGE_SOLVE]++;
+    }
+    if (grad) {
+        {
+            StageScope sp(ctx, MEDGP_STAGE_TRTRI, st);
+            for (int i = 1; i < Tmax; i++) {
+                k_trtri_row<<<dim3(i, sc.act(i)), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, i);
+                L[MEDGP_STAGE_TRTRI]++;
+            }
+            k_alpha<<<dim3(Tmax, ncta), 256, 0, st>>>(dd);
+            L[MEDGP_STAGE_TRTRI]++;
+        }
+        {
+            StageScope sp(ctx, MEDGP_STAGE_LAUUM, st);
+            k_lauum<<<dim3(ntri, ncta), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd);
+            L[MEDGP_STAGE_LAUUM]++;
+        }
+        {
+            StageScope sp(ctx, MEDGP_STAGE_GRAD, st);
+            launch_grad(md.Q, dim3((sc.items_max + 3) / 4, ncta), st, dd, md);
+            k_grad_finish<<<ncta, 256, fin_smem, st>>>(dd, md, d_grad, ctx->d_fail);
+            L[MEDGP_STAGE_GRAD] += 2;
+        }
+    }
+    if (pred && sc.nstar_max > 0) {
+        StageScope sp(ctx, MEDGP_STAGE_PREDICT, st);
+        k_pred_finish<<<dim3(sc.nstar_max, ncta), 256, 0, st>>>(dd, md, d_mean, d_var, ctx->d_fail);
+        L[MEDGP_STAGE_PREDICT]++;
+    }
+}
+
 // The core: run `reqs` (any sizes) through the stage sequence.  d_theta is indexed by
 // out_index.  mode: 0 = NLML only, 1 = NLML + gradient, 2 = prediction.
+// Evaluations are sorted by size, cut into chunks that fit the arena, and every chunk is dealt
+// round-robin into up to kMaxStreams sub-chunks that run on their own streams, so the
+// latency-bound phases of one sub-chunk (diagonal blocks, small trtri rows, tails) overlap the
+// tensor-core phases of the others.
 int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, int mode,
               double *d_nlml, double *d_grad, int *d_status, double *d_mean, double *d_var,
               size_t desc_base)
@@ -222,11 +342,6 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
     std::stable_sort(reqs.begin(), reqs.end(), [&](const Request &a, const Request &b) {
         return ctx->series[a.series].npad > ctx->series[b.series].npad;
     });
-    const int gemm_smem = kGemmSmemBytes;
-    const int asm_smem = (md.Q * md.D * md.D + md.Q) * 8;
-    const int npairs = md.D * (md.D + 1) / 2;
-    const int fin_smem = (md.Q * md.D * md.D + 2 * npairs * md.Q + md.D) * 8;
-
     size_t pos = 0, dpos = desc_base;
     while (pos < reqs.size()) {
         // ---- form a chunk
@@ -244,133 +359,79 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
             ctx->err = "workspace too small for one evaluation";
             return MEDGP_ERR_NOMEM;
         }
-        // ---- carve the arena and fill descriptors
+        // ---- deal the chunk into sub-chunks (one stream each)
+        const int Tbig = ctx->series[reqs[first].series].T;
+        int S = 1;
+        if (!ctx->profile && ctx->max_streams > 1) {
+            S = Tbig >= 16 ? (int)std::min<size_t>(cnt, ctx->max_streams)
+                           : (int)std::min<size_t>(std::max<size_t>(1, cnt / 32), ctx->max_streams);
+        }
+        std::vector<SubChunk> subs(S);
+        // ---- carve the arena and fill descriptors, sub-chunk major
         char *p = ctx->arena;
         auto take = [&](size_t bytes) {
             char *r = p;
             p += align_up(bytes, 256);
             return r;
         };
-        int Tmax = 0, items_max = 0, nstar_max = 0;
-        for (size_t c = 0; c < cnt; c++) {
-            const Request &rq = reqs[first + c];
-            const Series &s = ctx->series[rq.series];
-            EvalDesc &e = ctx->h_descs[dpos + c];
-            const size_t np = s.npad;
-            e.M = (double *)take(np * np * 8);
-            e.dinv = (double *)take(np * MEDGP_NB * 8);
-            e.dinvT = (double *)take(np * MEDGP_NB * 8);
-            e.rhs = (double *)take(np * (size_t)(1 + rq.nstar) * 8);
-            e.alpha = (double *)take(np * 8);
-            e.cs = (double *)take(np * (size_t)md.Q * 16);
-            e.par = (double *)take((size_t)md.parLen * 8);
-            e.blk = (double *)take((size_t)s.T * 8);
-            e.part = grad ? (double *)take((size_t)s.nitems * (3 * md.Q + 1) * 8) : nullptr;
-            e.t = s.d_t; e.y = s.d_y; e.meta = s.d_meta; e.off = s.d_off;
-            e.items = s.d_items; e.pair_start = s.d_pair_start;
-            e.star_t = pred ? ctx->d_star_t + rq.star_off : nullptr;
-            e.star_meta = pred ? ctx->d_star_meta + rq.star_off : nullptr;
-            e.n = s.n; e.npad = s.npad; e.T = s.T; e.nitems = s.nitems;
-            e.jitter = rq.jitter; e.nrhs = 1 + rq.nstar; e.nstar = rq.nstar;
-            e.out_index = rq.out_index; e.star_out = rq.star_off;
-            e.pad0 = e.pad1 = e.pad2 = 0;
-            Tmax = std::max(Tmax, s.T);
-            items_max = std::max(items_max, s.nitems);
-            nstar_max = std::max(nstar_max, rq.nstar);
-            // algorithmic work
-            const double n = s.n;
-            ctx->times.flops[MEDGP_STAGE_POTRF] += n * n * n / 3.0;
-            ctx->times.flops[MEDGP_STAGE_SOLVE] += n * n * (1 + rq.nstar);
-            ctx->times.bytes[MEDGP_STAGE_ASSEMBLE] += 8.0 * n * (n + 1) / 2 + 12.0 * n;
-            if (grad) {
-                ctx->times.flops[MEDGP_STAGE_TRTRI] += n * n * n / 3.0;
-                ctx->times.flops[MEDGP_STAGE_LAUUM] += n * n * n / 3.0;
-                ctx->times.bytes[MEDGP_STAGE_GRAD] += 8.0 * n * (n + 1) / 2 + 8.0 * md.P;
+        size_t dcur = dpos;
+        for (int sidx = 0; sidx < S; sidx++) {
+            SubChunk &sc = subs[sidx];
+            sc.base = dcur;
+            for (size_t c = sidx; c < cnt; c += S) {
+                const Request &rq = reqs[first + c];
+                const Series &s = ctx->series[rq.series];
+                EvalDesc &e = ctx->h_descs[dcur++];
+                const size_t np = s.npad;
+                e.M = (double *)take((size_t)s.T * s.T * kTileElems * 8);
+                e.dinv = (double *)take((size_t)s.T * kTileElems * 8);
+                e.dinvT = (double *)take((size_t)s.T * kTileElems * 8);
+                e.rhs = (double *)take(np * (size_t)(1 + rq.nstar) * 8);
+                e.alpha = (double *)take(np * 8);
+                e.cs = (double *)take(np * (size_t)md.Q * 16);
+                e.par = (double *)take((size_t)md.parLen * 8);
+                e.blk = (double *)take((size_t)s.T * 8);
+                e.part = grad ? (double *)take((size_t)s.nitems * (3 * md.Q + 1) * 8) : nullptr;
+                e.t = s.d_t; e.y = s.d_y; e.meta = s.d_meta; e.off = s.d_off;
+                e.items = s.d_items; e.pair_start = s.d_pair_start;
+                e.star_t = pred ? ctx->d_star_t + rq.star_off : nullptr;
+                e.star_meta = pred ? ctx->d_star_meta + rq.star_off : nullptr;
+                e.n = s.n; e.npad = s.npad; e.T = s.T; e.nitems = s.nitems;
+                e.jitter = rq.jitter; e.nrhs = 1 + rq.nstar; e.nstar = rq.nstar;
+                e.out_index = rq.out_index; e.star_out = rq.star_off;
+                e.pad0 = e.pad1 = e.pad2 = 0;
+                sc.T.push_back(s.T);
+                sc.cnt++;
+                sc.Tmax = std::max(sc.Tmax, s.T);
+                sc.items_max = std::max(sc.items_max, s.nitems);
+                sc.nstar_max = std::max(sc.nstar_max, rq.nstar);
+                // algorithmic work
+                const double n = s.n;
+                ctx->times.flops[MEDGP_STAGE_POTRF] += n * n * n / 3.0;
+                ctx->times.flops[MEDGP_STAGE_SOLVE] += n * n * (1 + rq.nstar);
+                ctx->times.bytes[MEDGP_STAGE_ASSEMBLE] += 8.0 * n * (n + 1) / 2 + 12.0 * n;
+                if (grad) {
+                    ctx->times.flops[MEDGP_STAGE_TRTRI] += n * n * n / 3.0;
+                    ctx->times.flops[MEDGP_STAGE_LAUUM] += n * n * n / 3.0;
+                    ctx->times.bytes[MEDGP_STAGE_GRAD] += 8.0 * n * (n + 1) / 2 + 8.0 * md.P;
+                }
+                if (pred) ctx->times.bytes[MEDGP_STAGE_PREDICT] += rq.nstar * (8.0 * n * (n + 1) / 2 + 8.0 * n);
+                ctx->times.evals++;
             }
-            if (pred) ctx->times.bytes[MEDGP_STAGE_PREDICT] += rq.nstar * (8.0 * n * (n + 1) / 2 + 8.0 * n);
-            ctx->times.evals++;
         }
-        const EvalDesc *dd = ctx->d_descs + dpos;
         CU(cudaMemcpyAsync(ctx->d_descs + dpos, ctx->h_descs + dpos, cnt * sizeof(EvalDesc),
                            cudaMemcpyHostToDevice, st));
-        // evaluations are sorted by T descending: the first act(k) of them have T > k
-        auto act = [&](int k) {
-            size_t lo = 0, hi = cnt;
-            while (lo < hi) {
-                const size_t mid = (lo + hi) / 2;
-                if (ctx->series[reqs[first + mid].series].T > k) lo = mid + 1; else hi = mid;
+        if (S == 1) {
+            launch_sub(ctx, subs[0], st, d_theta, mode, d_nlml, d_grad, d_status, d_mean, d_var);
+        } else {
+            CU(cudaEventRecord(ctx->ev_fork, st));
+            for (int sidx = 0; sidx < S; sidx++) {
+                cudaStream_t ss = ctx->sub_streams[sidx];
+                CU(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
+                launch_sub(ctx, subs[sidx], ss, d_theta, mode, d_nlml, d_grad, d_status, d_mean, d_var);
+                CU(cudaEventRecord(ctx->ev_join[sidx], ss));
             }
-            return (unsigned)lo;
-        };
-        const unsigned ncta = (unsigned)cnt;
-        const int ntri = Tmax * (Tmax + 1) / 2;
-        {
-            StageScope sc(ctx, MEDGP_STAGE_PREP);
-            k_prep<<<ncta, 256, 0, st>>>(dd, md, d_theta);
-            ctx->times.launches[MEDGP_STAGE_PREP]++;
-        }
-        {
-            StageScope sc(ctx, MEDGP_STAGE_ASSEMBLE);
-            k_assemble<<<dim3(ntri, ncta), 256, asm_smem, st>>>(dd, md);
-            ctx->times.launches[MEDGP_STAGE_ASSEMBLE]++;
-        }
-        {
-            StageScope sc(ctx, MEDGP_STAGE_POTRF);
-            for (int k = 0; k < Tmax; k++) {
-                k_potrf_diag<<<act(k), MEDGP_DIAG_THREADS, gemm_smem, st>>>(dd, k, ctx->d_fail);
-                ctx->times.launches[MEDGP_STAGE_POTRF]++;
-                if (k + 1 < Tmax) {
-                    k_potrf_panel<<<dim3(Tmax - k - 1, act(k + 1)), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k);
-                    ctx->times.launches[MEDGP_STAGE_POTRF]++;
-                }
-            }
-        }
-        if (pred && nstar_max > 0) {
-            StageScope sc(ctx, MEDGP_STAGE_PREDICT);
-            k_cross<<<dim3(nstar_max, ncta), 256, 0, st>>>(dd, md);
-            ctx->times.launches[MEDGP_STAGE_PREDICT]++;
-        }
-        {
-            StageScope sc(ctx, MEDGP_STAGE_SOLVE);
-            k_solve<<<ncta, 256, 0, st>>>(dd, md, d_nlml, d_status, ctx->d_fail);
-            ctx->times.launches[MEDGP_STAGE_SOLVE]++;
-        }
-        if (grad) {
-            {
-                StageScope sc(ctx, MEDGP_STAGE_TRTRI);
-                for (int i = 1; i < Tmax; i++) {
-                    k_trtri_row<<<dim3(i, act(i)), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, i);
-                    ctx->times.launches[MEDGP_STAGE_TRTRI]++;
-                }
-                k_alpha<<<dim3(Tmax, ncta), 256, 0, st>>>(dd);
-                ctx->times.launches[MEDGP_STAGE_TRTRI]++;
-            }
-            {
-                StageScope sc(ctx, MEDGP_STAGE_LAUUM);
-                k_lauum<<<dim3(ntri, ncta), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd);
-                ctx->times.launches[MEDGP_STAGE_LAUUM]++;
-            }
-            {
-                StageScope sc(ctx, MEDGP_STAGE_GRAD);
-                const dim3 gg((items_max + 3) / 4, ncta);
-                switch (md.Q) {
-                    case 1: k_grad<1><<<gg, 128, 0, st>>>(dd, md); break;
-                    case 2: k_grad<2><<<gg, 128, 0, st>>>(dd, md); break;
-                    case 3: k_grad<3><<<gg, 128, 0, st>>>(dd, md); break;
-                    case 4: k_grad<4><<<gg, 128, 0, st>>>(dd, md); break;
-                    case 5: k_grad<5><<<gg, 128, 0, st>>>(dd, md); break;
-                    case 6: k_grad<6><<<gg, 128, 0, st>>>(dd, md); break;
-                    case 7: k_grad<7><<<gg, 128, 0, st>>>(dd, md); break;
-                    default: k_grad<8><<<gg, 128, 0, st>>>(dd, md); break;
-                }
-                k_grad_finish<<<ncta, 256, fin_smem, st>>>(dd, md, d_grad, ctx->d_fail);
-                ctx->times.launches[MEDGP_STAGE_GRAD] += 2;
-            }
-        }
-        if (pred && nstar_max > 0) {
-            StageScope sc(ctx, MEDGP_STAGE_PREDICT);
-            k_pred_finish<<<dim3(nstar_max, ncta), 256, 0, st>>>(dd, md, d_mean, d_var, ctx->d_fail);
-            ctx->times.launches[MEDGP_STAGE_PREDICT]++;
+            for (int sidx = 0; sidx < S; sidx++) CU(cudaStreamWaitEvent(st, ctx->ev_join[sidx], 0));
         }
         CU(cudaGetLastError());
         dpos += cnt;
@@ -428,6 +489,13 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
         return MEDGP_ERR_NOMEM;
     }
     ctx->arena_bytes = workspace_bytes;
+    ctx->max_streams = 8;
+    if (const char *ev = getenv("MEDGP_STREAMS")) ctx->max_streams = std::max(1, std::min(8, atoi(ev)));
+    for (int i = 0; i < 8; i++) {
+        cudaStreamCreateWithFlags(&ctx->sub_streams[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
     cudaFuncSetAttribute(k_potrf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
     cudaFuncSetAttribute(k_trtri_row, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
@@ -445,6 +513,11 @@ MEDGP_API void medgp_cuda_destroy(medgp_ctx *ctx)
         if (s.alive) free_series_mem(s);
     resolve_marks(ctx);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 8; i++) {
+        if (ctx->sub_streams[i]) cudaStreamDestroy(ctx->sub_streams[i]);
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     cudaFree(ctx->arena);
     cudaFreeHost(ctx->h_descs); cudaFree(ctx->d_descs);
     cudaFreeHost(ctx->h_theta); cudaFree(ctx->d_theta);
@@ -738,11 +811,14 @@ MEDGP_API int medgp_cuda_debug_matrices(medgp_ctx *ctx, int series_id, const dou
     cudaStream_t st = ctx->stream;
     const size_t np = s.npad, n = s.n;
     CU(cudaMemcpyAsync(ctx->d_theta, theta, (size_t)md.P * 8, cudaMemcpyHostToDevice, st));
-    std::vector<double> hM(np * np), ha(np);
+    std::vector<double> hM(np * np), ha(np), hT((size_t)s.T * s.T * kTileElems);
     auto fetch = [&]() -> int {
-        // the single evaluation's M is the first arena allocation
-        CU(cudaMemcpyAsync(hM.data(), ctx->arena, np * np * 8, cudaMemcpyDeviceToHost, st));
+        // the single evaluation's M is the first arena allocation; convert tile-major ->
+        // plain column-major (ld = np)
+        CU(cudaMemcpyAsync(hT.data(), ctx->arena, hT.size() * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        for (size_t j = 0; j < np; j++)
+            for (size_t i = 0; i < np; i++) hM[j * np + i] = hT[elem_off(s.T, (int)i, (int)j)];
         return MEDGP_OK;
     };
     std::vector<Request> one = {{series_id, 0, 0, 0, 0}};
