@@ -1,0 +1,255 @@
+// main_one_test -- online one-step-ahead imputation of one patient, with and without online
+// hyper-parameter updates (same CLI, semantics and output files as the reference's
+// medgpc/src/main_one_test.cpp:45-480).
+//   main_one_test --cfg exp_setup.json --pan <PAN> --thread <T> --fold <F> --kernclust-alg <A>
+// Every held-out observation (tt, jj) trains on past + same-time observations and predicts
+// one point.  Without updates theta is fixed, so ALL training sets of the patient are
+// independent and go to the GPU in batches; with updates theta moves at each update time, so
+// the batch is the set of held-out points of one time stamp.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+
+#include "c_experiment.h"
+#include "medgp_host.h"
+
+using std::cout;
+using std::endl;
+using std::string;
+using std::vector;
+
+#define CMD_NUM 11
+
+static double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+namespace {
+struct HeldOut {            // one imputation task
+    vector<int> meta;       // training set
+    vector<float> time, value;
+    int test_meta;
+    float test_time, test_value, stamp;
+};
+
+// predicts every task with `theta`; fills pred / ok.  Tasks without training data stay !ok.
+void predict_tasks(medgp_ctx *ctx, const vector<double> &theta, const vector<HeldOut> &tasks, size_t b, size_t e,
+                   vector<double> &mean, vector<double> &var, vector<int> &status)
+{
+    const size_t B = e - b;
+    vector<int> sids, offs(1, 0), mstar;
+    vector<float> xstar;
+    vector<double> thetas;
+    vector<size_t> which;
+    for (size_t k = b; k < e; k++) {
+        status[k] = -1;
+        if (tasks[k].time.empty()) continue;
+        int id = -1;
+        if (medgp_cuda_add_series(ctx, (int)tasks[k].time.size(), (const int32_t *)tasks[k].meta.data(),
+                                  tasks[k].time.data(), tasks[k].value.data(), &id) != MEDGP_OK) {
+            std::cerr << "ERROR: medgp_cuda_add_series: " << medgp_cuda_last_error(ctx) << endl;
+            exit(1);
+        }
+        sids.push_back(id);
+        which.push_back(k);
+        mstar.push_back(tasks[k].test_meta);
+        xstar.push_back(tasks[k].test_time);
+        offs.push_back((int)mstar.size());
+        thetas.insert(thetas.end(), theta.begin(), theta.end());
+    }
+    (void)B;
+    if (sids.empty()) return;
+    vector<double> m(sids.size()), v(sids.size());
+    vector<int> st(sids.size());
+    if (medgp_cuda_predict(ctx, (int)sids.size(), sids.data(), thetas.data(), offs.data(), mstar.data(),
+                           xstar.data(), m.data(), v.data(), st.data()) != MEDGP_OK) {
+        std::cerr << "ERROR: medgp_cuda_predict: " << medgp_cuda_last_error(ctx) << endl;
+        exit(1);
+    }
+    for (size_t q = 0; q < sids.size(); q++) {
+        mean[which[q]] = (double)(float)m[q];  // the reference returns float moments
+        var[which[q]] = (double)(float)v[q];
+        status[which[q]] = st[q];
+        medgp_cuda_free_series(ctx, sids[q]);
+    }
+}
+}  // namespace
+
+static void run_test_one(c_experiment &curr_exp, const string &PAN, int fold, bool flag_update,
+                         const string &output_prefix, const string &kernel_clust_alg, c_kernel *&kptr,
+                         c_meanfunc *&mptr, c_likelihood *&lptr, c_inference *&iptr, c_prior *&pptr)
+{
+    cout << "running online imputation: " << (flag_update ? "with" : "without") << " online updating" << endl
+         << "testing patinet: " << PAN << " in cross-validation fold " << fold << endl;
+    const vector<int> test_kernel_param = curr_exp.get_test_kernel_param(fold, kernel_clust_alg);
+    vector<int> meta_array;
+    vector<float> time_array, value_array;
+    curr_exp.get_one_patient_data(PAN, meta_array, time_array, value_array);
+    cout << "number of data points = " << time_array.size() << endl;
+    const double t1 = now_s();
+    bool test_flag = true;
+    if (time_array.empty()) {
+        cout << "Warning: no samples for testing" << endl;
+        test_flag = false;
+    } else {
+        vector<float> unique_time_array(time_array);
+        std::sort(unique_time_array.begin(), unique_time_array.end());
+        unique_time_array.erase(std::unique(unique_time_array.begin(), unique_time_array.end()), unique_time_array.end());
+        cout << "total # of unique time stamps: " << unique_time_array.size() << endl;
+        const double learn_rate = curr_exp.get_online_learn_rate(), momentum = curr_exp.get_online_momentum();
+        const vector<double> mode_parameter = curr_exp.get_test_mode_param(fold, kernel_clust_alg);
+        vector<double> best_parameter(mode_parameter), delta_parameter(mode_parameter.size(), 0.0);
+        pptr->init_test_prior(curr_exp.get_kernel_index(), test_kernel_param, mode_parameter);
+        medgp_ctx *ctx = medgp_backend::context(test_kernel_param[0], test_kernel_param[1], test_kernel_param[2]);
+
+        vector<HeldOut> tasks;          // in the reference's output order (tt major, jj minor)
+        vector<double> mean, var;
+        vector<int> status;
+        vector<vector<double> > theta_of_task;  // only with updates
+        float last_update_time = unique_time_array[0];
+        for (int tt = 0; tt < (int)unique_time_array.size(); tt++) {
+            const float stamp = unique_time_array[tt];
+            vector<int> past_m, curr_m;
+            vector<float> past_t, past_v, curr_t, curr_v;
+            for (size_t ii = 0; ii < time_array.size(); ii++) {
+                if (time_array[ii] < stamp) {
+                    if (!flag_update || fabs(time_array[ii] - stamp) <= 72.0) {  // 72 h history with updates
+                        past_m.push_back(meta_array[ii]);
+                        past_t.push_back(time_array[ii]);
+                        past_v.push_back(value_array[ii]);
+                    }
+                } else if (time_array[ii] == stamp) {
+                    curr_m.push_back(meta_array[ii]);
+                    curr_t.push_back(time_array[ii]);
+                    curr_v.push_back(value_array[ii]);
+                }
+            }
+            if (flag_update && (tt > 3) && (stamp - last_update_time) > 5.0 / 60.0) {
+                // one momentum-SGD step on the past window (main_one_test.cpp:309-348)
+                last_update_time = stamp;
+                c_objective_one curr_objfunc(curr_exp.get_kernel_index(), test_kernel_param, past_m, past_t, past_v);
+                double best_loss;
+                vector<double> best_grads;
+                const bool obj_flag = curr_objfunc.compute_objective(true, best_parameter, best_loss, best_grads,
+                                                                     kptr, mptr, lptr, iptr, pptr);
+                if (obj_flag) {
+                    for (size_t h = 0; h < mode_parameter.size(); h++) {
+                        const bool prior_flag = pptr->get_one_prior_flag((int)h);
+                        const int prior_type = pptr->get_one_prior_type((int)h);
+                        if ((!prior_flag) | (prior_type != 0)) {
+                            delta_parameter[h] = momentum * delta_parameter[h] + learn_rate * best_grads[h];
+                            best_parameter[h] -= delta_parameter[h];
+                        }
+                    }
+                } else {
+                    cout << "Warning: failed to update at t[" << tt << "] = " << stamp << "; reset to mode parameters" << endl;
+                    best_parameter = mode_parameter;
+                    std::fill(delta_parameter.begin(), delta_parameter.end(), 0.0);
+                }
+            }
+            const size_t first_task = tasks.size();
+            for (size_t jj = 0; jj < curr_t.size(); jj++) {
+                HeldOut h;
+                h.meta = past_m; h.time = past_t; h.value = past_v;
+                for (size_t kk = 0; kk < curr_m.size(); kk++)
+                    if (kk != jj) {  // same-time observations of other covariates join the training set
+                        h.meta.push_back(curr_m[kk]);
+                        h.time.push_back(curr_t[kk]);
+                        h.value.push_back(curr_v[kk]);
+                    }
+                h.test_meta = curr_m[jj]; h.test_time = curr_t[jj]; h.test_value = curr_v[jj]; h.stamp = stamp;
+                tasks.push_back(h);
+            }
+            mean.resize(tasks.size(), 0.0);
+            var.resize(tasks.size(), 0.0);
+            status.resize(tasks.size(), -1);
+            if (flag_update) predict_tasks(ctx, best_parameter, tasks, first_task, tasks.size(), mean, var, status);
+            if ((tt % 100) == 0) cout << "finish testing " << tt << "/" << unique_time_array.size() << " time stamps" << endl;
+        }
+        if (!flag_update) {
+            const size_t step = 512;  // training sets per library call
+            for (size_t b = 0; b < tasks.size(); b += step)
+                predict_tasks(ctx, best_parameter, tasks, b, std::min(tasks.size(), b + step), mean, var, status);
+        }
+        vector<int> out_feature, out_ci;
+        vector<double> out_etime, out_error, out_pred;
+        for (size_t k = 0; k < tasks.size(); k++) {
+            double impute_error;
+            int ci;
+            if (status[k] >= 0) {
+                out_pred.push_back(mean[k]);
+                impute_error = (float)mean[k] - tasks[k].test_value;
+                ci = fabs(impute_error) <= 1.96 * sqrt(var[k]) ? 1 : 0;
+            } else {
+                // no training data or factorisation failure: zero-mean fallback (main_one_test.cpp:411-438)
+                cout << "Warning: predict with zero mean for task " << k << endl;
+                out_pred.push_back(0.0);
+                impute_error = 0.0 - tasks[k].test_value;
+                const double prior_var = exp(mode_parameter[tasks[k].test_meta]);
+                ci = fabs(impute_error) <= 1.96 * prior_var ? 1 : 0;
+            }
+            out_error.push_back(impute_error);
+            out_ci.push_back(ci);
+            out_feature.push_back(curr_exp.get_feature_index()[tasks[k].test_meta]);
+            out_etime.push_back(tasks[k].test_time - tasks[k].stamp);
+        }
+        if (!out_pred.empty()) {
+            const string prefix = curr_exp.get_exp_test_dir() + "test_" + output_prefix + "_";
+            curr_exp.output_int_txt(prefix + "feature_" + PAN, out_feature);
+            curr_exp.output_double_bin(prefix + "etime_" + PAN, out_etime);
+            curr_exp.output_int_txt(prefix + "ci_" + PAN, out_ci);
+            curr_exp.output_double_bin(prefix + "error_" + PAN, out_error);
+            curr_exp.output_double_bin(prefix + "pred_" + PAN, out_pred);
+        }
+    }
+    curr_exp.output_int_txt(curr_exp.get_exp_test_dir() + "test_" + output_prefix + "_flag_" + PAN,
+                            vector<int>(1, (int)test_flag));
+    cout << "finish (" << output_prefix << ") testing individual PAN " << PAN << " w/ " << time_array.size()
+         << " samples; flag = " << test_flag << "; elapsed time = " << now_s() - t1 << " seconds" << endl;
+}
+
+int main(int argc, const char *argv[])
+{
+    if (argc != CMD_NUM) {
+        cout << "ERROR: incorrect number of argument received!" << endl
+             << "expect " << CMD_NUM << " but received " << argc << endl
+             << "usage:\n\t --cfg\t --pan\t --thread\t --fold\t --kernclust-alg" << endl;
+        return 1;
+    }
+    string exp_cfg, patient_PAN, kernel_clust_alg;
+    int thread_num = 1, patient_fold = 0;
+    for (int i = 1; i < argc; i++) {
+        if (!strcmp(argv[i], "--cfg")) exp_cfg = argv[++i];
+        else if (!strcmp(argv[i], "--pan")) patient_PAN = argv[++i];
+        else if (!strcmp(argv[i], "--thread")) thread_num = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--fold")) patient_fold = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--kernclust-alg")) kernel_clust_alg = argv[++i];
+        else { cout << "Error: unknown argument: " << argv[i] << endl; return 1; }
+    }
+    c_experiment curr_exp(exp_cfg);
+    if (curr_exp.get_kernel_index() != 7) {
+        cout << "Error: not supported kernel type " << curr_exp.get_kernel_index() << " (GPU backend: LMC-SM only)" << endl;
+        return 1;
+    }
+    const double t1 = now_s();
+    const vector<int> test_kernel_param = curr_exp.get_test_kernel_param(patient_fold, kernel_clust_alg);
+    cout << "# of mixture for testing: " << test_kernel_param[0] << endl;
+    c_kernel_LMC_SM kernel(test_kernel_param);
+    c_inference_prior inffunc(thread_num);
+    c_meanfunc_zero meanfunc;
+    c_likelihood_gaussianMO likfunc(curr_exp.get_lik_param());
+    c_prior prior(curr_exp.get_test_cov_num(patient_fold, kernel_clust_alg), curr_exp.get_mean_num(), curr_exp.get_lik_num());
+    c_kernel *kptr = &kernel;
+    c_meanfunc *mptr = &meanfunc;
+    c_likelihood *lptr = &likfunc;
+    c_inference *iptr = &inffunc;
+    c_prior *pptr = &prior;
+    run_test_one(curr_exp, patient_PAN, patient_fold, false, "mean_wo_update", kernel_clust_alg, kptr, mptr, lptr, iptr, pptr);
+    run_test_one(curr_exp, patient_PAN, patient_fold, true, "mean_w_update", kernel_clust_alg, kptr, mptr, lptr, iptr, pptr);
+    cout << "Finish all jobs. Total elapsed time = " << now_s() - t1 << " seconds" << endl;
+    medgp_backend::shutdown();
+    return 0;
+}
