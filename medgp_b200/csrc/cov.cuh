@@ -51,6 +51,7 @@ k_prep(const EvalDesc *__restrict__ descs, ModelDims md, const double *__restric
         par[md.oBdiag + d] = s;  // prior variance of feature d (kernel/c_kernel_LMC_SM.cpp:137-144)
     }
     const int npad = e.npad;
+    for (int i = tid; i < npad; i += blockDim.x) e.rhs[i] = (i < e.n) ? e.y[i] : 0.0;  // rhs row 0 = y
     for (int idx = tid; idx < Q * npad; idx += blockDim.x) {
         const int q = idx / npad, i = idx - q * npad;
         double sn = 0.0, cs = 1.0;
@@ -100,6 +101,13 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
     const int mr = s_mr[r];
     const double jit = 1.0 + (double)e.jitter;
     double *out = e.M + tile_off(e.T, ti, tj) + r;
+    // row-side data stays in registers for the 16 columns this thread produces
+    double2 arow[MEDGP_QMAX];
+#pragma unroll
+    for (int q = 0; q < MEDGP_QMAX; q++)
+        if (q < Q) arow[q] = s_csr[q][r];
+    const double *brow = sB + mr * D;  // + q*D*D + mc
+    const int DD = D * D;
 #pragma unroll 2
     for (int u = 0; u < 16; u++) {
         const int c = g * 16 + u, gj = tj * MEDGP_NB + c;
@@ -109,12 +117,15 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
             val = (gi == gj) ? 1.0 : 0.0;
         } else {
             const double tau = tr - s_tc[c], tau2 = tau * tau;
-            const int mc = s_mc[c];
+            const double *bq = brow + s_mc[c];
             val = 0.0;
-            for (int q = 0; q < Q; q++) {
-                const double2 a = s_csr[q][r], b = s_csc[q][c];
-                const double cosphi = a.x * b.x + a.y * b.y;
-                val += sB[(q * D + mr) * D + mc] * cosphi * exp(-sC[q] * tau2);
+#pragma unroll
+            for (int q = 0; q < MEDGP_QMAX; q++) {
+                if (q < Q) {
+                    const double2 b = s_csc[q][c];
+                    const double cosphi = arow[q].x * b.x + arow[q].y * b.y;
+                    val += bq[q * DD] * cosphi * exp(-sC[q] * tau2);
+                }
             }
             if (gi == gj) val += jit * e.par[md.oSig2 + mr];
         }

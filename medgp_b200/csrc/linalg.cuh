@@ -23,8 +23,49 @@ __device__ __forceinline__ void gemm2_smem(double (&acc)[4][4][2], const double 
                                            const double *sX)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wn = warp >> 1;
     acc_zero(acc);
-    mma_panels(acc, sP, sX, MEDGP_NB / 4, warp & 1, warp >> 1, lane);
+    // X(n, c) = 0 for c > n: output columns 0..31 (wn == 0) only need the first 32 k-steps
+    mma_panels(acc, sP, sX, wn == 0 ? MEDGP_NB / 8 : MEDGP_NB / 4, warp & 1, wn, lane);
+}
+
+// lower-triangle tile enumeration: p -> (ti, tj), ti >= tj, row by row
+__device__ __forceinline__ void tri_index(int p, int &ti, int &tj)
+{
+    int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= p) i++;
+    while (i * (i + 1) / 2 > p) i--;
+    ti = i;
+    tj = p - i * (i + 1) / 2;
+}
+
+// ------------------------------------------------------------------ fused forward solve
+// The triangular solve z = L^-1 rhs rides on the factorisation: the diagonal kernel of step k
+// turns the already-updated block rhs_k into z_k = X_kk rhs_k, and every panel CTA (i, k)
+// pushes its fresh tile into the rows below, rhs_i -= L_ik z_k.  All right-hand sides of the
+// evaluation (row 0 = y, rows 1.. = cross-covariance columns) are carried along.
+// sTile: pitch-SLD tile in smem holding the operator (element (r, c) at c*SLD + r);
+// 128 threads: r = tid & 63, half = tid >> 6 splits the columns by parity.
+__device__ __forceinline__ void tile_matvec_rhs(const EvalDesc &e, const double *sTile, const double *vec_base,
+                                                double *out_base, bool lower_only, bool subtract,
+                                                double *red /*2*64*/)
+{
+    const int tid = threadIdx.x, r = tid & 63, half = tid >> 6, ld = e.npad;
+    for (int q = 0; q < e.nrhs; q++) {
+        const double *v = vec_base + (size_t)q * ld;
+        double s = 0.0;
+        const int cmax = lower_only ? r : MEDGP_NB - 1;
+#pragma unroll 4
+        for (int c = half; c <= cmax; c += 2) s += sTile[c * MEDGP_SLD + r] * v[c];
+        red[half * MEDGP_NB + r] = s;
+        __syncthreads();
+        if (half == 0) {
+            const double tot = red[r] + red[MEDGP_NB + r];
+            double *o = out_base + (size_t)q * ld;
+            o[r] = subtract ? o[r] - tot : tot;
+        }
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------ potrf: diagonal block k
@@ -147,7 +188,7 @@ __device__ __forceinline__ void potf2_inv_gj(double (&W)[32], int r, int g, GjBu
 // Writes L_kk (lower part of the tile), dinv[k], dinvT[k], blk[k] = sum log diag(L_kk) and
 // raises fail[] when a pivot is not positive.
 __global__ void __launch_bounds__(MEDGP_DIAG_THREADS, 3)
-k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail)
+k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int depth, int *__restrict__ fail)
 {
     extern __shared__ __align__(128) double smem[];
     __shared__ GemmBars bars;
@@ -163,7 +204,7 @@ k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail)
     {
         double acc[4][4][2];
         acc_zero(acc);
-        gemm_nt_tiles(acc, k,
+        gemm_nt_tiles(acc, depth,
                       [&](int l, const double *&A, const double *&B) {
                           A = tile_ptr(M, T, k, l);
                           B = A;
@@ -192,6 +233,8 @@ k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail)
         sD[c * MEDGP_SLD + r] = x;  // X(r, c)
     }
     __syncthreads();
+    // forward solve, block k: z_k = X_kk rhs_k (in place)
+    tile_matvec_rhs(e, sD, e.rhs + k * MEDGP_NB, e.rhs + k * MEDGP_NB, true, false, gjb.d[0]);
     // write back: L_kk (lower), dinv (X column-major), dinvT (X^T column-major)
     double *Lkk = tile_ptr(M, T, k, k);
     double *Xk = e.dinv + (size_t)k * kTileElems;
@@ -216,7 +259,7 @@ k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail)
 // ------------------------------------------------------------------ potrf: panel below block k
 // grid (row tiles i > k, evaluations): L_ik = (K_ik - sum_{l<k} L_il L_kl^T) X_kk^T
 __global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
-k_potrf_panel(const EvalDesc *__restrict__ descs, int k)
+k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_diag)
 {
     extern __shared__ __align__(128) double smem[];
     __shared__ GemmBars bars;
@@ -228,7 +271,7 @@ k_potrf_panel(const EvalDesc *__restrict__ descs, int k)
     double acc[4][4][2];
     acc_zero(acc);
     double *M = e.M;
-    gemm_nt_tiles(acc, k,
+    gemm_nt_tiles(acc, depth,
                   [&](int l, const double *&A, const double *&B) {
                       A = tile_ptr(M, T, i, l);
                       B = tile_ptr(M, T, k, l);
@@ -243,12 +286,27 @@ k_potrf_panel(const EvalDesc *__restrict__ descs, int k)
     __syncthreads();
     gemm2_smem(acc, sP, sX);
     acc_to_global(acc, Tik);
+    // forward solve: push the fresh tile into the right-hand sides of block row i
+    __syncthreads();  // GEMM2 is done reading sP / sX everywhere
+    acc_to_smem(acc, sP, 1.0);
+    __syncthreads();
+    tile_matvec_rhs(e, sP, e.rhs + k * MEDGP_NB, e.rhs + i * MEDGP_NB, false, true, sX);
+    if (fold_diag) {
+        // few matrices in flight: apply this tile to its diagonal block right away,
+        // K_ii -= L_ik L_ik^T, so that the (single-CTA) diagonal kernel has no product to do
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        acc_zero(acc);
+        mma_panels(acc, sP, sP, MEDGP_NB / 4, warp & 1, warp >> 1, lane);
+        double *Kii = tile_ptr(M, T, i, i);
+        acc_rsub_global(acc, Kii);
+        acc_to_global(acc, Kii);
+    }
 }
 
 // ------------------------------------------------------------------ trtri: block row i of L^-1
 // grid (j < i, evaluations): U_ji = -(sum_{l=j}^{i-1} U_jl L_il^T) X_ii^T, U_jj = X_jj^T
 __global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
-k_trtri_row(const EvalDesc *__restrict__ descs, int i)
+k_trtri_row(const EvalDesc *__restrict__ descs, int i, int right_looking)
 {
     extern __shared__ __align__(128) double smem[];
     __shared__ GemmBars bars;
@@ -261,13 +319,18 @@ k_trtri_row(const EvalDesc *__restrict__ descs, int i)
     acc_zero(acc);
     double *M = e.M;
     const double *XTj = e.dinvT + (size_t)j * kTileElems;
-    gemm_nt_tiles(acc, i - j,
-                  [&](int l0, const double *&A, const double *&B) {
-                      const int l = j + l0;
-                      A = (l0 == 0) ? XTj : tile_ptr(M, T, j, l);
-                      B = tile_ptr(M, T, i, l);
-                  },
-                  smem, &bars);
+    if (right_looking) {
+        // the sum was accumulated into tile (j, i) by k_trtri_update
+        acc_rsub_global(acc, tile_ptr(M, T, j, i));
+    } else {
+        gemm_nt_tiles(acc, i - j,
+                      [&](int l0, const double *&A, const double *&B) {
+                          const int l = j + l0;
+                          A = (l0 == 0) ? XTj : tile_ptr(M, T, j, l);
+                          B = tile_ptr(M, T, i, l);
+                      },
+                      smem, &bars);
+    }
     __syncthreads();
     double *sP = smem, *sX = smem + kTileElems;
     acc_to_smem(acc, sP, -1.0);
@@ -277,14 +340,72 @@ k_trtri_row(const EvalDesc *__restrict__ descs, int i)
     acc_to_global(acc, tile_ptr(M, T, j, i));
 }
 
-// lower-triangle tile enumeration: p -> (ti, tj), ti >= tj, row by row
-__device__ __forceinline__ void tri_index(int p, int &ti, int &tj)
+// ------------------------------------------------------------------ right-looking variants
+// For few, large matrices the left-looking panel has too few CTAs per launch ((T-k-1) per
+// matrix, each k tiles deep).  The right-looking form exposes (T-k)^2/2 independent one-tile
+// products per step instead, at the price of re-reading the trailing tiles T times:
+//   potrf:  K_ij -= L_ik L_jk^T            for k < j <= i      (k_syrk_update, after step k)
+//   trtri:  Acc_ji (+)= U_jk L_ik^T        for j <= k < i      (k_trtri_update), then
+//           U_j,k+1 = -Acc_j,k+1 X_k+1^T                       (k_trtri_row, right_looking = 1)
+__global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
+k_syrk_update(const EvalDesc *__restrict__ descs, int k)
 {
-    int i = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
-    while ((i + 1) * (i + 2) / 2 <= p) i++;
-    while (i * (i + 1) / 2 > p) i--;
-    ti = i;
-    tj = p - i * (i + 1) / 2;
+    extern __shared__ __align__(128) double smem[];
+    __shared__ GemmBars bars;
+    const EvalDesc &e = descs[blockIdx.y];
+    int a, b;
+    tri_index(blockIdx.x, a, b);
+    const int i = k + 1 + a, j = k + 1 + b, T = e.T;
+    if (i >= T) return;
+    gemm_bars_init(&bars);
+    double acc[4][4][2];
+    acc_zero(acc);
+    double *M = e.M;
+    gemm_nt_tiles(acc, 1,
+                  [&](int, const double *&A, const double *&B) {
+                      A = tile_ptr(M, T, i, k);
+                      B = tile_ptr(M, T, j, k);
+                  },
+                  smem, &bars);
+    double *Cij = tile_ptr(M, T, i, j);
+    acc_rsub_global(acc, Cij);
+    acc_to_global(acc, Cij);
+}
+
+__global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
+k_trtri_update(const EvalDesc *__restrict__ descs, int k)
+{
+    extern __shared__ __align__(128) double smem[];
+    __shared__ GemmBars bars;
+    const EvalDesc &e = descs[blockIdx.y];
+    const int T = e.T;
+    const int j = blockIdx.x % (k + 1), i = k + 1 + blockIdx.x / (k + 1);
+    if (i >= T) return;
+    gemm_bars_init(&bars);
+    double acc[4][4][2];
+    acc_zero(acc);
+    double *M = e.M;
+    const double *XTk = e.dinvT + (size_t)k * kTileElems;
+    gemm_nt_tiles(acc, 1,
+                  [&](int, const double *&A, const double *&B) {
+                      A = (j == k) ? XTk : tile_ptr(M, T, j, k);  // U_jk (U_kk = X_kk^T)
+                      B = tile_ptr(M, T, i, k);                   // L_ik
+                  },
+                  smem, &bars);
+    double *Aji = tile_ptr(M, T, j, i);
+    if (j != k) {  // first touch (j == k) initialises the accumulator tile
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int wm = warp & 1, wn = warp >> 1, r = lane >> 2, kq = lane & 3;
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+#pragma unroll
+            for (int y = 0; y < 4; y++) {
+                const int row = wm * 32 + 8 * x + r, col = wn * 32 + 8 * y + 2 * kq;
+                acc[x][y][0] += Aji[col * MEDGP_SLD + row];
+                acc[x][y][1] += Aji[(col + 1) * MEDGP_SLD + row];
+            }
+    }
+    acc_to_global(acc, Aji);
 }
 
 // ------------------------------------------------------------------ lauum: K^-1 lower tiles
@@ -314,80 +435,16 @@ k_lauum(const EvalDesc *__restrict__ descs)
     acc_to_global(acc, tile_ptr(M, T, i, j));
 }
 
-// ------------------------------------------------------------------ forward solves + NLML
-// One CTA per evaluation.  rhs rows r (0..nrhs): v_r = L^-1 rhs_r by blocked forward
-// substitution (diagonal blocks through X_kk).  Then, for row 0 (= y):
+// ------------------------------------------------------------------ NLML
+// One CTA per evaluation, after the factorisation (which carried the forward solve along):
 //   nlml = 1/2 z^T z + sum log L_ii + n log(2 PI)/2     (c_inference_exact.cpp:118-120,146-152)
-template <int NR>
-__device__ __forceinline__ void fwd_solve_group(const EvalDesc &e, double *rhs0, double *sz)
-{
-    const int ld = e.npad, tid = threadIdx.x, T = e.T;
-    for (int k = 0; k < T; k++) {
-        // z_k = X_kk * rhs_k : 256 threads = 64 rows x 4 column slices
-        const double *Xk = e.dinv + (size_t)k * kTileElems;
-        const int r = tid & 63, sl = tid >> 6;
-        double part[NR];
-#pragma unroll
-        for (int q = 0; q < NR; q++) part[q] = 0.0;
-        for (int c = sl * 16; c < sl * 16 + 16; c++) {
-            if (c > r) break;
-            const double xv = Xk[c * MEDGP_SLD + r];
-#pragma unroll
-            for (int q = 0; q < NR; q++) part[q] += xv * rhs0[(size_t)q * ld + k * MEDGP_NB + c];
-        }
-#pragma unroll
-        for (int q = 0; q < NR; q++) sz[(q * 4 + sl) * MEDGP_NB + r] = part[q];
-        __syncthreads();
-        if (tid < MEDGP_NB) {
-#pragma unroll
-            for (int q = 0; q < NR; q++) {
-                const double z = sz[(q * 4 + 0) * MEDGP_NB + tid] + sz[(q * 4 + 1) * MEDGP_NB + tid] +
-                                 sz[(q * 4 + 2) * MEDGP_NB + tid] + sz[(q * 4 + 3) * MEDGP_NB + tid];
-                sz[(NR * 4 + q) * MEDGP_NB + tid] = z;
-                rhs0[(size_t)q * ld + k * MEDGP_NB + tid] = z;
-            }
-        }
-        __syncthreads();
-        // rows below: rhs_i -= sum_c L(i, 64k + c) z_c
-        for (int i = (k + 1) * MEDGP_NB + tid; i < ld; i += blockDim.x) {
-            const double *Lrow = e.M + tile_off(T, i >> 6, k) + (i & 63);
-            double s[NR];
-#pragma unroll
-            for (int q = 0; q < NR; q++) s[q] = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < MEDGP_NB; c++) {
-                const double lv = Lrow[c * MEDGP_SLD];
-#pragma unroll
-                for (int q = 0; q < NR; q++) s[q] += lv * sz[(NR * 4 + q) * MEDGP_NB + c];
-            }
-#pragma unroll
-            for (int q = 0; q < NR; q++) rhs0[(size_t)q * ld + i] -= s[q];
-        }
-        __syncthreads();
-    }
-}
-
 __global__ void __launch_bounds__(256)
 k_solve(const EvalDesc *__restrict__ descs, ModelDims md, double *__restrict__ out_nlml,
         int *__restrict__ out_status, const int *__restrict__ fail)
 {
-    __shared__ double sz[(4 * 4 + 4) * MEDGP_NB];
     __shared__ double scratch[64];
     const EvalDesc &e = descs[blockIdx.x];
     const int ld = e.npad, tid = threadIdx.x;
-    // rhs row 0 <- y (pad rows 0)
-    for (int i = tid; i < ld; i += blockDim.x) e.rhs[i] = (i < e.n) ? e.y[i] : 0.0;
-    __syncthreads();
-    int r0 = 0;
-    while (r0 < e.nrhs) {
-        const int g = min(4, e.nrhs - r0);
-        double *base = e.rhs + (size_t)r0 * ld;
-        if (g == 4) fwd_solve_group<4>(e, base, sz);
-        else if (g == 3) fwd_solve_group<3>(e, base, sz);
-        else if (g == 2) fwd_solve_group<2>(e, base, sz);
-        else fwd_solve_group<1>(e, base, sz);
-        r0 += g;
-    }
     double v[2] = {0.0, 0.0};
     for (int i = tid; i < ld; i += blockDim.x) v[0] += e.rhs[i] * e.rhs[i];
     for (int k = tid; k < e.T; k += blockDim.x) v[1] += e.blk[k];

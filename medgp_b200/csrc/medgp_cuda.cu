@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <map>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -47,6 +49,11 @@ struct StageMark {
     cudaEvent_t a, b;
 };
 
+struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    long long launches[MEDGP_STAGE_COUNT] = {};
+};
+
 }  // namespace
 
 struct medgp_ctx {
@@ -70,11 +77,14 @@ struct medgp_ctx {
     size_t star_cap = 0;
     // sub-chunk streams (fork/join around the context's stream)
     int max_streams = 1;
+    bool use_graphs = true;  // MEDGP_GRAPHS=0 disables CUDA-graph replay of chunk launch sequences
+    std::map<uint64_t, GraphEntry> graphs;
+    int force_rl = -1;  // MEDGP_RL=0/1 forces the left-/right-looking factorisation (experiments)
     cudaStream_t sub_streams[8] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
     // profiling
     bool profile = false;
-    std::vector<StageMark> marks;
+    std::vector<StageMark> marks, open_marks;
     std::vector<cudaEvent_t> event_pool;
     medgp_stage_times times{};
 };
@@ -183,27 +193,28 @@ cudaEvent_t get_event(medgp_ctx *ctx)
     return e;
 }
 
-struct StageScope {
-    medgp_ctx *ctx;
-    int stage;
-    cudaEvent_t a = nullptr;
-    cudaStream_t st;
-    StageScope(medgp_ctx *c, int s, cudaStream_t stream) : ctx(c), stage(s), st(stream)
-    {
-        if (ctx->profile) {
-            a = get_event(ctx);
-            cudaEventRecord(a, st);
+// per-stage CUDA events (profiling only): begin pushes the start event, end closes the mark
+void stage_begin(medgp_ctx *ctx, int stage, cudaStream_t st)
+{
+    if (!ctx->profile) return;
+    cudaEvent_t a = get_event(ctx);
+    cudaEventRecord(a, st);
+    ctx->open_marks.push_back({stage, a, nullptr});
+}
+
+void stage_end(medgp_ctx *ctx, int stage, cudaStream_t st)
+{
+    if (!ctx->profile) return;
+    for (size_t i = ctx->open_marks.size(); i-- > 0;)
+        if (ctx->open_marks[i].stage == stage) {
+            StageMark m = ctx->open_marks[i];
+            ctx->open_marks.erase(ctx->open_marks.begin() + i);
+            m.b = get_event(ctx);
+            cudaEventRecord(m.b, st);
+            ctx->marks.push_back(m);
+            return;
         }
-    }
-    ~StageScope()
-    {
-        if (ctx->profile) {
-            cudaEvent_t b = get_event(ctx);
-            cudaEventRecord(b, st);
-            ctx->marks.push_back({stage, a, b});
-        }
-    }
-};
+}
 
 void resolve_marks(medgp_ctx *ctx)
 {
@@ -252,11 +263,15 @@ void launch_grad(int Q, dim3 gg, cudaStream_t st, const EvalDesc *dd, const Mode
     }
 }
 
-// the stage sequence of one sub-chunk on stream st
-void launch_sub(medgp_ctx *ctx, const SubChunk &sc, cudaStream_t st, const double *d_theta, int mode,
-                double *d_nlml, double *d_grad, int *d_status, double *d_mean, double *d_var)
+// The stage sequence of one sub-chunk on stream st, as a list of launch closures so that the
+// caller can interleave the sub-chunks' launches round-robin (every stream starts at once
+// instead of waiting for the CPU to issue all launches of the streams before it).
+typedef std::vector<std::function<void()> > LaunchList;
+
+void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStream_t st, const double *d_theta, int mode,
+               double *d_nlml, double *d_grad, int *d_status, double *d_mean, double *d_var, LaunchList &out)
 {
-    const ModelDims &md = ctx->md;
+    const ModelDims md = ctx->md;
     const bool grad = (mode == 1), pred = (mode == 2);
     const int gemm_smem = kGemmSmemBytes;
     const int asm_smem = (md.Q * md.D * md.D + md.Q) * 8;
@@ -265,64 +280,70 @@ void launch_sub(medgp_ctx *ctx, const SubChunk &sc, cudaStream_t st, const doubl
     const EvalDesc *dd = ctx->d_descs + sc.base;
     const unsigned ncta = (unsigned)sc.cnt;
     const int Tmax = sc.Tmax, ntri = Tmax * (Tmax + 1) / 2;
-    auto &L = ctx->times.launches;
-    {
-        StageScope sp(ctx, MEDGP_STAGE_PREP, st);
-        k_prep<<<ncta, 256, 0, st>>>(dd, md, d_theta);
-        L[MEDGP_STAGE_PREP]++;
+    long long *L = ctx->times.launches;
+    int *d_fail = ctx->d_fail;
+    const SubChunk *scp = &sc;
+    // stage markers (profiling): begin/end closures record events on the stream
+    auto begin = [&](int stage) { out.push_back([=]() { stage_begin(ctx, stage, st); }); };
+    auto end = [&](int stage) { out.push_back([=]() { stage_end(ctx, stage, st); }); };
+
+    begin(MEDGP_STAGE_PREP);
+    out.push_back([=]() { k_prep<<<ncta, 256, 0, st>>>(dd, md, d_theta); L[MEDGP_STAGE_PREP]++; });
+    end(MEDGP_STAGE_PREP);
+    begin(MEDGP_STAGE_ASSEMBLE);
+    out.push_back([=]() { k_assemble<<<dim3(ntri, ncta), 256, asm_smem, st>>>(dd, md); L[MEDGP_STAGE_ASSEMBLE]++; });
+    end(MEDGP_STAGE_ASSEMBLE);
+    if (pred && sc.nstar_max > 0) {  // cross-covariance columns ride along the factorisation
+        const int nsm = sc.nstar_max;
+        begin(MEDGP_STAGE_PREDICT);
+        out.push_back([=]() { k_cross<<<dim3(nsm, ncta), 256, 0, st>>>(dd, md); L[MEDGP_STAGE_PREDICT]++; });
+        end(MEDGP_STAGE_PREDICT);
     }
-    {
-        StageScope sp(ctx, MEDGP_STAGE_ASSEMBLE, st);
-        k_assemble<<<dim3(ntri, ncta), 256, asm_smem, st>>>(dd, md);
-        L[MEDGP_STAGE_ASSEMBLE]++;
-    }
-    {
-        StageScope sp(ctx, MEDGP_STAGE_POTRF, st);
-        for (int k = 0; k < Tmax; k++) {
-            k_potrf_diag<<<sc.act(k), MEDGP_DIAG_THREADS, gemm_smem, st>>>(dd, k, ctx->d_fail);
-            L[MEDGP_STAGE_POTRF]++;
-            if (k + 1 < Tmax) {
-                k_potrf_panel<<<dim3(Tmax - k - 1, sc.act(k + 1)), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k);
-                L[MEDGP_STAGE_POTRF]++;
-            }
+    begin(MEDGP_STAGE_POTRF);
+    for (int k = 0; k < Tmax; k++) {
+        const unsigned a0 = sc.act(k), a1 = k + 1 < Tmax ? sc.act(k + 1) : 0;
+        const int depth = (rl || fold) ? 0 : k, rem = Tmax - k - 1;
+        const int pdepth = rl ? 0 : k, pfold = (!rl && fold) ? 1 : 0;
+        out.push_back([=]() { k_potrf_diag<<<a0, MEDGP_DIAG_THREADS, gemm_smem, st>>>(dd, k, depth, d_fail); L[MEDGP_STAGE_POTRF]++; });
+        if (rem > 0) {
+            out.push_back([=]() { k_potrf_panel<<<dim3(rem, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, pdepth, pfold); L[MEDGP_STAGE_POTRF]++; });
+            if (rl)
+                out.push_back([=]() { k_syrk_update<<<dim3(rem * (rem + 1) / 2, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k); L[MEDGP_STAGE_POTRF]++; });
         }
     }
-    if (pred && sc.nstar_max > 0) {
-        StageScope sp(ctx, MEDGP_STAGE_PREDICT, st);
-        k_cross<<<dim3(sc.nstar_max, ncta), 256, 0, st>>>(dd, md);
-        L[MEDGP_STAGE_PREDICT]++;
-    }
-    {
-        StageScope sp(ctx, MEDGP_STAGE_SOLVE, st);
-        k_solve<<<ncta, 256, 0, st>>>(dd, md, d_nlml, d_status, ctx->d_fail);
-        L[MEDGP_STAGE_SOLVE]++;
-    }
+    end(MEDGP_STAGE_POTRF);
+    begin(MEDGP_STAGE_SOLVE);
+    out.push_back([=]() { k_solve<<<ncta, 256, 0, st>>>(dd, md, d_nlml, d_status, d_fail); L[MEDGP_STAGE_SOLVE]++; });
+    end(MEDGP_STAGE_SOLVE);
     if (grad) {
-        {
-            StageScope sp(ctx, MEDGP_STAGE_TRTRI, st);
-            for (int i = 1; i < Tmax; i++) {
-                k_trtri_row<<<dim3(i, sc.act(i)), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, i);
-                L[MEDGP_STAGE_TRTRI]++;
+        begin(MEDGP_STAGE_TRTRI);
+        for (int i = 1; i < Tmax; i++) {
+            const unsigned ai = sc.act(i);
+            if (rl) {
+                const int k = i - 1;  // rows 0..k of U are final: push them into rows i > k
+                out.push_back([=]() { k_trtri_update<<<dim3((Tmax - k - 1) * (k + 1), ai), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k); L[MEDGP_STAGE_TRTRI]++; });
             }
-            k_alpha<<<dim3(Tmax, ncta), 256, 0, st>>>(dd);
-            L[MEDGP_STAGE_TRTRI]++;
+            out.push_back([=]() { k_trtri_row<<<dim3(i, ai), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, i, rl ? 1 : 0); L[MEDGP_STAGE_TRTRI]++; });
         }
-        {
-            StageScope sp(ctx, MEDGP_STAGE_LAUUM, st);
-            k_lauum<<<dim3(ntri, ncta), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd);
-            L[MEDGP_STAGE_LAUUM]++;
-        }
-        {
-            StageScope sp(ctx, MEDGP_STAGE_GRAD, st);
-            launch_grad(md.Q, dim3((sc.items_max + 3) / 4, ncta), st, dd, md);
-            k_grad_finish<<<ncta, 256, fin_smem, st>>>(dd, md, d_grad, ctx->d_fail);
+        out.push_back([=]() { k_alpha<<<dim3(Tmax, ncta), 256, 0, st>>>(dd); L[MEDGP_STAGE_TRTRI]++; });
+        end(MEDGP_STAGE_TRTRI);
+        begin(MEDGP_STAGE_LAUUM);
+        out.push_back([=]() { k_lauum<<<dim3(ntri, ncta), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd); L[MEDGP_STAGE_LAUUM]++; });
+        end(MEDGP_STAGE_LAUUM);
+        begin(MEDGP_STAGE_GRAD);
+        const int items = scp->items_max;
+        out.push_back([=]() {
+            launch_grad(md.Q, dim3((items + 3) / 4, ncta), st, dd, md);
+            k_grad_finish<<<ncta, 256, fin_smem, st>>>(dd, md, d_grad, d_fail);
             L[MEDGP_STAGE_GRAD] += 2;
-        }
+        });
+        end(MEDGP_STAGE_GRAD);
     }
     if (pred && sc.nstar_max > 0) {
-        StageScope sp(ctx, MEDGP_STAGE_PREDICT, st);
-        k_pred_finish<<<dim3(sc.nstar_max, ncta), 256, 0, st>>>(dd, md, d_mean, d_var, ctx->d_fail);
-        L[MEDGP_STAGE_PREDICT]++;
+        const int nsm = sc.nstar_max;
+        begin(MEDGP_STAGE_PREDICT);
+        out.push_back([=]() { k_pred_finish<<<dim3(nsm, ncta), 256, 0, st>>>(dd, md, d_mean, d_var, d_fail); L[MEDGP_STAGE_PREDICT]++; });
+        end(MEDGP_STAGE_PREDICT);
     }
 }
 
@@ -366,6 +387,13 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
             S = Tbig >= 16 ? (int)std::min<size_t>(cnt, ctx->max_streams)
                            : (int)std::min<size_t>(std::max<size_t>(1, cnt / 32), ctx->max_streams);
         }
+        // few large matrices -> right-looking factorisation (more CTAs per launch); many small
+        // ones -> left-looking (less traffic).  Decided on the whole chunk, not per stream.
+        bool rl = Tbig >= 8 && cnt * (size_t)Tbig < 600;
+        if (ctx->force_rl >= 0) rl = ctx->force_rl != 0;
+        // left-looking with few matrices: the diagonal kernel (one CTA per matrix) must not carry
+        // a k-tile product; the panel CTAs fold their tile into the diagonal block instead
+        const bool fold = !rl && cnt < 128;
         std::vector<SubChunk> subs(S);
         // ---- carve the arena and fill descriptors, sub-chunk major
         char *p = ctx->arena;
@@ -421,17 +449,68 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         }
         CU(cudaMemcpyAsync(ctx->d_descs + dpos, ctx->h_descs + dpos, cnt * sizeof(EvalDesc),
                            cudaMemcpyHostToDevice, st));
-        if (S == 1) {
-            launch_sub(ctx, subs[0], st, d_theta, mode, d_nlml, d_grad, d_status, d_mean, d_var);
-        } else {
-            CU(cudaEventRecord(ctx->ev_fork, st));
-            for (int sidx = 0; sidx < S; sidx++) {
-                cudaStream_t ss = ctx->sub_streams[sidx];
-                CU(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
-                launch_sub(ctx, subs[sidx], ss, d_theta, mode, d_nlml, d_grad, d_status, d_mean, d_var);
-                CU(cudaEventRecord(ctx->ev_join[sidx], ss));
+        // ---- issue: a CUDA graph per chunk structure (captured once, replayed afterwards) keeps
+        //      the CPU out of the way -- a step is hundreds of launches over several streams
+        auto issue_all = [&]() -> int {
+            std::vector<LaunchList> prog(S);
+            for (int sidx = 0; sidx < S; sidx++)
+                build_sub(ctx, subs[sidx], rl, fold, S == 1 ? st : ctx->sub_streams[sidx], d_theta, mode, d_nlml,
+                          d_grad, d_status, d_mean, d_var, prog[sidx]);
+            if (S > 1) {
+                CU(cudaEventRecord(ctx->ev_fork, st));
+                for (int sidx = 0; sidx < S; sidx++) CU(cudaStreamWaitEvent(ctx->sub_streams[sidx], ctx->ev_fork, 0));
             }
-            for (int sidx = 0; sidx < S; sidx++) CU(cudaStreamWaitEvent(st, ctx->ev_join[sidx], 0));
+            size_t longest = 0;
+            for (auto &pl : prog) longest = std::max(longest, pl.size());
+            for (size_t step = 0; step < longest; step++)  // round-robin issue
+                for (int sidx = 0; sidx < S; sidx++)
+                    if (step < prog[sidx].size()) prog[sidx][step]();
+            if (S > 1)
+                for (int sidx = 0; sidx < S; sidx++) {
+                    CU(cudaEventRecord(ctx->ev_join[sidx], ctx->sub_streams[sidx]));
+                    CU(cudaStreamWaitEvent(st, ctx->ev_join[sidx], 0));
+                }
+            return MEDGP_OK;
+        };
+        if (ctx->profile || !ctx->use_graphs) {
+            const int rc = issue_all();
+            if (rc) return rc;
+        } else {
+            uint64_t key = 1469598103934665603ULL;
+            auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ULL; };
+            mix((uint64_t)mode); mix(rl); mix(fold); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
+            mix((uint64_t)(uintptr_t)d_theta); mix((uint64_t)(uintptr_t)d_nlml); mix((uint64_t)(uintptr_t)d_grad);
+            mix((uint64_t)(uintptr_t)d_status); mix((uint64_t)(uintptr_t)d_mean); mix((uint64_t)(uintptr_t)d_var);
+            mix((uint64_t)(uintptr_t)ctx->d_fail);
+            for (auto &sc : subs) {
+                mix(sc.cnt); mix((uint64_t)sc.items_max); mix((uint64_t)sc.nstar_max);
+                for (int t : sc.T) mix((uint64_t)t);
+            }
+            auto it = ctx->graphs.find(key);
+            if (it == ctx->graphs.end()) {
+                long long before[MEDGP_STAGE_COUNT];
+                memcpy(before, ctx->times.launches, sizeof(before));
+                CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                const int rc = issue_all();
+                cudaGraph_t graph = nullptr;
+                cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                if (rc) return rc;
+                if (ce != cudaSuccess) { ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return MEDGP_ERR_CUDA; }
+                GraphEntry ge;
+                CU(cudaGraphInstantiate(&ge.exec, graph, 0));
+                cudaGraphDestroy(graph);
+                for (int i = 0; i < MEDGP_STAGE_COUNT; i++) {
+                    ge.launches[i] = ctx->times.launches[i] - before[i];
+                    ctx->times.launches[i] = before[i];
+                }
+                if (ctx->graphs.size() >= 128) {  // bounded cache
+                    for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second.exec);
+                    ctx->graphs.clear();
+                }
+                it = ctx->graphs.emplace(key, ge).first;
+            }
+            CU(cudaGraphLaunch(it->second.exec, st));
+            for (int i = 0; i < MEDGP_STAGE_COUNT; i++) ctx->times.launches[i] += it->second.launches[i];
         }
         CU(cudaGetLastError());
         dpos += cnt;
@@ -490,6 +569,8 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     }
     ctx->arena_bytes = workspace_bytes;
     ctx->max_streams = 8;
+    if (const char *ev = getenv("MEDGP_RL")) ctx->force_rl = atoi(ev);
+    if (const char *ev = getenv("MEDGP_GRAPHS")) ctx->use_graphs = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_STREAMS")) ctx->max_streams = std::max(1, std::min(8, atoi(ev)));
     for (int i = 0; i < 8; i++) {
         cudaStreamCreateWithFlags(&ctx->sub_streams[i], cudaStreamNonBlocking);
@@ -500,6 +581,8 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     cudaFuncSetAttribute(k_potrf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
     cudaFuncSetAttribute(k_trtri_row, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
     cudaFuncSetAttribute(k_lauum, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    cudaFuncSetAttribute(k_trtri_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
     *out = ctx;
     return MEDGP_OK;
 }
@@ -513,6 +596,7 @@ MEDGP_API void medgp_cuda_destroy(medgp_ctx *ctx)
         if (s.alive) free_series_mem(s);
     resolve_marks(ctx);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second.exec);
     for (int i = 0; i < 8; i++) {
         if (ctx->sub_streams[i]) cudaStreamDestroy(ctx->sub_streams[i]);
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);

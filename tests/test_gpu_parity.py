@@ -142,3 +142,75 @@ def test_predict(api, oracle):
     assert rel(mean, np.concatenate(ref_m)) <= RTOL
     assert rel(var, np.concatenate(ref_v)) <= RTOL
     ctx.close()
+
+
+def test_left_and_right_looking_factorisations_agree(api, oracle, monkeypatch):
+    """n = 1100 (T = 18): one matrix takes the right-looking path, MEDGP_RL=0 forces the
+    left-looking one; both must match the oracle."""
+    Q, D, R, n = 3, 6, 2, 1100
+    meta, x, y = synth.make_patient(D, n, seed=31)
+    theta = synth.init_hyp_lmc_sm(Q, D, R, 1, seed=41)[0]
+    from oracle import oracle_np
+    f0, g0 = oracle_np.nlml_grad_np(Q, D, R, meta, x, y, theta)
+    res = {}
+    for rl in ("0", "1"):
+        monkeypatch.setenv("MEDGP_RL", rl)
+        ctx = api.Context(Q, D, R, workspace_bytes=2 << 30)
+        sid = ctx.add_series(meta, x, y)
+        f, g, st = ctx.nlml_grad([sid], theta[None], True)
+        ctx.close()
+        assert st[0] == 0
+        assert abs(f[0] - f0) <= RTOL * abs(f0)
+        assert rel(g[0], g0) <= RTOL
+        res[rl] = (f[0], g[0])
+    assert abs(res["0"][0] - res["1"][0]) <= 1e-12 * abs(f0)
+
+
+def test_cohort_sweep_sizes(api):
+    """C3-like ragged batch at full sizes (n up to 1500): checked through size-independent
+    properties -- bitwise determinism across calls, invariance to point order and to the sign
+    of A, and agreement with the numpy/LAPACK oracle on the largest series."""
+    Q, D, R = 5, 24, 8
+    rng = np.random.default_rng(7)
+    sizes = [1500, 300, 777, 1210, 512, 1024]
+    thetas = synth.init_hyp_lmc_sm(Q, D, R, len(sizes), seed=99)
+    ctx = api.Context(Q, D, R, workspace_bytes=4 << 30)
+    pats = [synth.make_patient(D, n, seed=500 + k) for k, n in enumerate(sizes)]
+    sids = [ctx.add_series(*p) for p in pats]
+    f1, g1, st = ctx.nlml_grad(sids, thetas, True)
+    f2, g2, _ = ctx.nlml_grad(sids, thetas, True)
+    assert (st == 0).all() and np.array_equal(f1, f2) and np.array_equal(g1, g2)
+    shuffled = []
+    for m, x, y in pats:
+        p = rng.permutation(len(x))
+        shuffled.append(ctx.add_series(m[p], x[p], y[p]))
+    flipped = thetas.copy()
+    flipped[:, D:D + Q * D * R] *= -1
+    f3, g3, _ = ctx.nlml_grad(shuffled, flipped, True)
+    assert np.abs(f3 - f1).max() <= 1e-10 * np.abs(f1).max()
+    gA = slice(D, D + Q * D * R)
+    for k in range(len(sizes)):
+        assert rel(-g3[k, gA], g1[k, gA]) <= 1e-8 and rel(g3[k, :D], g1[k, :D]) <= 1e-8
+    from oracle import oracle_np
+    f0, g0 = oracle_np.nlml_grad_np(Q, D, R, *pats[0], thetas[0])
+    assert abs(f1[0] - f0) <= RTOL * abs(f0) and rel(g1[0], g0) <= RTOL
+    ctx.close()
+
+
+def test_long_stay_patient(api):
+    """C4: n = 4000, 24 features, Q = 5, several initialisations of the same series in flight
+    (right-looking blocked Cholesky path) against the numpy/LAPACK oracle."""
+    Q, D, R, n = 5, 24, 8, 4000
+    meta, x, y = synth.make_patient(D, n, seed=4000, T=1200.0)
+    thetas = synth.init_hyp_lmc_sm(Q, D, R, 3, seed=4)
+    ctx = api.Context(Q, D, R, workspace_bytes=8 << 30)
+    sid = ctx.add_series(meta, x, y)
+    f, g, st = ctx.nlml_grad([sid] * 3, thetas, True)
+    assert (st == 0).all()
+    from oracle import oracle_np
+    f0, g0 = oracle_np.nlml_grad_np(Q, D, R, meta, x, y, thetas[1])
+    assert abs(f[1] - f0) <= RTOL * abs(f0)
+    assert rel(g[1], g0) <= RTOL
+    fn, _, _ = ctx.nlml_grad([sid] * 3, thetas, False)
+    assert np.array_equal(fn, f)
+    ctx.close()

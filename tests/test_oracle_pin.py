@@ -102,3 +102,15 @@ def test_prior_terms(oracle):
     lp, dlp = oracle.prior(2, -0.3, 0.0, 0.5)
     assert abs(lp - (-0.6 - np.log(1.0))) < 1e-15 and dlp == 2.0
     assert oracle.prior(2, 0.0, 0.0, 0.5)[1] == 0.0
+
+
+def test_numpy_large_n_oracle_agrees_with_c_oracle(oracle):
+    from oracle import oracle_np
+    Q, D, R, n = 3, 4, 2, 150
+    meta, x, y = synth.make_patient(D, n, seed=21)
+    theta = synth.init_hyp_lmc_sm(Q, D, R, 1, seed=8)[0]
+    perm = np.random.default_rng(1).permutation(n)
+    f0, g0, _ = oracle.nlml_grad(Q, D, R, meta, x, y, theta)
+    f1, g1 = oracle_np.nlml_grad_np(Q, D, R, meta[perm], x[perm], y[perm], theta)
+    assert abs(f1 - f0) <= 1e-11 * abs(f0)
+    assert np.abs(g1 - g0).max() <= 1e-10 * np.abs(g0).max()
