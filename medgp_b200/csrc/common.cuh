@@ -177,6 +177,7 @@ constexpr int kGemmSmemBytes = MEDGP_NSTAGE * kStageElems * 8; // 69632 B == 2 f
 struct GemmBars {
     uint64_t full[MEDGP_NSTAGE];
     uint64_t empty[MEDGP_NSTAGE];
+    uint64_t aux;  // whole-tile bulk copy of an epilogue operand (X_kk)
 };
 
 __device__ __forceinline__ void gemm_bars_init(GemmBars *bars)
@@ -186,6 +187,7 @@ __device__ __forceinline__ void gemm_bars_init(GemmBars *bars)
             mbar_init(&bars->full[s], 1);
             mbar_init(&bars->empty[s], MEDGP_GEMM_THREADS / 32);
         }
+        mbar_init(&bars->aux, 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -321,6 +323,26 @@ __device__ __forceinline__ void tile_g2s_plain(double *sT, const double *G)
 {
     for (int idx = threadIdx.x; idx < kTileElems / 2; idx += blockDim.x)
         reinterpret_cast<double2 *>(sT)[idx] = reinterpret_cast<const double2 *>(G)[idx];
+}
+
+// the same through the TMA engine: one 34816 B bulk copy, completion on bars->aux (phase 0).
+// Call after a block barrier that retired every earlier use of sT; wait with tile_bulk_wait.
+__device__ __forceinline__ void tile_bulk_g2s(double *sT, const double *G, GemmBars *bars)
+{
+    if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_expect_tx(&bars->aux, kTileElems * 8);
+        bulk_g2s(sT, G, kTileElems * 8, &bars->aux);
+    }
+}
+__device__ __forceinline__ void tile_bulk_wait(GemmBars *bars) { mbar_wait(&bars->aux, 0); }
+
+// pull a tile towards L2 ahead of its use (epilogue operands of the panel kernels)
+__device__ __forceinline__ void prefetch_tile_l2(const double *G)
+{
+    const char *p = reinterpret_cast<const char *>(G);
+    for (int off = threadIdx.x * 128; off < kTileElems * 8; off += blockDim.x * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
 }
 
 // block-wide sum of `NV` doubles per thread; result valid in thread 0.  scratch: NV*32 doubles.

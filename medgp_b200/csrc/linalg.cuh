@@ -68,6 +68,41 @@ __device__ __forceinline__ void tile_matvec_rhs(const EvalDesc &e, const double 
     }
 }
 
+// rhs_i -= L_ik z_k straight from the accumulator fragments (acc = L_ik): every thread forms the
+// partial dot products of its 4 row sub-tiles over its 8 columns, the 4 lanes of a quad are
+// combined with shuffles, the two column halves (wn) through a 2x64 shared scratch.
+__device__ __forceinline__ void acc_matvec_rhs(const double (&acc)[4][4][2], const EvalDesc &e,
+                                               const double *zk_base, double *out_base, double *red /*2*64*/)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, ld = e.npad;
+    const int wm = warp & 1, wn = warp >> 1, r = lane >> 2, kq = lane & 3;
+    for (int q = 0; q < e.nrhs; q++) {
+        const double *z = zk_base + (size_t)q * ld;
+        double ps[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int col = wn * 32 + 8 * b + 2 * kq;
+            const double z0 = z[col], z1 = z[col + 1];
+#pragma unroll
+            for (int a = 0; a < 4; a++) ps[a] += acc[a][b][0] * z0 + acc[a][b][1] * z1;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            ps[a] += __shfl_xor_sync(0xffffffffu, ps[a], 1);
+            ps[a] += __shfl_xor_sync(0xffffffffu, ps[a], 2);
+        }
+        if (kq == 0)
+#pragma unroll
+            for (int a = 0; a < 4; a++) red[wn * MEDGP_NB + wm * 32 + 8 * a + r] = ps[a];
+        __syncthreads();
+        if (threadIdx.x < MEDGP_NB) {
+            double *o = out_base + (size_t)q * ld;
+            o[threadIdx.x] -= red[threadIdx.x] + red[MEDGP_NB + threadIdx.x];
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ potrf: diagonal block k
 // Fused Cholesky + triangular inverse of one 64x64 block by Gauss-Jordan-style elimination on
 // the augmented matrix [D | I], entirely in registers.  128 threads: thread (r, g) (r = tid&63,
@@ -262,34 +297,38 @@ k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_dia
     const int i = k + 1 + blockIdx.x;
     if (i >= e.T) return;
     const int T = e.T;
+    double *M = e.M;
+    double *Tik = tile_ptr(M, T, i, k);
+    const double *Xk = e.dinv + (size_t)k * kTileElems;
+    __shared__ double red[2 * MEDGP_NB];
+    prefetch_tile_l2(Tik);  // epilogue operands: start them towards L2 now
+    prefetch_tile_l2(Xk);
     gemm_bars_init(&bars);
     double acc[4][4][2];
     acc_zero(acc);
-    double *M = e.M;
     gemm_nt_tiles(acc, depth,
                   [&](int l, const double *&A, const double *&B) {
                       A = tile_ptr(M, T, i, l);
                       B = tile_ptr(M, T, k, l);
                   },
                   smem, &bars);
-    double *Tik = tile_ptr(M, T, i, k);
-    acc_rsub_global(acc, Tik);
     __syncthreads();  // every warp is done with the pipeline buffers
     double *sP = smem, *sX = smem + kTileElems;
+    tile_bulk_g2s(sX, Xk, &bars);  // X_kk arrives while P = K_ik - C is formed
+    acc_rsub_global(acc, Tik);
     acc_to_smem(acc, sP, 1.0);
-    tile_g2s_plain(sX, e.dinv + (size_t)k * kTileElems);
+    tile_bulk_wait(&bars);
     __syncthreads();
     gemm2_smem(acc, sP, sX);
     acc_to_global(acc, Tik);
     // forward solve: push the fresh tile into the right-hand sides of block row i
-    __syncthreads();  // GEMM2 is done reading sP / sX everywhere
-    acc_to_smem(acc, sP, 1.0);
-    __syncthreads();
-    tile_matvec_rhs(e, sP, e.rhs + k * MEDGP_NB, e.rhs + i * MEDGP_NB, false, true, sX);
+    acc_matvec_rhs(acc, e, e.rhs + k * MEDGP_NB, e.rhs + i * MEDGP_NB, red);
     if (fold_diag) {
         // few matrices in flight: apply this tile to its diagonal block right away,
         // K_ii -= L_ik L_ik^T, so that the (single-CTA) diagonal kernel has no product to do
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        acc_to_smem(acc, sP, 1.0);  // (acc_matvec_rhs ended with a block barrier: GEMM2 is done with sP)
+        __syncthreads();
         acc_zero(acc);
         mma_panels(acc, sP, sP, MEDGP_NB / 4, warp & 1, warp >> 1, lane);
         double *Kii = tile_ptr(M, T, i, i);
@@ -328,8 +367,9 @@ k_trtri_row(const EvalDesc *__restrict__ descs, int i, int right_looking)
     }
     __syncthreads();
     double *sP = smem, *sX = smem + kTileElems;
+    tile_bulk_g2s(sX, e.dinv + (size_t)i * kTileElems, &bars);
     acc_to_smem(acc, sP, -1.0);
-    tile_g2s_plain(sX, e.dinv + (size_t)i * kTileElems);
+    tile_bulk_wait(&bars);
     __syncthreads();
     gemm2_smem(acc, sP, sX);
     acc_to_global(acc, tile_ptr(M, T, j, i));
