@@ -35,6 +35,7 @@ struct ModelDims {
 
 struct __align__(16) EvalDesc {
     double *M, *dinv, *dinvT, *rhs, *alpha, *cs, *par, *part, *blk;
+    int *flags;              // T ints: flags[k] = 1 once diagonal block k is factored (k_potrf_step)
     const double *t, *y;
     const int *meta, *off;
     const int4 *items;
@@ -44,7 +45,7 @@ struct __align__(16) EvalDesc {
     int n, npad, T, nitems;
     int jitter, nrhs, nstar, out_index;
     int star_out;            // offset of this evaluation's predictions in the output arrays
-    int pad0, pad1, pad2;
+    int pad0;
 };
 
 // tile-major addressing (kTileElems doubles per tile, column pitch MEDGP_SLD)
@@ -111,6 +112,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
             "r"(smem_u32(dst)),
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+
+// inter-CTA flag (same kernel): release by the producer CTA, acquire-spin by the consumers
+__device__ __forceinline__ void flag_release(int *flag)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+}
+__device__ __forceinline__ int flag_acquire(const int *flag)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    return v;
 }
 
 // D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor core (SASS: DMMA.8x8x4)
@@ -330,7 +343,7 @@ __device__ __forceinline__ void tile_g2s_plain(double *sT, const double *G)
 __device__ __forceinline__ void tile_bulk_g2s(double *sT, const double *G, GemmBars *bars)
 {
     if (threadIdx.x == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");  // generic -> async, shared and global
         mbar_arrive_expect_tx(&bars->aux, kTileElems * 8);
         bulk_g2s(sT, G, kTileElems * 8, &bars->aux);
     }

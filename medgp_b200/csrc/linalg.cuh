@@ -82,7 +82,7 @@ __device__ __forceinline__ void acc_matvec_rhs(const double (&acc)[4][4][2], con
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int col = wn * 32 + 8 * b + 2 * kq;
-            const double z0 = z[col], z1 = z[col + 1];
+            const double z0 = __ldcg(z + col), z1 = __ldcg(z + col + 1);
 #pragma unroll
             for (int a = 0; a < 4; a++) ps[a] += acc[a][b][0] * z0 + acc[a][b][1] * z1;
         }
@@ -214,9 +214,61 @@ __device__ __forceinline__ void potf2_inv_gj(double (&W)[32], int r, int g, GjBu
     }
 }
 
-// One CTA per evaluation: D = K_kk - sum_{l<k} L_kl L_kl^T ; L_kk = chol(D) ; X_kk = inv(L_kk).
-// Writes L_kk (lower part of the tile), dinv[k], dinvT[k], blk[k] = sum log diag(L_kk) and
-// raises fail[] when a pivot is not positive.
+// Factor one diagonal block: D = K_kk - C with the accumulated product C in sD (pitch SLD);
+// L_kk = chol(D), X_kk = inv(L_kk).  Writes L_kk (lower part of the tile), dinv[k], dinvT[k],
+// blk[k] = sum log diag(L_kk), turns rhs block k into z_k = X_kk rhs_k and raises fail[] when a
+// pivot is not positive.  128 threads; sD / sL are the two halves of the dynamic smem ring.
+__device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, double *sD, double *sL,
+                                                  GjBufs *gjb, int *s_fail, int *__restrict__ fail,
+                                                  bool have_product = true)
+{
+    const int T = e.T, tid = threadIdx.x;
+    const int r = tid & 63, g = tid >> 6;
+    const double *Kkk = tile_ptr(e.M, T, k, k);
+    double W[32];
+#pragma unroll
+    for (int s = 0; s < 32; s++) {
+        const int c = 2 * s + g;
+        W[s] = (c <= r) ? Kkk[c * MEDGP_SLD + r] - (have_product ? sD[c * MEDGP_SLD + r] : 0.0) : 0.0;
+    }
+    __syncthreads();  // sD is dead from here on: it becomes the staging tile for X
+    potf2_inv_gj(W, r, g, gjb, sL, s_fail);
+    __syncthreads();
+    const double lrr_inv = 1.0 / sL[r * MEDGP_SLD + r];
+#pragma unroll
+    for (int s = 0; s < 32; s++) {
+        const int c = 2 * s + g;
+        const double x = (c < r) ? W[s] * lrr_inv : (c == r ? lrr_inv : 0.0);
+        sD[c * MEDGP_SLD + r] = x;  // X(r, c)
+    }
+    __syncthreads();
+    // forward solve, block k: z_k = X_kk rhs_k (in place)
+    tile_matvec_rhs(e, sD, e.rhs + k * MEDGP_NB, e.rhs + k * MEDGP_NB, true, false, gjb->d[0]);
+    // write back: L_kk (lower), dinv (X column-major), dinvT (X^T column-major)
+    double *Lkk = tile_ptr(e.M, T, k, k);
+    double *Xk = e.dinv + (size_t)k * kTileElems;
+    double *XTk = e.dinvT + (size_t)k * kTileElems;
+    for (int idx = tid; idx < MEDGP_NB * MEDGP_NB; idx += blockDim.x) {
+        const int c = idx >> 6, rr = idx & 63;
+        if (rr >= c) Lkk[c * MEDGP_SLD + rr] = sL[c * MEDGP_SLD + rr];
+        Xk[c * MEDGP_SLD + rr] = sD[c * MEDGP_SLD + rr];   // X(rr, c)
+        XTk[c * MEDGP_SLD + rr] = sD[rr * MEDGP_SLD + c];  // X^T(rr, c) = X(c, rr)
+    }
+    if (tid < 32) {
+        double s = log(sL[tid * MEDGP_SLD + tid]) + log(sL[(tid + 32) * MEDGP_SLD + tid + 32]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (tid == 0) {
+            e.blk[k] = s;
+            if (*s_fail) fail[e.out_index] = 1;
+        }
+    }
+}
+
+// Stand-alone diagonal kernel, one CTA per evaluation: D = K_kk - sum_{l<depth} L_kl L_kl^T.
+// Used for block 0, for the right-looking path (depth 0: the tile is already updated), and as
+// the general fallback; in the left-looking path blocks k >= 1 are factored inside the panel
+// kernel of step k-1 (see k_potrf_panel).
 __global__ void __launch_bounds__(MEDGP_DIAG_THREADS, 3)
 k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int depth, int *__restrict__ fail)
 {
@@ -244,52 +296,13 @@ k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int depth, int *__restri
         acc_to_smem(acc, sD, 1.0);
     }
     __syncthreads();
-    const int r = tid & 63, g = tid >> 6;
-    const double *Kkk = tile_ptr(M, T, k, k);
-    double W[32];
-#pragma unroll
-    for (int s = 0; s < 32; s++) {
-        const int c = 2 * s + g;
-        W[s] = (c <= r) ? Kkk[c * MEDGP_SLD + r] - sD[c * MEDGP_SLD + r] : 0.0;
-    }
-    __syncthreads();  // sD is dead from here on: it becomes the staging tile for X
-    potf2_inv_gj(W, r, g, &gjb, sL, &s_fail);
-    __syncthreads();
-    const double lrr_inv = 1.0 / sL[r * MEDGP_SLD + r];
-#pragma unroll
-    for (int s = 0; s < 32; s++) {
-        const int c = 2 * s + g;
-        const double x = (c < r) ? W[s] * lrr_inv : (c == r ? lrr_inv : 0.0);
-        sD[c * MEDGP_SLD + r] = x;  // X(r, c)
-    }
-    __syncthreads();
-    // forward solve, block k: z_k = X_kk rhs_k (in place)
-    tile_matvec_rhs(e, sD, e.rhs + k * MEDGP_NB, e.rhs + k * MEDGP_NB, true, false, gjb.d[0]);
-    // write back: L_kk (lower), dinv (X column-major), dinvT (X^T column-major)
-    double *Lkk = tile_ptr(M, T, k, k);
-    double *Xk = e.dinv + (size_t)k * kTileElems;
-    double *XTk = e.dinvT + (size_t)k * kTileElems;
-    for (int idx = tid; idx < MEDGP_NB * MEDGP_NB; idx += blockDim.x) {
-        const int c = idx >> 6, rr = idx & 63;
-        if (rr >= c) Lkk[c * MEDGP_SLD + rr] = sL[c * MEDGP_SLD + rr];
-        Xk[c * MEDGP_SLD + rr] = sD[c * MEDGP_SLD + rr];   // X(rr, c)
-        XTk[c * MEDGP_SLD + rr] = sD[rr * MEDGP_SLD + c];  // X^T(rr, c) = X(c, rr)
-    }
-    if (tid < 32) {
-        double s = log(sL[tid * MEDGP_SLD + tid]) + log(sL[(tid + 32) * MEDGP_SLD + tid + 32]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (tid == 0) {
-            e.blk[k] = s;
-            if (s_fail) fail[e.out_index] = 1;
-        }
-    }
+    diag_block_factor(e, k, sD, sL, &gjb, &s_fail, fail);
 }
 
 // ------------------------------------------------------------------ potrf: panel below block k
 // grid (row tiles i > k, evaluations): L_ik = (K_ik - sum_{l<k} L_il L_kl^T) X_kk^T
 __global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
-k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_diag)
+k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_diag, int *__restrict__ fail)
 {
     extern __shared__ __align__(128) double smem[];
     __shared__ GemmBars bars;
@@ -324,17 +337,95 @@ k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_dia
     // forward solve: push the fresh tile into the right-hand sides of block row i
     acc_matvec_rhs(acc, e, e.rhs + k * MEDGP_NB, e.rhs + i * MEDGP_NB, red);
     if (fold_diag) {
-        // few matrices in flight: apply this tile to its diagonal block right away,
-        // K_ii -= L_ik L_ik^T, so that the (single-CTA) diagonal kernel has no product to do
+        // apply this tile to its diagonal block right away, K_ii -= L_ik L_ik^T, so that no
+        // diagonal kernel has a k-tile product to do.  With fold_diag == 2 the CTA of row k+1,
+        // whose diagonal block is now complete, factors it on the spot: the next step's
+        // diagonal kernel disappears and its latency hides behind the other panel CTAs.
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         acc_to_smem(acc, sP, 1.0);  // (acc_matvec_rhs ended with a block barrier: GEMM2 is done with sP)
         __syncthreads();
         acc_zero(acc);
         mma_panels(acc, sP, sP, MEDGP_NB / 4, warp & 1, warp >> 1, lane);
-        double *Kii = tile_ptr(M, T, i, i);
-        acc_rsub_global(acc, Kii);
-        acc_to_global(acc, Kii);
+        if (fold_diag == 2 && i == k + 1) {
+            __shared__ __align__(16) GjBufs gjb;
+            __shared__ int s_fail;
+            if (threadIdx.x == 0) s_fail = 0;
+            __syncthreads();  // everyone is done reading sP
+            acc_to_smem(acc, sP, 1.0);
+            __syncthreads();
+            diag_block_factor(e, i, sP, sX, &gjb, &s_fail, fail);
+        } else {
+            double *Kii = tile_ptr(M, T, i, i);
+            acc_rsub_global(acc, Kii);
+            acc_to_global(acc, Kii);
+        }
     }
+}
+
+// ------------------------------------------------------------------ potrf: one left-looking step
+// grid (evaluations, 1 + rows below).  CTA y == 0 factors diagonal block k (already complete:
+// every earlier panel CTA folded its tile into it) while the CTAs y >= 1 run the k-tile
+// products of their panel tiles; they then wait on flags[k] (set by the diagonal CTA of the same
+// evaluation, which was dispatched before them), finish L_ik = P X_kk^T, push it into the
+// right-hand sides and fold it into their own diagonal block.  One launch per block column,
+// with the latency-bound diagonal factorisation hidden behind the tensor-core work.
+__global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
+k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail)
+{
+    extern __shared__ __align__(128) double smem[];
+    __shared__ GemmBars bars;
+    __shared__ __align__(16) GjBufs gjb;
+    __shared__ double red[2 * MEDGP_NB];
+    __shared__ int s_fail;
+    const EvalDesc &e = descs[blockIdx.x];  // x = evaluation: ALL diagonal CTAs (y == 0) are dispatched first
+    const int T = e.T;
+    double *M = e.M;
+    double *sP = smem, *sX = smem + kTileElems;
+    if (blockIdx.y == 0) {
+        if (k >= T) return;
+        if (threadIdx.x == 0) s_fail = 0;
+        __syncthreads();
+        diag_block_factor(e, k, sP, sX, &gjb, &s_fail, fail, false);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) flag_release(e.flags + k);
+        return;
+    }
+    const int i = k + blockIdx.y;
+    if (i >= T) return;
+    double *Tik = tile_ptr(M, T, i, k);
+    const double *Xk = e.dinv + (size_t)k * kTileElems;
+    prefetch_tile_l2(Tik);
+    gemm_bars_init(&bars);
+    double acc[4][4][2];
+    acc_zero(acc);
+    gemm_nt_tiles(acc, k,
+                  [&](int l, const double *&A, const double *&B) {
+                      A = tile_ptr(M, T, i, l);
+                      B = tile_ptr(M, T, k, l);
+                  },
+                  smem, &bars);
+    acc_rsub_global(acc, Tik);  // P = K_ik - C (does not depend on the diagonal block)
+    __syncthreads();            // every warp is done with the pipeline buffers
+    acc_to_smem(acc, sP, 1.0);
+    if (threadIdx.x == 0)
+        while (flag_acquire(e.flags + k) == 0) __nanosleep(64);
+    __syncthreads();
+    tile_bulk_g2s(sX, Xk, &bars);
+    tile_bulk_wait(&bars);
+    __syncthreads();
+    gemm2_smem(acc, sP, sX);
+    acc_to_global(acc, Tik);
+    acc_matvec_rhs(acc, e, e.rhs + k * MEDGP_NB, e.rhs + i * MEDGP_NB, red);
+    // fold into the own diagonal block: K_ii -= L_ik L_ik^T
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    acc_to_smem(acc, sP, 1.0);
+    __syncthreads();
+    acc_zero(acc);
+    mma_panels(acc, sP, sP, MEDGP_NB / 4, warp & 1, warp >> 1, lane);
+    double *Kii = tile_ptr(M, T, i, i);
+    acc_rsub_global(acc, Kii);
+    acc_to_global(acc, Kii);
 }
 
 // ------------------------------------------------------------------ trtri: block row i of L^-1

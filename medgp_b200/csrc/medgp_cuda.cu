@@ -79,6 +79,7 @@ struct medgp_ctx {
     int max_streams = 1;
     bool use_graphs = true;  // MEDGP_GRAPHS=0 disables CUDA-graph replay of chunk launch sequences
     std::map<uint64_t, GraphEntry> graphs;
+    bool fuse_diag = true;   // MEDGP_FUSE_DIAG=0: separate diagonal kernels in the left-looking path
     int force_rl = -1;  // MEDGP_RL=0/1 forces the left-/right-looking factorisation (experiments)
     cudaStream_t sub_streams[8] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
@@ -129,6 +130,7 @@ size_t eval_bytes(const ModelDims &md, const Series &s, int nrhs, bool grad)
     b += align_up(np * (size_t)md.Q * 16, 256);            // cs
     b += align_up((size_t)md.parLen * 8, 256);             // par
     b += align_up((size_t)s.T * 8, 256);                   // blk
+    b += align_up((size_t)s.T * 4, 256);                   // flags
     if (grad) b += align_up((size_t)s.nitems * (3 * md.Q + 1) * 8, 256);
     return b;
 }
@@ -323,13 +325,22 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
         end(MEDGP_STAGE_PREDICT);
     }
     begin(MEDGP_STAGE_POTRF);
+    // left-looking default: ONE launch per block column (k_potrf_step: the diagonal CTA factors
+    // block k while the panel CTAs run their k-tile products, then wait on its flag).
+    // MEDGP_FUSE_DIAG=0 or the right-looking path use the separate diagonal / panel kernels.
+    const bool step_kernel = !rl && ctx->fuse_diag;
     for (int k = 0; k < Tmax; k++) {
         const unsigned a0 = sc.act(k), a1 = k + 1 < Tmax ? sc.act(k + 1) : 0;
-        const int depth = (rl || fold) ? 0 : k, rem = Tmax - k - 1;
+        const int rem = Tmax - k - 1;
+        if (step_kernel) {
+            out.push_back([=]() { k_potrf_step<<<dim3(a0, rem + 1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, d_fail); L[MEDGP_STAGE_POTRF]++; });
+            continue;
+        }
+        const int depth = (rl || fold) ? 0 : k;
         const int pdepth = rl ? 0 : k, pfold = (!rl && fold) ? 1 : 0;
         out.push_back([=]() { k_potrf_diag<<<a0, MEDGP_DIAG_THREADS, gemm_smem, st>>>(dd, k, depth, d_fail); L[MEDGP_STAGE_POTRF]++; });
         if (rem > 0) {
-            out.push_back([=]() { k_potrf_panel<<<dim3(rem, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, pdepth, pfold); L[MEDGP_STAGE_POTRF]++; });
+            out.push_back([=]() { k_potrf_panel<<<dim3(rem, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, pdepth, pfold, d_fail); L[MEDGP_STAGE_POTRF]++; });
             if (rl)
                 out.push_back([=]() { k_syrk_update<<<dim3(rem * (rem + 1) / 2, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k); L[MEDGP_STAGE_POTRF]++; });
         }
@@ -442,6 +453,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
                 e.cs = (double *)take(np * (size_t)md.Q * 16);
                 e.par = (double *)take((size_t)md.parLen * 8);
                 e.blk = (double *)take((size_t)s.T * 8);
+                e.flags = (int *)take((size_t)s.T * 4);
                 e.part = grad ? (double *)take((size_t)s.nitems * (3 * md.Q + 1) * 8) : nullptr;
                 e.t = s.d_t; e.y = s.d_y; e.meta = s.d_meta; e.off = s.d_off;
                 e.items = s.d_items; e.pair_start = s.d_pair_start;
@@ -450,7 +462,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
                 e.n = s.n; e.npad = s.npad; e.T = s.T; e.nitems = s.nitems;
                 e.jitter = rq.jitter; e.nrhs = 1 + rq.nstar; e.nstar = rq.nstar;
                 e.out_index = rq.out_index; e.star_out = rq.star_off;
-                e.pad0 = e.pad1 = e.pad2 = 0;
+                e.pad0 = 0;
                 sc.T.push_back(s.T);
                 sc.cnt++;
                 sc.Tmax = std::max(sc.Tmax, s.T);
@@ -501,7 +513,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         } else {
             uint64_t key = 1469598103934665603ULL;
             auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ULL; };
-            mix((uint64_t)mode); mix(rl); mix(fold); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
+            mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
             mix((uint64_t)(uintptr_t)d_theta); mix((uint64_t)(uintptr_t)d_nlml); mix((uint64_t)(uintptr_t)d_grad);
             mix((uint64_t)(uintptr_t)d_status); mix((uint64_t)(uintptr_t)d_mean); mix((uint64_t)(uintptr_t)d_var);
             mix((uint64_t)(uintptr_t)ctx->d_fail);
@@ -593,6 +605,7 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     ctx->arena_bytes = workspace_bytes;
     ctx->max_streams = 8;
     if (const char *ev = getenv("MEDGP_RL")) ctx->force_rl = atoi(ev);
+    if (const char *ev = getenv("MEDGP_FUSE_DIAG")) ctx->fuse_diag = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_GRAPHS")) ctx->use_graphs = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_STREAMS")) ctx->max_streams = std::max(1, std::min(8, atoi(ev)));
     for (int i = 0; i < 8; i++) {
@@ -604,6 +617,7 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     cudaFuncSetAttribute(k_potrf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
     cudaFuncSetAttribute(k_trtri_row, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
     cudaFuncSetAttribute(k_lauum, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    cudaFuncSetAttribute(k_potrf_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
     cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
     cudaFuncSetAttribute(k_trtri_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
     *out = ctx;
