@@ -46,7 +46,8 @@ typedef enum {
 enum {
     MEDGP_STAGE_PREP = 0,     /* theta -> B_q, sigma^2, per-point cos/sin tables          */
     MEDGP_STAGE_ASSEMBLE,     /* kernel (1): covariance assembly                           */
-    MEDGP_STAGE_POTRF,        /* kernel (2): blocked FP64 Cholesky (DMMA)                  */
+    MEDGP_STAGE_POTRF,        /* kernel (2): blocked FP64 Cholesky, panel/update kernels (DMMA) */
+    MEDGP_STAGE_DIAG,         /* kernel (2): 64x64 diagonal-block Cholesky + inverse       */
     MEDGP_STAGE_SOLVE,        /* kernel (2): triangular solves, log-det, NLML              */
     MEDGP_STAGE_TRTRI,        /* kernel (2): L^-1                                          */
     MEDGP_STAGE_LAUUM,        /* kernel (2): K^-1 = L^-T L^-1                              */

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MEDGP_LIB", os.path.join(HERE, "libmedgp_cuda.so"))  # MEDGP_LIB: experiments only
 PI_REF = 3.14159265  # medgpc/src/util/global_settings.h:6
 
-STAGES = ["prep", "assemble", "potrf", "solve", "trtri", "lauum", "grad", "predict"]
+STAGES = ["prep", "assemble", "potrf", "diag", "solve", "trtri", "lauum", "grad", "predict"]
 
 # every symbol include/medgp_cuda.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -30,8 +30,8 @@ SYMBOLS = [
 
 
 class StageTimes(ctypes.Structure):
-    _fields_ = [("ms", ctypes.c_double * 8), ("launches", ctypes.c_longlong * 8),
-                ("flops", ctypes.c_double * 8), ("bytes", ctypes.c_double * 8),
+    _fields_ = [("ms", ctypes.c_double * 9), ("launches", ctypes.c_longlong * 9),
+                ("flops", ctypes.c_double * 9), ("bytes", ctypes.c_double * 9),
                 ("evals", ctypes.c_longlong)]
 
 

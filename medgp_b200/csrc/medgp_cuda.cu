@@ -324,28 +324,33 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
         out.push_back([=]() { k_cross<<<dim3(nsm, ncta), 256, 0, st>>>(dd, md); L[MEDGP_STAGE_PREDICT]++; });
         end(MEDGP_STAGE_PREDICT);
     }
-    begin(MEDGP_STAGE_POTRF);
-    // left-looking default: ONE launch per block column (k_potrf_step: the diagonal CTA factors
-    // block k while the panel CTAs run their k-tile products, then wait on its flag).
-    // MEDGP_FUSE_DIAG=0 or the right-looking path use the separate diagonal / panel kernels.
-    const bool step_kernel = !rl && ctx->fuse_diag;
+    // left-looking with few matrices in the chunk: ONE launch per block column (k_potrf_step: the
+    // diagonal CTA factors block k while the panel CTAs run their k-tile products, then wait on
+    // its flag).  Large batches keep separate diagonal / panel kernels: their sub-chunk streams
+    // already overlap, and CTAs spinning on a flag would hold slots the other streams can use.
+    const bool step_kernel = !rl && fold && ctx->fuse_diag;  // fold <=> few matrices in the chunk
     for (int k = 0; k < Tmax; k++) {
         const unsigned a0 = sc.act(k), a1 = k + 1 < Tmax ? sc.act(k + 1) : 0;
         const int rem = Tmax - k - 1;
         if (step_kernel) {
+            begin(MEDGP_STAGE_POTRF);
             out.push_back([=]() { k_potrf_step<<<dim3(a0, rem + 1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, d_fail); L[MEDGP_STAGE_POTRF]++; });
+            end(MEDGP_STAGE_POTRF);
             continue;
         }
         const int depth = (rl || fold) ? 0 : k;
         const int pdepth = rl ? 0 : k, pfold = (!rl && fold) ? 1 : 0;
-        out.push_back([=]() { k_potrf_diag<<<a0, MEDGP_DIAG_THREADS, gemm_smem, st>>>(dd, k, depth, d_fail); L[MEDGP_STAGE_POTRF]++; });
+        begin(MEDGP_STAGE_DIAG);
+        out.push_back([=]() { k_potrf_diag<<<a0, MEDGP_DIAG_THREADS, gemm_smem, st>>>(dd, k, depth, d_fail); L[MEDGP_STAGE_DIAG]++; });
+        end(MEDGP_STAGE_DIAG);
         if (rem > 0) {
+            begin(MEDGP_STAGE_POTRF);
             out.push_back([=]() { k_potrf_panel<<<dim3(rem, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, pdepth, pfold, d_fail); L[MEDGP_STAGE_POTRF]++; });
             if (rl)
                 out.push_back([=]() { k_syrk_update<<<dim3(rem * (rem + 1) / 2, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k); L[MEDGP_STAGE_POTRF]++; });
+            end(MEDGP_STAGE_POTRF);
         }
     }
-    end(MEDGP_STAGE_POTRF);
     begin(MEDGP_STAGE_SOLVE);
     out.push_back([=]() { k_solve<<<ncta, 256, 0, st>>>(dd, md, d_nlml, d_status, d_fail); L[MEDGP_STAGE_SOLVE]++; });
     end(MEDGP_STAGE_SOLVE);
