@@ -572,8 +572,7 @@ int check_series_ids(medgp_ctx *ctx, int batch, const int *series_id)
 
 void free_series_mem(Series &s)
 {
-    cudaFree(s.d_t); cudaFree(s.d_y); cudaFree(s.d_meta); cudaFree(s.d_off);
-    cudaFree(s.d_items); cudaFree(s.d_pair_start);
+    cudaFree(s.d_t);  // d_t is the base of the series' single allocation
     s = Series();
 }
 
@@ -737,19 +736,27 @@ MEDGP_API int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, 
         }
     pair_start.back() = (int)items.size();
     s.nitems = (int)items.size();
-    CU(cudaMalloc(&s.d_t, s.npad * 8));
-    CU(cudaMalloc(&s.d_y, s.npad * 8));
-    CU(cudaMalloc(&s.d_meta, s.npad * sizeof(int)));
-    CU(cudaMalloc(&s.d_off, (D + 1) * sizeof(int)));
-    CU(cudaMalloc(&s.d_items, std::max<size_t>(1, items.size()) * sizeof(int4)));
-    CU(cudaMalloc(&s.d_pair_start, pair_start.size() * sizeof(int)));
-    CU(cudaMemcpy(s.d_t, ht.data(), s.npad * 8, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s.d_y, hy.data(), s.npad * 8, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s.d_meta, hm.data(), s.npad * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s.d_off, off.data(), (D + 1) * sizeof(int), cudaMemcpyHostToDevice));
-    if (!items.empty())
-        CU(cudaMemcpy(s.d_items, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s.d_pair_start, pair_start.data(), pair_start.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // one allocation + one copy per series (test-time workloads upload thousands of short ones)
+    const size_t o_t = 0, o_y = o_t + (size_t)s.npad * 8, o_meta = o_y + (size_t)s.npad * 8;
+    const size_t o_off = align_up(o_meta + (size_t)s.npad * 4, 16), o_items = align_up(o_off + (size_t)(D + 1) * 4, 16);
+    const size_t o_pair = o_items + std::max<size_t>(1, items.size()) * sizeof(int4);
+    const size_t total = o_pair + pair_start.size() * sizeof(int);
+    std::vector<char> blob(total, 0);
+    memcpy(blob.data() + o_t, ht.data(), (size_t)s.npad * 8);
+    memcpy(blob.data() + o_y, hy.data(), (size_t)s.npad * 8);
+    memcpy(blob.data() + o_meta, hm.data(), (size_t)s.npad * 4);
+    memcpy(blob.data() + o_off, off.data(), (size_t)(D + 1) * 4);
+    if (!items.empty()) memcpy(blob.data() + o_items, items.data(), items.size() * sizeof(int4));
+    memcpy(blob.data() + o_pair, pair_start.data(), pair_start.size() * sizeof(int));
+    char *d_blob = nullptr;
+    CU(cudaMalloc(&d_blob, total));
+    CU(cudaMemcpy(d_blob, blob.data(), total, cudaMemcpyHostToDevice));
+    s.d_t = (double *)(d_blob + o_t);
+    s.d_y = (double *)(d_blob + o_y);
+    s.d_meta = (int *)(d_blob + o_meta);
+    s.d_off = (int *)(d_blob + o_off);
+    s.d_items = (int4 *)(d_blob + o_items);
+    s.d_pair_start = (int *)(d_blob + o_pair);
     // reuse a dead slot if there is one
     int id = -1;
     for (size_t i = 0; i < ctx->series.size(); i++)

@@ -214,3 +214,29 @@ def test_long_stay_patient(api):
     fn, _, _ = ctx.nlml_grad([sid] * 3, thetas, False)
     assert np.array_equal(fn, f)
     ctx.close()
+
+
+@pytest.mark.parametrize("env,batch", [
+    ({"MEDGP_RL": "1"}, 6),                                 # right-looking potrf / trtri
+    ({"MEDGP_RL": "0"}, 6),                                 # left-looking, one launch per step (k_potrf_step)
+    ({"MEDGP_RL": "0", "MEDGP_FUSE_DIAG": "0"}, 6),         # left-looking, separate kernels, folded diagonal update
+    ({"MEDGP_RL": "0"}, 140),                               # left-looking, separate kernels, large batch
+    ({"MEDGP_RL": "0", "MEDGP_STREAMS": "1", "MEDGP_GRAPHS": "0"}, 140),   # single stream, no CUDA graph
+])
+def test_every_factorisation_path(api, oracle, monkeypatch, env, batch):
+    """all scheduling variants of kernel (2) give the oracle's numbers (n = 330: T = 6)"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    Q, D, R, n = 2, 4, 2, 330
+    pats = [synth.make_patient(D, n - 7 * (k % 3), seed=900 + k) for k in range(batch)]
+    thetas = synth.init_hyp_lmc_sm(Q, D, R, batch, seed=77)
+    ctx = api.Context(Q, D, R, workspace_bytes=2 << 30)
+    sids = [ctx.add_series(*p) for p in pats]
+    f, g, st = ctx.nlml_grad(sids, thetas, True)
+    f2, _, _ = ctx.nlml_grad(sids, thetas, False)
+    ctx.close()
+    assert (st == 0).all() and np.array_equal(f, f2)
+    for k in list(range(0, batch, max(1, batch // 5)))[:6]:
+        f0, g0, _ = oracle.nlml_grad(Q, D, R, *pats[k], thetas[k])
+        assert abs(f[k] - f0) <= RTOL * abs(f0)
+        assert rel(g[k], g0) <= RTOL
