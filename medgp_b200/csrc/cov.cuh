@@ -73,10 +73,12 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
     __shared__ double s_tr[MEDGP_NB], s_tc[MEDGP_NB];
     __shared__ int s_mr[MEDGP_NB], s_mc[MEDGP_NB];
     __shared__ double2 s_csr[MEDGP_QMAX][MEDGP_NB], s_csc[MEDGP_QMAX][MEDGP_NB];
+    __shared__ double s_tab[32];
     const EvalDesc &e = descs[blockIdx.y];
     int ti, tj;
     tri_index(blockIdx.x, ti, tj);
     if (ti >= e.T) return;
+    exp_tab_stage(s_tab);
     const int Q = md.Q, D = md.D, tid = threadIdx.x, n = e.n, ld = e.npad;
     double *sB = sm, *sC = sm + Q * D * D;
     for (int i = tid; i < Q * D * D; i += blockDim.x) sB[i] = e.par[md.oB + i];
@@ -122,7 +124,7 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
             double xarg[QT], ex[QT];
 #pragma unroll
             for (int q = 0; q < QT; q++) xarg[q] = -sC[q] * tau2;
-            exp_nonpos<QT>(xarg, ex);
+            exp_nonpos<QT>(xarg, ex, s_tab);
             val = 0.0;
 #pragma unroll
             for (int q = 0; q < QT; q++) {
@@ -150,7 +152,10 @@ __global__ void __launch_bounds__(128, 3)
 k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
 {
     // one WARP per work item (4 items per CTA): the 3Q+1 partial sums stay in registers and
-    // are combined with shuffles only -- no shared memory, no block barrier.
+    // are combined with shuffles only.
+    __shared__ double s_tab[32];
+    exp_tab_stage(s_tab);
+    __syncthreads();
     const EvalDesc &e = descs[blockIdx.y];
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -181,20 +186,19 @@ k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
             if (i == j) sdiag += w;
             else if (diagblk) w *= 2.0;
             const double tau = tt[i] - tt[j], tau2 = tau * tau;
+            const double wt = w * tau, wt2 = w * tau2;
             double xarg[QT], ex[QT];
 #pragma unroll
             for (int q = 0; q < QT; q++) xarg[q] = -cq[q] * tau2;
-            exp_nonpos<QT>(xarg, ex);
+            exp_nonpos<QT>(xarg, ex, s_tab);
 #pragma unroll
             for (int q = 0; q < QT; q++) {
                 const double2 a = cs[(size_t)q * ld + i], b = cs[(size_t)q * ld + j];
-                const double cosphi = a.x * b.x + a.y * b.y;
-                const double sinphi = a.y * b.x - a.x * b.y;
-                const double wex = w * ex[q];
-                const double wk = wex * cosphi;
-                sk[q] += wk;
-                sm[q] -= wex * (wq[q] * tau) * sinphi;   // km: c_kernel_LMC_SM.cpp:379-384
-                sv[q] -= (2.0 * cq[q] * tau2) * wk;      // kv: c_kernel_LMC_SM.cpp:385-391
+                const double ec = ex[q] * (a.x * b.x + a.y * b.y);  // e cos(phi)
+                const double es = ex[q] * (a.y * b.x - a.x * b.y);  // e sin(phi)
+                sk[q] = fma(w, ec, sk[q]);     // sum w k
+                sm[q] = fma(wt, es, sm[q]);    // sum w tau e sin(phi)      (times -w_q below)
+                sv[q] = fma(wt2, ec, sv[q]);   // sum w tau^2 k             (times -2 c_q below)
             }
         }
         ii += 32;
@@ -215,8 +219,8 @@ k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
 #pragma unroll
         for (int q = 0; q < QT; q++) {
             p[q] = sk[q];
-            p[QT + q] = sm[q];
-            p[2 * QT + q] = sv[q];
+            p[QT + q] = -wq[q] * sm[q];          // km = -phi sin(phi) e, phi = w_q tau   (c_kernel_LMC_SM.cpp:379-384)
+            p[2 * QT + q] = -2.0 * cq[q] * sv[q];  // kv = -4 (PI v)^2 tau^2 k             (c_kernel_LMC_SM.cpp:385-391)
         }
         p[3 * QT] = sdiag;
     }
