@@ -39,7 +39,7 @@ struct __align__(16) EvalDesc {
     const double *t, *y;
     const int *meta, *off;
     const int4 *items;
-    const int *pair_start;
+    const int *seg_start;
     const double *star_t;    // prediction points of this evaluation (device), or null
     const int *star_meta;
     int n, npad, T, nitems;

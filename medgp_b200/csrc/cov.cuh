@@ -142,17 +142,19 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
 // g = 1/2 sum_ij W_ij dK_ij/dtheta over the FULL matrix, W = K^-1 - alpha alpha^T
 // (inference/c_inference_exact.cpp:168-172, kernel/c_kernel_LMC_SM.cpp:198-327), collapsed to
 // block sums per feature pair.  Points are feature-major inside the
-// library, so a work item is a rectangle rows [i0,i1) of feature d  x  all columns of feature
-// e <= d; every element of an item belongs to the same (d, e) and is reduced in registers:
-//   part[item] = [ sum W k_q (Q) | sum W km_q (Q) | sum W kv_q (Q) | sum_{i} W_ii ]
-// For d == e only j <= i is visited and off-diagonal elements count twice, so the sums are
-// those of the full square block.  K^-1 is read once (lower triangle), dK is never stored.
+// library.  A work item (one WARP) is a block of 32 consecutive rows -- lane = row, so the
+// row's time, alpha and cos/sin table entries stay in registers -- against the columns j <= i of
+// ONE column feature f: the column-side operands are the same address for all lanes (one L1
+// wavefront each), K^-1 is read once, coalesced, and dK is never stored.  The 32 rows may
+// belong to several row features ("segments", contiguous lanes); a segmented shuffle reduction
+// leaves each segment's sums in its first lane:
+//   part[(segment, f)] = [ sum W k_q (Q) | sum W km_q (Q) | sum W kv_q (Q) | sum_{i} W_ii ]
+// Only j <= i is visited; off-diagonal elements of a diagonal feature block count twice, so
+// the sums are those of the full square block.
 template <int QT>
 __global__ void __launch_bounds__(128, 3)
 k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
 {
-    // one WARP per work item (4 items per CTA): the 3Q+1 partial sums stay in registers and
-    // are combined with shuffles only.
     __shared__ double s_tab[32];
     exp_tab_stage(s_tab);
     __syncthreads();
@@ -160,67 +162,117 @@ k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (item >= e.nitems) return;
-    const int4 it = e.items[item];
-    const int ld = e.npad, T = e.T;
-    double wq[QT], cq[QT];
+    const int4 it = e.items[item];  // (row block, column feature, column end, first segment id)
+    const int ld = e.npad, T = e.T, f = it.y;
+    const int i = it.x * 32 + lane;
+    const bool valid = i < e.n;
+    const int mi = valid ? __ldg(e.meta + i) : -1;
+    // segments of this row block
+    const int mprev = __shfl_up_sync(0xffffffffu, mi, 1);
+    const unsigned headmask = __ballot_sync(0xffffffffu, valid && (lane == 0 || mi != mprev));
+    const unsigned validmask = __ballot_sync(0xffffffffu, valid);
+    const unsigned upto = (2u << lane) - 1u;  // lanes 0..lane
+    const unsigned higher = headmask & ~upto;
+    const int seg_end = !valid ? lane : (higher ? __ffs(higher) - 2 : 31 - __clz(validmask));
+    const int seg = it.w + __popc(headmask & upto) - 1;
+    const bool head = (headmask >> lane) & 1u;
+
+    double cq[QT];
+    double2 a[QT];
+    const double2 *__restrict__ cs = reinterpret_cast<const double2 *>(e.cs);
 #pragma unroll
     for (int q = 0; q < QT; q++) {
-        wq[q] = __ldg(e.par + md.oW + q);
         cq[q] = __ldg(e.par + md.oC + q);
+        a[q] = valid ? cs[(size_t)q * ld + i] : make_double2(0.0, 0.0);
     }
-    const int d = it.x, f = it.y, i0 = it.z, nr = it.w - it.z;
-    const int j0 = __ldg(e.off + f), nc = __ldg(e.off + f + 1) - j0;
-    const bool diagblk = (d == f);
-    const double2 *__restrict__ cs = reinterpret_cast<const double2 *>(e.cs);
-    const double *__restrict__ M = e.M;
+    const double ti = valid ? e.t[i] : 0.0, ali = valid ? e.alpha[i] : 0.0;
+    const double dbl = (mi == f) ? 2.0 : 1.0;
+    const double *__restrict__ Mrow = e.M + (size_t)(i & (MEDGP_NB - 1));  // + tile + column offset
+    const int tile_i = i >> 6;
     const double *__restrict__ tt = e.t;
     const double *__restrict__ al = e.alpha;
     double sk[QT], sm[QT], sv[QT], sdiag = 0.0;
 #pragma unroll
     for (int q = 0; q < QT; q++) sk[q] = sm[q] = sv[q] = 0.0;
-    int jj = lane / nr, ii = lane - jj * nr;
-    while (jj < nc) {
-        const int i = i0 + ii, j = j0 + jj;
-        if (!(diagblk && j > i)) {
-            double w = M[elem_off(T, i, j)] - al[i] * al[j];
-            if (i == j) sdiag += w;
-            else if (diagblk) w *= 2.0;
-            const double tau = tt[i] - tt[j], tau2 = tau * tau;
-            const double wt = w * tau, wt2 = w * tau2;
-            double xarg[QT], ex[QT];
+    const int j0 = __ldg(e.off + f), j1 = it.z;
+    // column-side operands go through a per-warp shared-memory stage, 32 columns at a time
+    // (lane c fetches column c: coalesced), and are then read back as broadcasts; K^-1 elements
+    // are fetched one group of GU columns ahead of their use.
+    constexpr int GU = 4;
+    __shared__ double s_ct[4][32], s_ca[4][32];
+    __shared__ double2 s_cb[4][QT][32];
+    const int wp = threadIdx.x >> 5;
+    auto fetch = [&](int j) -> double {
+        return (valid && j < j1 && j <= i)
+                   ? Mrow[tile_off(T, tile_i, j >> 6) + (size_t)(j & (MEDGP_NB - 1)) * MEDGP_SLD] : 0.0;
+    };
+    for (int jc = j0; jc < j1; jc += 32) {
+        const int nc = min(32, j1 - jc);
+        __syncwarp();
+        if (lane < nc) {
+            s_ct[wp][lane] = tt[jc + lane];
+            s_ca[wp][lane] = al[jc + lane];
 #pragma unroll
-            for (int q = 0; q < QT; q++) xarg[q] = -cq[q] * tau2;
-            exp_nonpos<QT>(xarg, ex, s_tab);
+            for (int q = 0; q < QT; q++) s_cb[wp][q][lane] = cs[(size_t)q * ld + jc + lane];
+        }
+        double mnext[GU];
 #pragma unroll
-            for (int q = 0; q < QT; q++) {
-                const double2 a = cs[(size_t)q * ld + i], b = cs[(size_t)q * ld + j];
-                const double ec = ex[q] * (a.x * b.x + a.y * b.y);  // e cos(phi)
-                const double es = ex[q] * (a.y * b.x - a.x * b.y);  // e sin(phi)
-                sk[q] = fma(w, ec, sk[q]);     // sum w k
-                sm[q] = fma(wt, es, sm[q]);    // sum w tau e sin(phi)      (times -w_q below)
-                sv[q] = fma(wt2, ec, sv[q]);   // sum w tau^2 k             (times -2 c_q below)
+        for (int u = 0; u < GU; u++) mnext[u] = fetch(jc + u);
+        __syncwarp();
+        for (int c0 = 0; c0 < nc; c0 += GU) {
+            double mcur[GU];
+#pragma unroll
+            for (int u = 0; u < GU; u++) {
+                mcur[u] = mnext[u];
+                mnext[u] = (c0 + GU + u < nc) ? fetch(jc + c0 + GU + u) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < GU; u++) {
+                const int c = c0 + u, j = jc + c;
+                if (c >= nc || !valid || j > i) continue;
+                double w = mcur[u] - ali * s_ca[wp][c];
+                if (i == j) sdiag += w;
+                else w *= dbl;
+                const double tau = ti - s_ct[wp][c], tau2 = tau * tau;
+                const double wt = w * tau, wt2 = w * tau2;
+                double xarg[QT], ex[QT];
+#pragma unroll
+                for (int q = 0; q < QT; q++) xarg[q] = -cq[q] * tau2;
+                exp_nonpos<QT>(xarg, ex, s_tab);
+#pragma unroll
+                for (int q = 0; q < QT; q++) {
+                    const double2 b = s_cb[wp][q][c];
+                    const double ec = ex[q] * (a[q].x * b.x + a[q].y * b.y);  // e cos(phi)
+                    const double es = ex[q] * (a[q].y * b.x - a[q].x * b.y);  // e sin(phi)
+                    sk[q] = fma(w, ec, sk[q]);    // sum w k
+                    sm[q] = fma(wt, es, sm[q]);   // sum w tau e sin(phi)      (times -w_q below)
+                    sv[q] = fma(wt2, ec, sv[q]);  // sum w tau^2 k             (times -2 c_q below)
+                }
             }
         }
-        ii += 32;
-        while (ii >= nr) { ii -= nr; jj++; }
     }
+    // segmented reduction: afterwards the first lane of every segment holds the segment's sums
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 1; o < 32; o <<= 1) {
+        const bool take = lane + o <= seg_end;
 #pragma unroll
         for (int q = 0; q < QT; q++) {
-            sk[q] += __shfl_xor_sync(0xffffffffu, sk[q], o);
-            sm[q] += __shfl_xor_sync(0xffffffffu, sm[q], o);
-            sv[q] += __shfl_xor_sync(0xffffffffu, sv[q], o);
+            const double x0 = __shfl_down_sync(0xffffffffu, sk[q], o);
+            const double x1 = __shfl_down_sync(0xffffffffu, sm[q], o);
+            const double x2 = __shfl_down_sync(0xffffffffu, sv[q], o);
+            if (take) { sk[q] += x0; sm[q] += x1; sv[q] += x2; }
         }
-        sdiag += __shfl_xor_sync(0xffffffffu, sdiag, o);
+        const double x3 = __shfl_down_sync(0xffffffffu, sdiag, o);
+        if (take) sdiag += x3;
     }
-    if (lane == 0) {
-        double *p = e.part + (size_t)item * (3 * QT + 1);
+    if (head && mi >= f) {  // (d = mi, f) with f > d is never read
+        double *p = e.part + ((size_t)seg * md.D + f) * (3 * QT + 1);
 #pragma unroll
         for (int q = 0; q < QT; q++) {
+            const double wq = __ldg(e.par + md.oW + q);
             p[q] = sk[q];
-            p[QT + q] = -wq[q] * sm[q];          // km = -phi sin(phi) e, phi = w_q tau   (c_kernel_LMC_SM.cpp:379-384)
-            p[2 * QT + q] = -2.0 * cq[q] * sv[q];  // kv = -4 (PI v)^2 tau^2 k             (c_kernel_LMC_SM.cpp:385-391)
+            p[QT + q] = -wq * sm[q];                 // km = -phi sin(phi) e, phi = w_q tau   (c_kernel_LMC_SM.cpp:379-384)
+            p[2 * QT + q] = -2.0 * cq[q] * sv[q];    // kv = -4 (PI v)^2 tau^2 k             (c_kernel_LMC_SM.cpp:385-391)
         }
         p[3 * QT] = sdiag;
     }
@@ -247,12 +299,13 @@ k_grad_finish(const EvalDesc *__restrict__ descs, ModelDims md, double *__restri
         int d, f;
         tri_index(p, d, f);
         double sk = 0.0, smu = 0.0, sv = 0.0;
-        for (int itx = e.pair_start[p]; itx < e.pair_start[p + 1]; itx++) {
-            const double *row = e.part + (size_t)itx * W;
-            sk += row[q];
-            smu += row[Q + q];
-            sv += row[2 * Q + q];
-        }
+        if (e.off[f + 1] > e.off[f])  // (segment, f) parts exist only for non-empty column features
+            for (int sg = e.seg_start[d]; sg < e.seg_start[d + 1]; sg++) {
+                const double *row = e.part + ((size_t)sg * D + f) * W;
+                sk += row[q];
+                smu += row[Q + q];
+                sv += row[2 * Q + q];
+            }
         S[(q * D + d) * D + f] = sk;
         S[(q * D + f) * D + d] = sk;
         const double b = par[md.oB + (q * D + d) * D + f] * (d == f ? 1.0 : 2.0);
@@ -260,10 +313,9 @@ k_grad_finish(const EvalDesc *__restrict__ descs, ModelDims md, double *__restri
         gv[idx] = b * sv;
     }
     for (int d = tid; d < D; d += blockDim.x) {
-        const int p = d * (d + 1) / 2 + d;
         double s = 0.0;
-        for (int itx = e.pair_start[p]; itx < e.pair_start[p + 1]; itx++)
-            s += e.part[(size_t)itx * W + 3 * Q];
+        for (int sg = e.seg_start[d]; sg < e.seg_start[d + 1]; sg++)
+            s += e.part[((size_t)sg * D + d) * W + 3 * Q];
         dg[d] = s;
     }
     __syncthreads();

@@ -28,14 +28,14 @@
 
 namespace {
 
-constexpr int kGradRows = 32;   // rows per gradient work item
+constexpr int kGradRows = 32;   // rows per gradient work item (= one warp, lane per row)
 constexpr int kMaxJitter = 10;  // inference/c_inference_exact.cpp:99
 
 struct Series {
     bool alive = false;
-    int n = 0, npad = 0, T = 0, nitems = 0;
+    int n = 0, npad = 0, T = 0, nitems = 0, nseg = 0;
     double *d_t = nullptr, *d_y = nullptr;
-    int *d_meta = nullptr, *d_off = nullptr, *d_pair_start = nullptr;
+    int *d_meta = nullptr, *d_off = nullptr, *d_seg_start = nullptr;
     int4 *d_items = nullptr;
     std::vector<int> perm;  // internal position -> caller position
 };
@@ -131,7 +131,7 @@ size_t eval_bytes(const ModelDims &md, const Series &s, int nrhs, bool grad)
     b += align_up((size_t)md.parLen * 8, 256);             // par
     b += align_up((size_t)s.T * 8, 256);                   // blk
     b += align_up((size_t)s.T * 4, 256);                   // flags
-    if (grad) b += align_up((size_t)s.nitems * (3 * md.Q + 1) * 8, 256);
+    if (grad) b += align_up((size_t)s.nseg * md.D * (3 * md.Q + 1) * 8, 256);
     return b;
 }
 
@@ -459,9 +459,9 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
                 e.par = (double *)take((size_t)md.parLen * 8);
                 e.blk = (double *)take((size_t)s.T * 8);
                 e.flags = (int *)take((size_t)s.T * 4);
-                e.part = grad ? (double *)take((size_t)s.nitems * (3 * md.Q + 1) * 8) : nullptr;
+                e.part = grad ? (double *)take((size_t)s.nseg * md.D * (3 * md.Q + 1) * 8) : nullptr;
                 e.t = s.d_t; e.y = s.d_y; e.meta = s.d_meta; e.off = s.d_off;
-                e.items = s.d_items; e.pair_start = s.d_pair_start;
+                e.items = s.d_items; e.seg_start = s.d_seg_start;
                 e.star_t = pred ? ctx->d_star_t + rq.star_off : nullptr;
                 e.star_meta = pred ? ctx->d_star_meta + rq.star_off : nullptr;
                 e.n = s.n; e.npad = s.npad; e.T = s.T; e.nitems = s.nitems;
@@ -724,30 +724,37 @@ MEDGP_API int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, 
         off[meta[src] + 1]++;
     }
     for (int d = 0; d < D; d++) off[d + 1] += off[d];
+    // gradient work items: (block of 32 rows) x (column feature f with columns <= the block's
+    // last row); a row block's rows split into segments of equal feature, numbered globally in
+    // row order, so the segments of feature d are seg_start[d] .. seg_start[d+1]-1.
     std::vector<int4> items;
-    std::vector<int> pair_start(D * (D + 1) / 2 + 1, 0);
-    for (int d = 0; d < D; d++)
-        for (int f = 0; f <= d; f++) {
-            const int p = d * (d + 1) / 2 + f;
-            pair_start[p] = (int)items.size();
-            if (off[f + 1] > off[f])
-                for (int i0 = off[d]; i0 < off[d + 1]; i0 += kGradRows)
-                    items.push_back(make_int4(d, f, i0, std::min(i0 + kGradRows, off[d + 1])));
-        }
-    pair_start.back() = (int)items.size();
+    std::vector<int> seg_start(D + 1, 0);
+    int nseg = 0;
+    for (int i0 = 0; i0 < n; i0 += kGradRows) {
+        const int i1 = std::min(i0 + kGradRows, n);
+        for (int f = 0; f < D && off[f] < i1; f++)
+            if (off[f + 1] > off[f]) items.push_back(make_int4(i0 / kGradRows, f, std::min(off[f + 1], i1), nseg));
+        for (int i = i0; i < i1; i++)
+            if (i == i0 || hm[i] != hm[i - 1]) {
+                seg_start[hm[i] + 1]++;
+                nseg++;
+            }
+    }
+    for (int d = 0; d < D; d++) seg_start[d + 1] += seg_start[d];
     s.nitems = (int)items.size();
+    s.nseg = nseg;
     // one allocation + one copy per series (test-time workloads upload thousands of short ones)
     const size_t o_t = 0, o_y = o_t + (size_t)s.npad * 8, o_meta = o_y + (size_t)s.npad * 8;
     const size_t o_off = align_up(o_meta + (size_t)s.npad * 4, 16), o_items = align_up(o_off + (size_t)(D + 1) * 4, 16);
     const size_t o_pair = o_items + std::max<size_t>(1, items.size()) * sizeof(int4);
-    const size_t total = o_pair + pair_start.size() * sizeof(int);
+    const size_t total = o_pair + seg_start.size() * sizeof(int);
     std::vector<char> blob(total, 0);
     memcpy(blob.data() + o_t, ht.data(), (size_t)s.npad * 8);
     memcpy(blob.data() + o_y, hy.data(), (size_t)s.npad * 8);
     memcpy(blob.data() + o_meta, hm.data(), (size_t)s.npad * 4);
     memcpy(blob.data() + o_off, off.data(), (size_t)(D + 1) * 4);
     if (!items.empty()) memcpy(blob.data() + o_items, items.data(), items.size() * sizeof(int4));
-    memcpy(blob.data() + o_pair, pair_start.data(), pair_start.size() * sizeof(int));
+    memcpy(blob.data() + o_pair, seg_start.data(), seg_start.size() * sizeof(int));
     char *d_blob = nullptr;
     CU(cudaMalloc(&d_blob, total));
     CU(cudaMemcpy(d_blob, blob.data(), total, cudaMemcpyHostToDevice));
@@ -756,7 +763,7 @@ MEDGP_API int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, 
     s.d_meta = (int *)(d_blob + o_meta);
     s.d_off = (int *)(d_blob + o_off);
     s.d_items = (int4 *)(d_blob + o_items);
-    s.d_pair_start = (int *)(d_blob + o_pair);
+    s.d_seg_start = (int *)(d_blob + o_pair);
     // reuse a dead slot if there is one
     int id = -1;
     for (size_t i = 0; i < ctx->series.size(); i++)
