@@ -46,6 +46,8 @@ struct __align__(16) EvalDesc {
     int jitter, nrhs, nstar, out_index;
     int star_out;            // offset of this evaluation's predictions in the output arrays
     int pad0;
+    double trange2;          // (max t - min t)^2 of the series: bounds every tau^2 of the training block
+    double pad1;
 };
 
 // tile-major addressing (kTileElems doubles per tile, column pitch MEDGP_SLD)
@@ -134,6 +136,19 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// per-thread asynchronous global->shared copies (LDGSTS) for warp-private double buffering
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem, const void *gmem)
+{
+    if (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem)), "l"(gmem), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---------------------------------------------------------------------------------------
 // exp(x) for x <= 0, NV values at once.  The covariance kernels need one exp per mixture
 // component per point pair; libdevice's exp() gets serialised per component, which leaves the
@@ -159,33 +174,47 @@ __device__ __forceinline__ void exp_tab_stage(double *s_tab)  // call by >= 32 t
     if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
 }
 
-template <int NV>
+// polynomial and reduction constants live in constant memory so that the DFMAs take them as
+// constant-bank operands instead of re-materialising 64-bit immediates in registers
+__constant__ double c_expc[10] = {
+    46.16624130844683,        // 0: 32/ln2
+    0.021660849391992087,     // 1: ln2/32 high part (low 18 mantissa bits zero)
+    5.062034433330175e-13,    // 2: ln2/32 low part
+    1.38888888888888888889e-03, 8.33333333333333333333e-03, 4.16666666666666666667e-02,
+    1.66666666666666666667e-01, 0.5, 1.0, 1.0};  // 3..9: 1/6! .. 1/0!
+
+// Largest |x| for which the unchecked variant is valid (k = x*32/ln2 must fit 32 bits).
+#define MEDGP_EXP_UNCHECKED_MAX 4.0e7
+
+// CHECKED: any x <= 0 (x < -708 gives exactly 0).  !CHECKED: requires x >= -MEDGP_EXP_UNCHECKED_MAX;
+// results below 2^-1022 come out as some value < 2^-1021 instead of exactly 0 (the exponent
+// field saturates at 0), which saves a compare and two selects per value.
+template <int NV, bool CHECKED = true>
 __device__ __forceinline__ void exp_nonpos(const double (&x)[NV], double (&out)[NV], const double *s_tab)
 {
-    const double INV = 46.16624130844683, HI = 0.021660849391992087, LO = 5.062034433330175e-13,
-                 MAGIC = 6755399441055744.0;  // 32/ln2 ; ln2/32 = HI + LO ; 1.5 * 2^52
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
     double r[NV], p[NV];
     int k[NV];
 #pragma unroll
     for (int i = 0; i < NV; i++) {
-        const double t = fma(x[i], INV, MAGIC);
+        const double t = fma(x[i], c_expc[0], MAGIC);
         k[i] = __double2loint(t);
         const double kf = t - MAGIC;
-        r[i] = fma(-kf, HI, x[i]);
-        r[i] = fma(-kf, LO, r[i]);
-        p[i] = 1.38888888888888888889e-03;  // 1/6!
+        r[i] = fma(-kf, c_expc[1], x[i]);
+        r[i] = fma(-kf, c_expc[2], r[i]);
+        p[i] = c_expc[3];
     }
-    const double C[6] = {8.33333333333333333333e-03, 4.16666666666666666667e-02, 1.66666666666666666667e-01,
-                         0.5, 1.0, 1.0};  // 1/5! ... 1/0!
 #pragma unroll
-    for (int c = 0; c < 6; c++)
+    for (int c = 4; c < 10; c++)
 #pragma unroll
-        for (int i = 0; i < NV; i++) p[i] = fma(p[i], r[i], C[c]);
+        for (int i = 0; i < NV; i++) p[i] = fma(p[i], r[i], c_expc[c]);
 #pragma unroll
     for (int i = 0; i < NV; i++) {
         const double tj = s_tab[k[i] & 31];
-        const double scale = __hiloint2double(__double2hiint(tj) + ((k[i] >> 5) << 20), __double2loint(tj));
-        out[i] = (x[i] < -708.0) ? 0.0 : p[i] * scale;
+        int m = k[i] >> 5;
+        if (!CHECKED) m = max(m, -1023);  // exponent field saturates at 0
+        const double v = p[i] * __hiloint2double(__double2hiint(tj) + (m << 20), __double2loint(tj));
+        out[i] = (CHECKED && x[i] < -708.0) ? 0.0 : v;
     }
 }
 

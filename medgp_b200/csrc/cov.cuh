@@ -110,6 +110,10 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
 #pragma unroll
     for (int q = 0; q < QT; q++) arow[q] = s_csr[q][r];
     const double *brow = sB + mr * D;  // + q*D*D + mc
+    double cmax = 0.0;
+#pragma unroll
+    for (int q = 0; q < QT; q++) cmax = fmax(cmax, sC[q]);
+    const bool fastexp = cmax * e.trange2 < MEDGP_EXP_UNCHECKED_MAX;  // uniform per evaluation
     const int DD = D * D;
 #pragma unroll 2
     for (int u = 0; u < 16; u++) {
@@ -124,7 +128,8 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
             double xarg[QT], ex[QT];
 #pragma unroll
             for (int q = 0; q < QT; q++) xarg[q] = -sC[q] * tau2;
-            exp_nonpos<QT>(xarg, ex, s_tab);
+            if (fastexp) exp_nonpos<QT, false>(xarg, ex, s_tab);
+            else exp_nonpos<QT, true>(xarg, ex, s_tab);
             val = 0.0;
 #pragma unroll
             for (int q = 0; q < QT; q++) {
@@ -143,31 +148,132 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
 // (inference/c_inference_exact.cpp:168-172, kernel/c_kernel_LMC_SM.cpp:198-327), collapsed to
 // block sums per feature pair.  Points are feature-major inside the
 // library.  A work item (one WARP) is a block of 32 consecutive rows -- lane = row, so the
-// row's time, alpha and cos/sin table entries stay in registers -- against the columns j <= i of
-// ONE column feature f: the column-side operands are the same address for all lanes (one L1
-// wavefront each), K^-1 is read once, coalesced, and dK is never stored.  The 32 rows may
-// belong to several row features ("segments", contiguous lanes); a segmented shuffle reduction
-// leaves each segment's sums in its first lane:
+// row's time, alpha and cos/sin table entries stay in registers -- against a range of columns
+// [jb, je), je <= the block's last row + 1, cut at feature boundaries.  The columns stream
+// through a warp-private double-buffered shared-memory stage, MEDGP_GC columns at a time,
+// filled with per-thread asynchronous copies (LDGSTS) one chunk ahead of the arithmetic:
+// the 32 x GC block of K^-1 (each element read exactly once from HBM) and the column-side
+// time / alpha / feature / cos-sin entries, which are then read back as broadcasts.
+// dK is never stored.  The 32 rows may belong to several row features ("segments", contiguous
+// lanes); whenever the column feature changes a segmented shuffle reduction leaves each
+// segment's sums in its first lane:
 //   part[(segment, f)] = [ sum W k_q (Q) | sum W km_q (Q) | sum W kv_q (Q) | sum_{i} W_ii ]
 // Only j <= i is visited; off-diagonal elements of a diagonal feature block count twice, so
 // the sums are those of the full square block.
+#define MEDGP_GC 16
+
 template <int QT>
-__global__ void __launch_bounds__(128, 3)
-k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
+struct __align__(16) GradStage {
+    double m[MEDGP_GC][32];      // K^-1[row block][column], column-major
+    double2 b[QT][MEDGP_GC];     // (cos, sin)(w_q t_j)
+    double t[MEDGP_GC], al[MEDGP_GC];
+    int f[MEDGP_GC];             // feature of column j
+};
+
+template <int QT>
+struct GradAcc {
+    double sk[QT], sm[QT], sv[QT], sdiag;
+};
+
+// one column's contribution for this lane's row.  w = weight * (K^-1 - alpha alpha^T)_ij.
+template <int QT, bool CHECKED>
+__device__ __forceinline__ void grad_column(GradAcc<QT> &acc, double w, double tau, const double (&cq)[QT],
+                                            const double2 (&a)[QT], const double2 *s_b /* [q * GC] */,
+                                            const double *s_tab)
 {
-    __shared__ double s_tab[32];
-    exp_tab_stage(s_tab);
-    __syncthreads();
-    const EvalDesc &e = descs[blockIdx.y];
-    const int lane = threadIdx.x & 31;
-    const int item = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (item >= e.nitems) return;
-    const int4 it = e.items[item];  // (row block, column feature, column end, first segment id)
-    const int ld = e.npad, T = e.T, f = it.y;
-    const int i = it.x * 32 + lane;
+    const double tau2 = tau * tau;
+    const double wt = w * tau, wt2 = w * tau2;
+    double xarg[QT], ex[QT];
+#pragma unroll
+    for (int q = 0; q < QT; q++) xarg[q] = -cq[q] * tau2;
+    exp_nonpos<QT, CHECKED>(xarg, ex, s_tab);
+#pragma unroll
+    for (int q = 0; q < QT; q++) {
+        const double2 b = s_b[q * MEDGP_GC];
+        const double ec = ex[q] * (a[q].x * b.x + a[q].y * b.y);  // e cos(phi)
+        const double es = ex[q] * (a[q].y * b.x - a[q].x * b.y);  // e sin(phi)
+        acc.sk[q] = fma(w, ec, acc.sk[q]);    // sum w k
+        acc.sm[q] = fma(wt, es, acc.sm[q]);   // sum w tau e sin(phi)      (times -w_q at the end)
+        acc.sv[q] = fma(wt2, ec, acc.sv[q]);  // sum w tau^2 k             (times -2 c_q at the end)
+    }
+}
+
+// segmented reduction over the lanes of each row segment, then the segment heads store the
+// sums of column feature f and the accumulators restart.
+template <int QT>
+__device__ __forceinline__ void grad_flush(GradAcc<QT> &acc, const EvalDesc &e, const ModelDims &md, int lane,
+                                           int seg_end, bool head, int mi, int seg, int f,
+                                           const double (&cq)[QT])
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const bool take = lane + o <= seg_end;
+#pragma unroll
+        for (int q = 0; q < QT; q++) {
+            const double x0 = __shfl_down_sync(0xffffffffu, acc.sk[q], o);
+            const double x1 = __shfl_down_sync(0xffffffffu, acc.sm[q], o);
+            const double x2 = __shfl_down_sync(0xffffffffu, acc.sv[q], o);
+            if (take) { acc.sk[q] += x0; acc.sm[q] += x1; acc.sv[q] += x2; }
+        }
+        const double x3 = __shfl_down_sync(0xffffffffu, acc.sdiag, o);
+        if (take) acc.sdiag += x3;
+    }
+    if (head && mi >= f) {  // (d = mi, f) with f > d is never read
+        double *p = e.part + ((size_t)seg * md.D + f) * (3 * QT + 1);
+#pragma unroll
+        for (int q = 0; q < QT; q++) {
+            const double wq = __ldg(e.par + md.oW + q);
+            p[q] = acc.sk[q];
+            p[QT + q] = -wq * acc.sm[q];               // km = -phi sin(phi) e, phi = w_q tau   (c_kernel_LMC_SM.cpp:379-384)
+            p[2 * QT + q] = -2.0 * cq[q] * acc.sv[q];  // kv = -4 (PI v)^2 tau^2 k             (c_kernel_LMC_SM.cpp:385-391)
+        }
+        p[3 * QT] = acc.sdiag;
+    }
+#pragma unroll
+    for (int q = 0; q < QT; q++) acc.sk[q] = acc.sm[q] = acc.sv[q] = 0.0;
+    acc.sdiag = 0.0;
+}
+
+template <int QT, bool CHECKED>
+__device__ __forceinline__ void grad_item(const EvalDesc &e, const ModelDims &md, const int4 it, int lane,
+                                          GradStage<QT> *stage, const double *s_tab)
+{
+    const int ld = e.npad, T = e.T;
+    const int ifirst = it.x * 32, i = ifirst + lane, jb = it.y, je = it.z;
     const bool valid = i < e.n;
+    const double2 *__restrict__ cs = reinterpret_cast<const double2 *>(e.cs);
+    const double *__restrict__ Mblk = e.M + tile_off(T, ifirst >> 6, 0) + (size_t)(ifirst & (MEDGP_NB - 1));
+    const size_t tile_col = (size_t)T * (MEDGP_NB * MEDGP_SLD);  // tile (ti, tj) -> (ti, tj + 1)
+
+    auto issue = [&](int ch) {
+        GradStage<QT> &st = stage[ch & 1];
+        const int jc = jb + ch * MEDGP_GC;
+#pragma unroll
+        for (int k = 0; k < MEDGP_GC / 2; k++) {  // 32 lanes x 16 B = two 256 B column segments per trip
+            const int c = 2 * k + (lane >> 4), part = lane & 15, j = min(jc + c, je - 1);
+            cp_async<16>(&st.m[c][part * 2],
+                         Mblk + (size_t)(j >> 6) * tile_col + (size_t)(j & (MEDGP_NB - 1)) * MEDGP_SLD + part * 2);
+        }
+        {
+            const int c = lane & 15, j = min(jc + c, je - 1);
+            if (lane < 16) {
+                cp_async<8>(&st.t[c], e.t + j);
+                cp_async<4>(&st.f[c], e.meta + j);
+            } else {
+                cp_async<8>(&st.al[c], e.alpha + j);
+            }
+        }
+        for (int p = lane; p < QT * MEDGP_GC; p += 32) {
+            const int q = p / MEDGP_GC, c = p % MEDGP_GC, j = min(jc + c, je - 1);
+            cp_async<16>(&st.b[q][c], cs + (size_t)q * ld + j);
+        }
+        cp_async_commit();
+    };
+    const int nch = (je - jb + MEDGP_GC - 1) / MEDGP_GC;
+    issue(0);
+
+    // row-side data and the segments of this row block (overlaps the first copies)
     const int mi = valid ? __ldg(e.meta + i) : -1;
-    // segments of this row block
     const int mprev = __shfl_up_sync(0xffffffffu, mi, 1);
     const unsigned headmask = __ballot_sync(0xffffffffu, valid && (lane == 0 || mi != mprev));
     const unsigned validmask = __ballot_sync(0xffffffffu, valid);
@@ -176,107 +282,82 @@ k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
     const int seg_end = !valid ? lane : (higher ? __ffs(higher) - 2 : 31 - __clz(validmask));
     const int seg = it.w + __popc(headmask & upto) - 1;
     const bool head = (headmask >> lane) & 1u;
-
     double cq[QT];
     double2 a[QT];
-    const double2 *__restrict__ cs = reinterpret_cast<const double2 *>(e.cs);
 #pragma unroll
     for (int q = 0; q < QT; q++) {
         cq[q] = __ldg(e.par + md.oC + q);
         a[q] = valid ? cs[(size_t)q * ld + i] : make_double2(0.0, 0.0);
     }
     const double ti = valid ? e.t[i] : 0.0, ali = valid ? e.alpha[i] : 0.0;
-    const double dbl = (mi == f) ? 2.0 : 1.0;
-    const double *__restrict__ Mrow = e.M + (size_t)(i & (MEDGP_NB - 1));  // + tile + column offset
-    const int tile_i = i >> 6;
-    const double *__restrict__ tt = e.t;
-    const double *__restrict__ al = e.alpha;
-    double sk[QT], sm[QT], sv[QT], sdiag = 0.0;
+    GradAcc<QT> acc;
 #pragma unroll
-    for (int q = 0; q < QT; q++) sk[q] = sm[q] = sv[q] = 0.0;
-    const int j0 = __ldg(e.off + f), j1 = it.z;
-    // column-side operands go through a per-warp shared-memory stage, 32 columns at a time
-    // (lane c fetches column c: coalesced), and are then read back as broadcasts; K^-1 elements
-    // are fetched one group of GU columns ahead of their use.
-    constexpr int GU = 4;
-    __shared__ double s_ct[4][32], s_ca[4][32];
-    __shared__ double2 s_cb[4][QT][32];
-    const int wp = threadIdx.x >> 5;
-    auto fetch = [&](int j) -> double {
-        return (valid && j < j1 && j <= i)
-                   ? Mrow[tile_off(T, tile_i, j >> 6) + (size_t)(j & (MEDGP_NB - 1)) * MEDGP_SLD] : 0.0;
-    };
-    for (int jc = j0; jc < j1; jc += 32) {
-        const int nc = min(32, j1 - jc);
-        __syncwarp();
-        if (lane < nc) {
-            s_ct[wp][lane] = tt[jc + lane];
-            s_ca[wp][lane] = al[jc + lane];
-#pragma unroll
-            for (int q = 0; q < QT; q++) s_cb[wp][q][lane] = cs[(size_t)q * ld + jc + lane];
+    for (int q = 0; q < QT; q++) acc.sk[q] = acc.sm[q] = acc.sv[q] = 0.0;
+    acc.sdiag = 0.0;
+    int fcur = -1;
+    double dbl = 1.0;
+
+    for (int ch = 0; ch < nch; ch++) {
+        if (ch + 1 < nch) {
+            issue(ch + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
-        double mnext[GU];
-#pragma unroll
-        for (int u = 0; u < GU; u++) mnext[u] = fetch(jc + u);
         __syncwarp();
-        for (int c0 = 0; c0 < nc; c0 += GU) {
-            double mcur[GU];
-#pragma unroll
-            for (int u = 0; u < GU; u++) {
-                mcur[u] = mnext[u];
-                mnext[u] = (c0 + GU + u < nc) ? fetch(jc + c0 + GU + u) : 0.0;
+        const GradStage<QT> &st = stage[ch & 1];
+        const int jc = jb + ch * MEDGP_GC, nc = min(MEDGP_GC, je - jc);
+        for (int c = 0; c < nc; c++) {
+            const int j = jc + c, fc = st.f[c];
+            if (fc != fcur) {  // uniform: the column feature changed
+                if (fcur >= 0) grad_flush<QT>(acc, e, md, lane, seg_end, head, mi, seg, fcur, cq);
+                fcur = fc;
+                dbl = (mi == fc) ? 2.0 : 1.0;
             }
+            const double m = st.m[c][lane];
+            if (j < ifirst) {
+                // below every row of the block: no per-lane predicate.  Lanes past the end of
+                // the series carry a = 0 and read finite padding rows: they add exact zeros.
+                grad_column<QT, CHECKED>(acc, (m - ali * st.al[c]) * dbl, ti - st.t[c], cq, a, &st.b[0][c], s_tab);
+            } else if (valid && j < i) {
+                grad_column<QT, CHECKED>(acc, (m - ali * st.al[c]) * dbl, ti - st.t[c], cq, a, &st.b[0][c], s_tab);
+            } else if (valid && j == i) {  // the diagonal element: tau = 0, weight 1
+                const double wd = m - ali * ali;
+                acc.sdiag += wd;
 #pragma unroll
-            for (int u = 0; u < GU; u++) {
-                const int c = c0 + u, j = jc + c;
-                if (c >= nc || !valid || j > i) continue;
-                double w = mcur[u] - ali * s_ca[wp][c];
-                if (i == j) sdiag += w;
-                else w *= dbl;
-                const double tau = ti - s_ct[wp][c], tau2 = tau * tau;
-                const double wt = w * tau, wt2 = w * tau2;
-                double xarg[QT], ex[QT];
-#pragma unroll
-                for (int q = 0; q < QT; q++) xarg[q] = -cq[q] * tau2;
-                exp_nonpos<QT>(xarg, ex, s_tab);
-#pragma unroll
-                for (int q = 0; q < QT; q++) {
-                    const double2 b = s_cb[wp][q][c];
-                    const double ec = ex[q] * (a[q].x * b.x + a[q].y * b.y);  // e cos(phi)
-                    const double es = ex[q] * (a[q].y * b.x - a[q].x * b.y);  // e sin(phi)
-                    sk[q] = fma(w, ec, sk[q]);    // sum w k
-                    sm[q] = fma(wt, es, sm[q]);   // sum w tau e sin(phi)      (times -w_q below)
-                    sv[q] = fma(wt2, ec, sv[q]);  // sum w tau^2 k             (times -2 c_q below)
-                }
+                for (int q = 0; q < QT; q++) acc.sk[q] = fma(wd, a[q].x * a[q].x + a[q].y * a[q].y, acc.sk[q]);
             }
         }
+        __syncwarp();  // everyone is done with this stage before it is refilled
     }
-    // segmented reduction: afterwards the first lane of every segment holds the segment's sums
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const bool take = lane + o <= seg_end;
-#pragma unroll
-        for (int q = 0; q < QT; q++) {
-            const double x0 = __shfl_down_sync(0xffffffffu, sk[q], o);
-            const double x1 = __shfl_down_sync(0xffffffffu, sm[q], o);
-            const double x2 = __shfl_down_sync(0xffffffffu, sv[q], o);
-            if (take) { sk[q] += x0; sm[q] += x1; sv[q] += x2; }
-        }
-        const double x3 = __shfl_down_sync(0xffffffffu, sdiag, o);
-        if (take) sdiag += x3;
-    }
-    if (head && mi >= f) {  // (d = mi, f) with f > d is never read
-        double *p = e.part + ((size_t)seg * md.D + f) * (3 * QT + 1);
-#pragma unroll
-        for (int q = 0; q < QT; q++) {
-            const double wq = __ldg(e.par + md.oW + q);
-            p[q] = sk[q];
-            p[QT + q] = -wq * sm[q];                 // km = -phi sin(phi) e, phi = w_q tau   (c_kernel_LMC_SM.cpp:379-384)
-            p[2 * QT + q] = -2.0 * cq[q] * sv[q];    // kv = -4 (PI v)^2 tau^2 k             (c_kernel_LMC_SM.cpp:385-391)
-        }
-        p[3 * QT] = sdiag;
-    }
+    grad_flush<QT>(acc, e, md, lane, seg_end, head, mi, seg, fcur, cq);
 }
+
+template <int QT>
+__global__ void __launch_bounds__(128, 3)
+k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
+{
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ double s_tab[32];
+    exp_tab_stage(s_tab);
+    __syncthreads();
+    const EvalDesc &e = descs[blockIdx.y];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int item = blockIdx.x * 4 + wp;
+    if (item >= e.nitems) return;
+    const int4 it = e.items[item];  // (row block, first column, column end, first segment id)
+    GradStage<QT> *stage = reinterpret_cast<GradStage<QT> *>(dsm) + 2 * wp;
+    double cmax = 0.0;
+#pragma unroll
+    for (int q = 0; q < QT; q++) cmax = fmax(cmax, __ldg(e.par + md.oC + q));
+    if (cmax * e.trange2 < MEDGP_EXP_UNCHECKED_MAX)  // uniform per evaluation
+        grad_item<QT, false>(e, md, it, lane, stage, s_tab);
+    else
+        grad_item<QT, true>(e, md, it, lane, stage, s_tab);
+}
+
+template <int QT>
+constexpr int grad_smem_bytes() { return 4 * 2 * (int)sizeof(GradStage<QT>); }
 
 // Gradient epilogue, one CTA per evaluation (deterministic: fixed summation order):
 //   noise   g_d        = sigma_d^2 sum_{i in d} W_ii                inference/c_inference_exact.cpp:191-203

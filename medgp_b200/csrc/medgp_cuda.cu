@@ -29,11 +29,13 @@
 namespace {
 
 constexpr int kGradRows = 32;   // rows per gradient work item (= one warp, lane per row)
+constexpr int kGradCols = 96;   // target columns per gradient work item
 constexpr int kMaxJitter = 10;  // inference/c_inference_exact.cpp:99
 
 struct Series {
     bool alive = false;
     int n = 0, npad = 0, T = 0, nitems = 0, nseg = 0;
+    double trange2 = 0.0;   // (max t - min t)^2
     double *d_t = nullptr, *d_y = nullptr;
     int *d_meta = nullptr, *d_off = nullptr, *d_seg_start = nullptr;
     int4 *d_items = nullptr;
@@ -248,7 +250,7 @@ struct SubChunk {
 template <int QT>
 void launch_grad_q(dim3 gg, cudaStream_t st, const EvalDesc *dd, const ModelDims &md)
 {
-    k_grad<QT><<<gg, 128, 0, st>>>(dd, md);
+    k_grad<QT><<<gg, 128, grad_smem_bytes<QT>(), st>>>(dd, md);
 }
 
 template <int QT>
@@ -272,7 +274,11 @@ void launch_assemble(int Q, dim3 gg, int smem, cudaStream_t st, const EvalDesc *
 }
 
 template <int QT>
-void set_assemble_smem_q(int bytes) { cudaFuncSetAttribute(k_assemble<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
+void set_assemble_smem_q(int bytes)
+{
+    cudaFuncSetAttribute(k_assemble<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_grad<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, grad_smem_bytes<QT>());
+}
 
 void launch_grad(int Q, dim3 gg, cudaStream_t st, const EvalDesc *dd, const ModelDims &md)
 {
@@ -467,7 +473,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
                 e.n = s.n; e.npad = s.npad; e.T = s.T; e.nitems = s.nitems;
                 e.jitter = rq.jitter; e.nrhs = 1 + rq.nstar; e.nstar = rq.nstar;
                 e.out_index = rq.out_index; e.star_out = rq.star_off;
-                e.pad0 = 0;
+                e.pad0 = 0; e.trange2 = s.trange2; e.pad1 = 0.0;
                 sc.T.push_back(s.T);
                 sc.cnt++;
                 sc.Tmax = std::max(sc.Tmax, s.T);
@@ -724,16 +730,27 @@ MEDGP_API int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, 
         off[meta[src] + 1]++;
     }
     for (int d = 0; d < D; d++) off[d + 1] += off[d];
-    // gradient work items: (block of 32 rows) x (column feature f with columns <= the block's
-    // last row); a row block's rows split into segments of equal feature, numbered globally in
-    // row order, so the segments of feature d are seg_start[d] .. seg_start[d+1]-1.
+    {
+        const auto mm = std::minmax_element(ht.begin(), ht.begin() + n);
+        s.trange2 = (*mm.second - *mm.first) * (*mm.second - *mm.first);
+    }
+    // gradient work items: (block of 32 rows) x (column range [jb, je) cut at feature boundaries,
+    // about kGradCols columns, never past the block's last row); a row block's rows split into
+    // segments of equal feature, numbered globally in row order, so the segments of feature d
+    // are seg_start[d] .. seg_start[d+1]-1.
     std::vector<int4> items;
     std::vector<int> seg_start(D + 1, 0);
     int nseg = 0;
     for (int i0 = 0; i0 < n; i0 += kGradRows) {
         const int i1 = std::min(i0 + kGradRows, n);
-        for (int f = 0; f < D && off[f] < i1; f++)
-            if (off[f + 1] > off[f]) items.push_back(make_int4(i0 / kGradRows, f, std::min(off[f + 1], i1), nseg));
+        int jb = 0;
+        for (int f = 0; f < D && off[f] < i1; f++) {
+            const int je = std::min(off[f + 1], i1);
+            if (je - jb >= kGradCols || je == i1) {
+                if (je > jb) items.push_back(make_int4(i0 / kGradRows, jb, je, nseg));
+                jb = je;
+            }
+        }
         for (int i = i0; i < i1; i++)
             if (i == i0 || hm[i] != hm[i - 1]) {
                 seg_start[hm[i] + 1]++;
