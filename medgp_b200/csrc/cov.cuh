@@ -161,6 +161,15 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
 // Only j <= i is visited; off-diagonal elements of a diagonal feature block count twice, so
 // the sums are those of the full square block.
 #define MEDGP_GC 16
+#ifndef MEDGP_GW
+#define MEDGP_GW 4   // warps (work items) per CTA
+#endif
+#ifndef MEDGP_GOCC
+#define MEDGP_GOCC 12  // resident warps per SM the register budget is set for
+#endif
+#ifndef MEDGP_GPAIR
+#define MEDGP_GPAIR 1
+#endif
 
 template <int QT>
 struct __align__(16) GradStage {
@@ -175,31 +184,40 @@ struct GradAcc {
     double sk[QT], sm[QT], sv[QT], sdiag;
 };
 
-// one column's contribution for this lane's row.  w = weight * (K^-1 - alpha alpha^T)_ij.
-template <int QT, bool CHECKED>
-__device__ __forceinline__ void grad_column(GradAcc<QT> &acc, double w, double tau, const double (&cq)[QT],
-                                            const double2 (&a)[QT], const double2 *s_b /* [q * GC] */,
-                                            const double *s_tab)
+// NC adjacent columns' contributions for this lane's row (NC = 2 doubles the independent
+// dependency chains in flight).  w = weight * (K^-1 - alpha alpha^T)_ij.
+template <int QT, int NC, bool CHECKED>
+__device__ __forceinline__ void grad_column(GradAcc<QT> &acc, const double (&w)[NC], const double (&tau)[NC],
+                                            const double (&cq)[QT], const double2 (&a)[QT],
+                                            const double2 *s_b /* [q * GC + column] */, const double *s_tab)
 {
-    const double tau2 = tau * tau;
-    const double wt = w * tau, wt2 = w * tau2;
-    double xarg[QT], ex[QT];
+    double tau2[NC], wt[NC], wt2[NC], xarg[NC * QT], ex[NC * QT];
 #pragma unroll
-    for (int q = 0; q < QT; q++) xarg[q] = -cq[q] * tau2;
-    exp_nonpos<QT, CHECKED>(xarg, ex, s_tab);
+    for (int u = 0; u < NC; u++) {
+        tau2[u] = tau[u] * tau[u];
+        wt[u] = w[u] * tau[u];
+        wt2[u] = w[u] * tau2[u];
 #pragma unroll
-    for (int q = 0; q < QT; q++) {
-        const double2 b = s_b[q * MEDGP_GC];
-        const double ec = ex[q] * (a[q].x * b.x + a[q].y * b.y);  // e cos(phi)
-        const double es = ex[q] * (a[q].y * b.x - a[q].x * b.y);  // e sin(phi)
-        acc.sk[q] = fma(w, ec, acc.sk[q]);    // sum w k
-        acc.sm[q] = fma(wt, es, acc.sm[q]);   // sum w tau e sin(phi)      (times -w_q at the end)
-        acc.sv[q] = fma(wt2, ec, acc.sv[q]);  // sum w tau^2 k             (times -2 c_q at the end)
+        for (int q = 0; q < QT; q++) xarg[u * QT + q] = -cq[q] * tau2[u];
     }
+    exp_nonpos<NC * QT, CHECKED>(xarg, ex, s_tab);
+#pragma unroll
+    for (int u = 0; u < NC; u++)
+#pragma unroll
+        for (int q = 0; q < QT; q++) {
+            const double2 b = s_b[q * MEDGP_GC + u];
+            const double ec = ex[u * QT + q] * (a[q].x * b.x + a[q].y * b.y);  // e cos(phi)
+            const double es = ex[u * QT + q] * (a[q].y * b.x - a[q].x * b.y);  // e sin(phi)
+            acc.sk[q] = fma(w[u], ec, acc.sk[q]);    // sum w k
+            acc.sm[q] = fma(wt[u], es, acc.sm[q]);   // sum w tau e sin(phi)      (times -w_q at the end)
+            acc.sv[q] = fma(wt2[u], ec, acc.sv[q]);  // sum w tau^2 k             (times -2 c_q at the end)
+        }
 }
 
-// segmented reduction over the lanes of each row segment, then the segment heads store the
-// sums of column feature f and the accumulators restart.
+// Segmented reduction over the lanes (rows) of each row segment: log-step shuffles in which a
+// lane adds its neighbour's value only while that neighbour is still inside its own segment
+// (the mask is applied as a 0/1 factor of an FMA: no selects).  The first lane of every
+// segment then stores the segment's sums for column feature f and the accumulators restart.
 template <int QT>
 __device__ __forceinline__ void grad_flush(GradAcc<QT> &acc, const EvalDesc &e, const ModelDims &md, int lane,
                                            int seg_end, bool head, int mi, int seg, int f,
@@ -207,16 +225,14 @@ __device__ __forceinline__ void grad_flush(GradAcc<QT> &acc, const EvalDesc &e, 
 {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const bool take = lane + o <= seg_end;
+        const double take = (lane + o <= seg_end) ? 1.0 : 0.0;
 #pragma unroll
         for (int q = 0; q < QT; q++) {
-            const double x0 = __shfl_down_sync(0xffffffffu, acc.sk[q], o);
-            const double x1 = __shfl_down_sync(0xffffffffu, acc.sm[q], o);
-            const double x2 = __shfl_down_sync(0xffffffffu, acc.sv[q], o);
-            if (take) { acc.sk[q] += x0; acc.sm[q] += x1; acc.sv[q] += x2; }
+            acc.sk[q] = fma(__shfl_down_sync(0xffffffffu, acc.sk[q], o), take, acc.sk[q]);
+            acc.sm[q] = fma(__shfl_down_sync(0xffffffffu, acc.sm[q], o), take, acc.sm[q]);
+            acc.sv[q] = fma(__shfl_down_sync(0xffffffffu, acc.sv[q], o), take, acc.sv[q]);
         }
-        const double x3 = __shfl_down_sync(0xffffffffu, acc.sdiag, o);
-        if (take) acc.sdiag += x3;
+        acc.sdiag = fma(__shfl_down_sync(0xffffffffu, acc.sdiag, o), take, acc.sdiag);
     }
     if (head && mi >= f) {  // (d = mi, f) with f > d is never read
         double *p = e.part + ((size_t)seg * md.D + f) * (3 * QT + 1);
@@ -307,7 +323,7 @@ __device__ __forceinline__ void grad_item(const EvalDesc &e, const ModelDims &md
         __syncwarp();
         const GradStage<QT> &st = stage[ch & 1];
         const int jc = jb + ch * MEDGP_GC, nc = min(MEDGP_GC, je - jc);
-        for (int c = 0; c < nc; c++) {
+        for (int c = 0; c < nc;) {
             const int j = jc + c, fc = st.f[c];
             if (fc != fcur) {  // uniform: the column feature changed
                 if (fcur >= 0) grad_flush<QT>(acc, e, md, lane, seg_end, head, mi, seg, fcur, cq);
@@ -315,18 +331,25 @@ __device__ __forceinline__ void grad_item(const EvalDesc &e, const ModelDims &md
                 dbl = (mi == fc) ? 2.0 : 1.0;
             }
             const double m = st.m[c][lane];
-            if (j < ifirst) {
-                // below every row of the block: no per-lane predicate.  Lanes past the end of
-                // the series carry a = 0 and read finite padding rows: they add exact zeros.
-                grad_column<QT, CHECKED>(acc, (m - ali * st.al[c]) * dbl, ti - st.t[c], cq, a, &st.b[0][c], s_tab);
-            } else if (valid && j < i) {
-                grad_column<QT, CHECKED>(acc, (m - ali * st.al[c]) * dbl, ti - st.t[c], cq, a, &st.b[0][c], s_tab);
+            if (MEDGP_GPAIR && c + 1 < nc && j + 1 < ifirst && st.f[c + 1] == fc) {
+                // two columns below every row of the block: no per-lane predicate.  Lanes past
+                // the end of the series carry a = 0 and read finite padding rows: exact zeros.
+                const double w[2] = {(m - ali * st.al[c]) * dbl, (st.m[c + 1][lane] - ali * st.al[c + 1]) * dbl};
+                const double tau[2] = {ti - st.t[c], ti - st.t[c + 1]};
+                grad_column<QT, 2, CHECKED>(acc, w, tau, cq, a, &st.b[0][c], s_tab);
+                c += 2;
+                continue;
+            }
+            if (j < ifirst || (valid && j < i)) {
+                const double w[1] = {(m - ali * st.al[c]) * dbl}, tau[1] = {ti - st.t[c]};
+                grad_column<QT, 1, CHECKED>(acc, w, tau, cq, a, &st.b[0][c], s_tab);
             } else if (valid && j == i) {  // the diagonal element: tau = 0, weight 1
                 const double wd = m - ali * ali;
                 acc.sdiag += wd;
 #pragma unroll
                 for (int q = 0; q < QT; q++) acc.sk[q] = fma(wd, a[q].x * a[q].x + a[q].y * a[q].y, acc.sk[q]);
             }
+            c++;
         }
         __syncwarp();  // everyone is done with this stage before it is refilled
     }
@@ -334,7 +357,7 @@ __device__ __forceinline__ void grad_item(const EvalDesc &e, const ModelDims &md
 }
 
 template <int QT>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(32 * MEDGP_GW, MEDGP_GOCC / MEDGP_GW)
 k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
@@ -343,7 +366,7 @@ k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
     __syncthreads();
     const EvalDesc &e = descs[blockIdx.y];
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    const int item = blockIdx.x * 4 + wp;
+    const int item = blockIdx.x * MEDGP_GW + wp;
     if (item >= e.nitems) return;
     const int4 it = e.items[item];  // (row block, first column, column end, first segment id)
     GradStage<QT> *stage = reinterpret_cast<GradStage<QT> *>(dsm) + 2 * wp;
@@ -357,7 +380,7 @@ k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
 }
 
 template <int QT>
-constexpr int grad_smem_bytes() { return 4 * 2 * (int)sizeof(GradStage<QT>); }
+constexpr int grad_smem_bytes() { return MEDGP_GW * 2 * (int)sizeof(GradStage<QT>); }
 
 // Gradient epilogue, one CTA per evaluation (deterministic: fixed summation order):
 //   noise   g_d        = sigma_d^2 sum_{i in d} W_ii                inference/c_inference_exact.cpp:191-203

@@ -250,7 +250,7 @@ struct SubChunk {
 template <int QT>
 void launch_grad_q(dim3 gg, cudaStream_t st, const EvalDesc *dd, const ModelDims &md)
 {
-    k_grad<QT><<<gg, 128, grad_smem_bytes<QT>(), st>>>(dd, md);
+    k_grad<QT><<<gg, 32 * MEDGP_GW, grad_smem_bytes<QT>(), st>>>(dd, md);
 }
 
 template <int QT>
@@ -378,7 +378,7 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
         begin(MEDGP_STAGE_GRAD);
         const int items = scp->items_max;
         out.push_back([=]() {
-            launch_grad(md.Q, dim3((items + 3) / 4, ncta), st, dd, md);
+            launch_grad(md.Q, dim3((items + MEDGP_GW - 1) / MEDGP_GW, ncta), st, dd, md);
             k_grad_finish<<<ncta, 256, fin_smem, st>>>(dd, md, d_grad, d_fail);
             L[MEDGP_STAGE_GRAD] += 2;
         });
