@@ -48,15 +48,18 @@ __device__ __forceinline__ void tri_index(int p, int &ti, int &tj)
 // 128 threads: r = tid & 63, half = tid >> 6 splits the columns by parity.
 __device__ __forceinline__ void tile_matvec_rhs(const EvalDesc &e, const double *sTile, const double *vec_base,
                                                 double *out_base, bool lower_only, bool subtract,
-                                                double *red /*2*64*/)
+                                                double *red /*3*64*/, bool have_v0 = false, double v0 = 0.0)
 {
+    // have_v0: thread tid < 64 already holds vec_base[tid] of right-hand side 0 (fetched early)
     const int tid = threadIdx.x, r = tid & 63, half = tid >> 6, ld = e.npad;
+    double *vs = red + 2 * MEDGP_NB;
     for (int q = 0; q < e.nrhs; q++) {
-        const double *v = vec_base + (size_t)q * ld;
+        if (tid < MEDGP_NB) vs[tid] = (q == 0 && have_v0) ? v0 : vec_base[(size_t)q * ld + tid];
+        __syncthreads();
         double s = 0.0;
         const int cmax = lower_only ? r : MEDGP_NB - 1;
 #pragma unroll 4
-        for (int c = half; c <= cmax; c += 2) s += sTile[c * MEDGP_SLD + r] * v[c];
+        for (int c = half; c <= cmax; c += 2) s += sTile[c * MEDGP_SLD + r] * vs[c];
         red[half * MEDGP_NB + r] = s;
         __syncthreads();
         if (half == 0) {
@@ -104,114 +107,212 @@ __device__ __forceinline__ void acc_matvec_rhs(const double (&acc)[4][4][2], con
 }
 
 // ------------------------------------------------------------------ potrf: diagonal block k
-// Fused Cholesky + triangular inverse of one 64x64 block by Gauss-Jordan-style elimination on
-// the augmented matrix [D | I], entirely in registers.  128 threads: thread (r, g) (r = tid&63,
-// g = tid>>6, warp-uniform) owns row r and the 32 columns of parity g.
-// Step j (pivot d = D_jj after earlier updates, a_r = D_rj):
-//      L_rj = a_r / sqrt(d)                       (saved to sL by the owner of column j)
-//      W_rc -= (a_r / d) * row_j[c]    for every r > j, c != j   (c > r: dead slots, harmless)
-//      W_rj  = -a_r / d
-// where row_j[c] = D_cj for c > j (symmetry) and the running Y_jc for c < j, Y = rows of
-// L^-1 before the final scaling X_rc = Y_rc / L_rr.  One block barrier per step; row_j travels
-// through a double-buffered 64-entry shared vector laid out by column parity (16-byte
-// broadcast reads).  To keep the code inside the instruction cache only 8 steps are unrolled:
-// after each panel of 8 columns the register file is rotated by 4 slots, so the pivot columns
-// always sit in W[0..3] and every register index stays static:
-//      during panel p, W[pos] holds column c = 2*((pos + 4p) mod 32) + g.
+// Cholesky factor L and triangular inverse X = L^-1 of one 64x64 block held in shared memory,
+// 128 threads, blocked by 16 columns so that the only serial chain is the 64 pivots:
+//   for J = 0..3 (column block c0 = 16 J):
+//     (a) warp 0 factors the 16x16 diagonal block in registers (lane = row), exchanging the
+//         pivot column by shuffles; the reciprocal square root of the NEXT pivot is started
+//         before the rest of the rank-1 update is issued, so per pivot the chain is
+//         shuffle -> multiply -> fma -> rsqrt.
+//     (b) warps 0-1 (lane = row) solve the rows below against the block, L_IJ = S_IJ L_JJ^-T,
+//         by right-looking substitution in registers, while warp 2 inverts the diagonal block
+//         (lane = column).
+//     (c) all warps apply the rank-16 update to the trailing lower part with DMMA.
+//   then the off-diagonal blocks X_IJ = -X_II sum_K L_IK X_KJ, level by level, with DMMA.
+// LAPACK semantics: a non-positive (or NaN) pivot raises *s_fail (potrf info > 0).
 #define MEDGP_DIAG_THREADS 128
 
-// shared scratch: d[2][2*32] (column j of D by parity), y[2][2][64] (row j of Y in the rotated
-// slot coordinates of its owner, per parity), rs[2] = 1/sqrt(pivot)
+// scratch of the diagonal-block routines: d[0] holds 1/L_cc during the factorisation and is the
+// reduction buffer of the forward-solve matvec afterwards
 struct GjBufs {
-    double d[2][MEDGP_NB];
-    double y[2][2][MEDGP_NB];
-    double rs[2];
+    double d[3][MEDGP_NB];
 };
 
-__device__ __forceinline__ void potf2_inv_gj(double (&W)[32], int r, int g, GjBufs *gb,
-                                             double *sL /*pitch SLD*/, int *s_fail)
+// 1/sqrt(d): hardware approximation (about 22 bits) refined by one third-order step,
+// y1 = y0 (1 + e/2 + 3 e^2/8), e = 1 - d y0^2: error O(e^3), below the rounding of the result.
+__device__ __forceinline__ double rsqrt_fast(double d)
 {
-    const int rslot = (r & 1) * 32 + (r >> 1);
-    // 1/sqrt of the NEXT pivot is computed during the previous update sweep (by every thread on
-    // its own slot, branch-free, so the compiler interleaves it with the sweep's FMAs; only the
-    // owner's value is published).  The first one here.
-    double rs_next = rsqrt(W[0]);
-    if (r == 0 && g == 0 && !(W[0] > 0.0)) *s_fail = 1;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double t = d * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    return fma(y * e, p, y);
+}
+
+// (a) 16x16 diagonal block at (c0, c0): in-place Cholesky (lower part), 1/L_cc -> s_rs[c0 + c].
+// One warp; lanes 16..31 mirror lanes 0..15 and store nothing.
+__device__ __forceinline__ void chol16_warp(double *sA, double *s_rs, int c0, int lane, int *s_fail)
+{
+    const int r = lane & 15;
+    double a[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) a[c] = (c <= r) ? sA[(c0 + c) * MEDGP_SLD + c0 + r] : 0.0;
+    double rs = rsqrt_fast(a[0]), rs_mine = rs;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        if (r == j) {
+            if (!(a[j] > 0.0)) *s_fail = 1;
+            rs_mine = rs;
+        }
+        const double rsj = __shfl_sync(0xffffffffu, rs, j);
+        const double l = a[j] * rsj;  // L_rj for r >= j (r == j: sqrt of the pivot)
+        a[j] = l;
+        if (j < 15) {
+            rs = rsqrt_fast(fma(-l, l, a[j + 1]));  // next pivot: meaningful in lane j + 1
+#pragma unroll
+            for (int c = j + 1; c < 16; c++) a[c] = fma(-l, __shfl_sync(0xffffffffu, l, c), a[c]);
+        }
+    }
+    if (lane < 16) {
+#pragma unroll
+        for (int c = 0; c < 16; c++)
+            if (c <= r) sA[(c0 + c) * MEDGP_SLD + c0 + r] = a[c];
+        s_rs[c0 + r] = rs_mine;
+    }
+}
+
+// (b) one row below the diagonal block: l_rj = (s_rj - sum_{c<j} l_rc L_jc) / L_jj, right-looking
+__device__ __forceinline__ void panel16_row(double *sA, const double *s_rs, int c0, int row)
+{
+    double a[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) a[c] = sA[(c0 + c) * MEDGP_SLD + row];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const double l = a[j] * s_rs[c0 + j];
+        a[j] = l;
+#pragma unroll
+        for (int c = j + 1; c < 16; c++) a[c] = fma(-l, sA[(c0 + j) * MEDGP_SLD + c0 + c], a[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 16; c++) sA[(c0 + c) * MEDGP_SLD + row] = a[c];
+}
+
+// (b') inverse of the 16x16 diagonal block of L into sX (full block, zeros above the diagonal).
+// One warp, lane = column c: x_cc = 1/L_cc, x_kc = -(sum_{m<k} L_km x_mc) / L_kk.
+__device__ __forceinline__ void trinv16_warp(const double *sA, double *sX, const double *s_rs, int c0, int lane)
+{
+    const int c = lane & 15;
+    double acc[16], x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const double rk = s_rs[c0 + k];
+        const double xk = (k == c) ? rk : ((k > c) ? -rk * acc[k] : 0.0);
+        x[k] = xk;
+#pragma unroll
+        for (int r = k + 1; r < 16; r++) acc[r] = fma(sA[(c0 + k) * MEDGP_SLD + c0 + r], xk, acc[r]);
+    }
+    if (lane < 16) {
+#pragma unroll
+        for (int r = 0; r < 16; r++) sX[(c0 + c) * MEDGP_SLD + c0 + r] = x[r];
+    }
+}
+
+// (c) trailing update S -= P P^T, P = the 16 columns at c0, rows/columns >= c0 + 16, lower
+// 8x8 tiles dealt round-robin to the 4 warps
+__device__ __forceinline__ void trail16_update(double *sA, int c0, int warp, int lane)
+{
+    const int c1 = c0 + 16, m = (MEDGP_NB - c1) / 8;
+    const int lr = lane >> 2, lk = lane & 3;
+    int cnt = 0;
+    for (int ti = 0; ti < m; ti++)
+        for (int tj = 0; tj <= ti; tj++, cnt++) {
+            if ((cnt & 3) != warp) continue;
+            const int row0 = c1 + 8 * ti, col0 = c1 + 8 * tj;
+            double *pc = sA + (col0 + 2 * lk) * MEDGP_SLD + row0 + lr;
+            double v0 = pc[0], v1 = pc[MEDGP_SLD];
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                const double *pk = sA + (c0 + 4 * kk + lk) * MEDGP_SLD;
+                dmma884(v0, v1, -pk[row0 + lr], pk[col0 + lr]);
+            }
+            pc[0] = v0;
+            pc[MEDGP_SLD] = v1;
+        }
+}
+
+// sA: the SPD block (lower part; element (r, c) at c*SLD + r) -> L in place.  sX -> X = L^-1
+// (full tile, zeros above the diagonal).  Call with all 128 threads after a barrier that makes
+// sA visible; returns after a barrier.
+__device__ __forceinline__ void potf2_inv_blocked(double *sA, double *sX, double *s_rs, int *s_fail)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lr = lane >> 2, lk = lane & 3;
+    for (int i = tid; i < kTileElems; i += MEDGP_DIAG_THREADS) sX[i] = 0.0;
 #pragma unroll 1
-    for (int p = 0; p < 8; p++) {
-        const int base = 4 * p;  // W[pos] holds column 2*((pos + base) mod 32) + g
-#pragma unroll
-        for (int jj = 0; jj < 8; jj++) {
-            const int j = 8 * p + jj;
-            const int gj = jj & 1, pj = jj >> 1;  // static: parity and register slot of column j
-            const int pn = (jj + 1) >> 1;         // ... and slot of column j + 1 (4 when jj == 7)
-            double *db = gb->d[jj & 1];
-            double *yb = gb->y[jj & 1][g];
-            if (g == gj && r >= j) db[rslot] = W[pj];  // column j of D: D_rj, r >= j
-            if (r == j) {                              // row j of Y (all 32 slots, rotated coords)
-                if (g == gj) {
-                    gb->rs[jj & 1] = rs_next;
-                    if (!(W[pj] > 0.0)) *s_fail = 1;   // LAPACK potrf: info > 0 (also NaN)
-                }
-#pragma unroll
-                for (int pos = 0; pos < 32; pos += 2)
-                    *reinterpret_cast<double2 *>(yb + base + pos) = make_double2(W[pos], W[pos + 1]);
+    for (int J = 0; J < 4; J++) {
+        const int c0 = 16 * J;
+        if (warp == 0) chol16_warp(sA, s_rs, c0, lane, s_fail);
+        __syncthreads();
+        if (J < 3) {
+            if (warp < 2) {
+                if (tid >= c0 + 16) panel16_row(sA, s_rs, c0, tid);
+            } else if (warp == 2) {
+                trinv16_warp(sA, sX, s_rs, c0, lane);
             }
             __syncthreads();
-            if (r >= j) {
-                const double rs = gb->rs[jj & 1];
-                const double ar = db[rslot];
-                const double l = ar * rs;  // L_rj = a_r / sqrt(d)   (r == j: sqrt(d))
-                if (g == gj) sL[j * MEDGP_SLD + r] = l;
-                if (r > j) {
-                    const double nard = -ar * (rs * rs);  // -a_r / d
-                    const double *dsrc = db + g * 32 + base;  // future columns: D_cj
-                    const double *ysrc = yb + base;           // past columns:   Y_jc
-                    // slots 0..3: the current panel (columns 8p + 2 pos + g), per-slot choice
-                    {
-                        const double2 d0 = *reinterpret_cast<const double2 *>(dsrc);
-                        const double2 d1 = *reinterpret_cast<const double2 *>(dsrc + 2);
-                        const double2 y0 = *reinterpret_cast<const double2 *>(ysrc);
-                        const double2 y1 = *reinterpret_cast<const double2 *>(ysrc + 2);
-                        const double dv[4] = {d0.x, d0.y, d1.x, d1.y};
-                        const double yv[4] = {y0.x, y0.y, y1.x, y1.y};
-#pragma unroll
-                        for (int pos = 0; pos < 4; pos++) {
-                            const double v = (2 * pos + g < jj) ? yv[pos] : dv[pos];
-                            W[pos] = fma(nard, v, W[pos]);
-                        }
-                        if (g == gj) W[pj] = nard;
-                    }
-                    // slot group 1 next: for jj == 7 it holds the next pivot
-                    {
-                        const double *sp = (1 >= 8 - p) ? ysrc : dsrc;
-                        const double2 v0 = *reinterpret_cast<const double2 *>(sp + 4);
-                        const double2 v1 = *reinterpret_cast<const double2 *>(sp + 6);
-                        W[4] = fma(nard, v0.x, W[4]);
-                        W[5] = fma(nard, v0.y, W[5]);
-                        W[6] = fma(nard, v1.x, W[6]);
-                        W[7] = fma(nard, v1.y, W[7]);
-                    }
-                    rs_next = rsqrt(W[pn]);  // meaningful in the thread that owns pivot j + 1
-#pragma unroll
-                    for (int q = 2; q < 8; q++) {
-                        const double *sp = (q >= 8 - p) ? ysrc : dsrc;
-                        const double2 v0 = *reinterpret_cast<const double2 *>(sp + 4 * q);
-                        const double2 v1 = *reinterpret_cast<const double2 *>(sp + 4 * q + 2);
-                        W[4 * q] = fma(nard, v0.x, W[4 * q]);
-                        W[4 * q + 1] = fma(nard, v0.y, W[4 * q + 1]);
-                        W[4 * q + 2] = fma(nard, v1.x, W[4 * q + 2]);
-                        W[4 * q + 3] = fma(nard, v1.y, W[4 * q + 3]);
-                    }
-                }
-            }
+            trail16_update(sA, c0, warp, lane);
+            __syncthreads();
+        } else if (warp == 2) {
+            trinv16_warp(sA, sX, s_rs, c0, lane);
         }
-        // rotate the register file by 4 slots
-        const double t0 = W[0], t1 = W[1], t2 = W[2], t3 = W[3];
-#pragma unroll
-        for (int pos = 0; pos < 28; pos++) W[pos] = W[pos + 4];
-        W[28] = t0; W[29] = t1; W[30] = t2; W[31] = t3;
     }
+    // off-diagonal blocks of X, level d = I - J
+#pragma unroll 1
+    for (int d = 1; d < 4; d++) {
+        __syncthreads();
+        if (warp < 4 - d) {
+            const int J = warp, I = J + d;
+            double t[2][2][2];
+#pragma unroll
+            for (int u = 0; u < 8; u++) (&t[0][0][0])[u] = 0.0;
+            for (int K = J; K < I; K++)  // T = sum_K L_IK X_KJ
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    const double *pa = sA + (16 * K + 4 * kk + lk) * MEDGP_SLD + 16 * I + lr;
+                    const double *pb = sX + (16 * J + lr) * MEDGP_SLD + 16 * K + 4 * kk + lk;
+                    const double a0 = pa[0], a1 = pa[8], b0 = pb[0], b1 = pb[8 * MEDGP_SLD];
+                    dmma884(t[0][0][0], t[0][0][1], a0, b0);
+                    dmma884(t[0][1][0], t[0][1][1], a0, b1);
+                    dmma884(t[1][0][0], t[1][0][1], a1, b0);
+                    dmma884(t[1][1][0], t[1][1][1], a1, b1);
+                }
+            double *px = sX + (16 * J + 2 * lk) * MEDGP_SLD + 16 * I + lr;  // block (I, J), this lane's C slots
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) {
+                    px[8 * nt * MEDGP_SLD + 8 * mt] = t[mt][nt][0];
+                    px[(8 * nt + 1) * MEDGP_SLD + 8 * mt] = t[mt][nt][1];
+                }
+            __syncwarp();
+            double x[2][2][2];
+#pragma unroll
+            for (int u = 0; u < 8; u++) (&x[0][0][0])[u] = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {  // X_IJ = -X_II T
+                const double *pa = sX + (16 * I + 4 * kk + lk) * MEDGP_SLD + 16 * I + lr;
+                const double *pb = sX + (16 * J + lr) * MEDGP_SLD + 16 * I + 4 * kk + lk;
+                const double a0 = -pa[0], a1 = -pa[8], b0 = pb[0], b1 = pb[8 * MEDGP_SLD];
+                dmma884(x[0][0][0], x[0][0][1], a0, b0);
+                dmma884(x[0][1][0], x[0][1][1], a0, b1);
+                dmma884(x[1][0][0], x[1][0][1], a1, b0);
+                dmma884(x[1][1][0], x[1][1][1], a1, b1);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) {
+                    px[8 * nt * MEDGP_SLD + 8 * mt] = x[mt][nt][0];
+                    px[(8 * nt + 1) * MEDGP_SLD + 8 * mt] = x[mt][nt][1];
+                }
+        }
+    }
+    __syncthreads();
 }
 
 // Factor one diagonal block: D = K_kk - C with the accumulated product C in sD (pitch SLD);
@@ -223,27 +324,32 @@ __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, doub
                                                   bool have_product = true)
 {
     const int T = e.T, tid = threadIdx.x;
-    const int r = tid & 63, g = tid >> 6;
     const double *Kkk = tile_ptr(e.M, T, k, k);
-    double W[32];
+    // all global loads of this block are issued up front: one memory round trip
+    double2 kv[16];
 #pragma unroll
-    for (int s = 0; s < 32; s++) {
-        const int c = 2 * s + g;
-        W[s] = (c <= r) ? Kkk[c * MEDGP_SLD + r] - (have_product ? sD[c * MEDGP_SLD + r] : 0.0) : 0.0;
+    for (int u = 0; u < 16; u++) {
+        const int idx = tid + MEDGP_DIAG_THREADS * u, c = idx >> 5, rp = idx & 31;
+        kv[u] = *reinterpret_cast<const double2 *>(Kkk + c * MEDGP_SLD + 2 * rp);
     }
-    __syncthreads();  // sD is dead from here on: it becomes the staging tile for X
-    potf2_inv_gj(W, r, g, gjb, sL, s_fail);
-    __syncthreads();
-    const double lrr_inv = 1.0 / sL[r * MEDGP_SLD + r];
+    const double v0 = (tid < MEDGP_NB) ? e.rhs[k * MEDGP_NB + tid] : 0.0;
 #pragma unroll
-    for (int s = 0; s < 32; s++) {
-        const int c = 2 * s + g;
-        const double x = (c < r) ? W[s] * lrr_inv : (c == r ? lrr_inv : 0.0);
-        sD[c * MEDGP_SLD + r] = x;  // X(r, c)
+    for (int u = 0; u < 16; u++) {
+        const int idx = tid + MEDGP_DIAG_THREADS * u, c = idx >> 5, rp = idx & 31, o = c * MEDGP_SLD + 2 * rp;
+        double2 v = kv[u];
+        if (have_product) {
+            const double2 pr = *reinterpret_cast<const double2 *>(sD + o);
+            v.x -= pr.x;
+            v.y -= pr.y;
+        }
+        if (2 * rp < c) v.x = 0.0;
+        if (2 * rp + 1 < c) v.y = 0.0;
+        *reinterpret_cast<double2 *>(sL + o) = v;
     }
-    __syncthreads();
+    __syncthreads();  // sD is dead from here on: it receives X
+    potf2_inv_blocked(sL, sD, gjb->d[0], s_fail);
     // forward solve, block k: z_k = X_kk rhs_k (in place)
-    tile_matvec_rhs(e, sD, e.rhs + k * MEDGP_NB, e.rhs + k * MEDGP_NB, true, false, gjb->d[0]);
+    tile_matvec_rhs(e, sD, e.rhs + k * MEDGP_NB, e.rhs + k * MEDGP_NB, true, false, gjb->d[0], true, v0);
     // write back: L_kk (lower), dinv (X column-major), dinvT (X^T column-major)
     double *Lkk = tile_ptr(e.M, T, k, k);
     double *Xk = e.dinv + (size_t)k * kTileElems;
@@ -279,6 +385,7 @@ k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int depth, int *__restri
     const EvalDesc &e = descs[blockIdx.x];
     if (k >= e.T) return;
     const int T = e.T, tid = threadIdx.x;
+    if (depth > 0) prefetch_tile_l2(tile_ptr(e.M, T, k, k));  // wanted right after the products
     gemm_bars_init(&bars);
     if (tid == 0) s_fail = 0;
     double *M = e.M;
