@@ -301,7 +301,7 @@ def run_ours(args):
         hbm = peaks.get("hbm_gbs", 6650.0)
         hbm_src = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         fp64_peak = measure_fp64_peak(torch, dev)
-        kernel_of = {"potrf": "k_potrf_panel + k_potrf_diag", "diag": "k_potrf_diag", "trtri": "k_trtri_row (+k_alpha)", "lauum": "k_lauum",
+        kernel_of = {"potrf": "k_potrf_panel + k_potrf_diag", "diag": "k_potrf_diag", "trtri": "k_trtri_row", "lauum": "k_lauum",
                      "grad": "k_grad (+k_grad_finish)", "assemble": "k_assemble", "prep": "k_prep",
                      "solve": "k_solve", "predict": "k_cross/k_pred_finish"}
         traffic = {}

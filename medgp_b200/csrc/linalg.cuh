@@ -141,7 +141,9 @@ __device__ __forceinline__ double rsqrt_fast(double d)
 }
 
 // (a) 16x16 diagonal block at (c0, c0): in-place Cholesky (lower part), 1/L_cc -> s_rs[c0 + c].
-// One warp; lanes 16..31 mirror lanes 0..15 and store nothing.
+// One warp, lane = row (lanes 16..31 mirror lanes 0..15 and store nothing).  The pivot's
+// reciprocal square root travels by shuffle (it is on the serial chain); the pivot column is
+// stored to the tile itself -- its final place -- and read back as broadcasts.
 __device__ __forceinline__ void chol16_warp(double *sA, double *s_rs, int c0, int lane, int *s_fail)
 {
     const int r = lane & 15;
@@ -149,27 +151,38 @@ __device__ __forceinline__ void chol16_warp(double *sA, double *s_rs, int c0, in
 #pragma unroll
     for (int c = 0; c < 16; c++) a[c] = (c <= r) ? sA[(c0 + c) * MEDGP_SLD + c0 + r] : 0.0;
     double rs = rsqrt_fast(a[0]), rs_mine = rs;
+    bool bad = false;
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-        if (r == j) {
-            if (!(a[j] > 0.0)) *s_fail = 1;
-            rs_mine = rs;
-        }
+        bad = bad || (r == j && !(a[j] > 0.0));
+        rs_mine = (r == j) ? rs : rs_mine;
         const double rsj = __shfl_sync(0xffffffffu, rs, j);
         const double l = a[j] * rsj;  // L_rj for r >= j (r == j: sqrt of the pivot)
-        a[j] = l;
+        double *col = sA + (c0 + j) * MEDGP_SLD + c0;
+        if (lane < 16 && r >= j) col[r] = l;
         if (j < 15) {
             rs = rsqrt_fast(fma(-l, l, a[j + 1]));  // next pivot: meaningful in lane j + 1
+            __syncwarp();
+            if (j & 1) {  // rows j+1 .. 15 of column j; 16-byte aligned pairs start at an even row
 #pragma unroll
-            for (int c = j + 1; c < 16; c++) a[c] = fma(-l, __shfl_sync(0xffffffffu, l, c), a[c]);
+                for (int c = j + 1; c < 16; c += 2) {
+                    const double2 lc = *reinterpret_cast<const double2 *>(col + c);
+                    a[c] = fma(-l, lc.x, a[c]);
+                    a[c + 1] = fma(-l, lc.y, a[c + 1]);
+                }
+            } else {
+                a[j + 1] = fma(-l, col[j + 1], a[j + 1]);
+#pragma unroll
+                for (int c = j + 2; c < 16; c += 2) {
+                    const double2 lc = *reinterpret_cast<const double2 *>(col + c);
+                    a[c] = fma(-l, lc.x, a[c]);
+                    a[c + 1] = fma(-l, lc.y, a[c + 1]);
+                }
+            }
         }
     }
-    if (lane < 16) {
-#pragma unroll
-        for (int c = 0; c < 16; c++)
-            if (c <= r) sA[(c0 + c) * MEDGP_SLD + c0 + r] = a[c];
-        s_rs[c0 + r] = rs_mine;
-    }
+    if (bad) *s_fail = 1;
+    if (lane < 16) s_rs[c0 + r] = rs_mine;
 }
 
 // (b) one row below the diagonal block: l_rj = (s_rj - sum_{c<j} l_rc L_jc) / L_jj, right-looking
@@ -642,12 +655,15 @@ k_trtri_update(const EvalDesc *__restrict__ descs, int k)
 }
 
 // ------------------------------------------------------------------ lauum: K^-1 lower tiles
-// grid (lower tiles, evaluations): (K^-1)_ij = sum_{l>=i} U_il U_jl^T  -> written over L_ij
+// grid (lower tiles, evaluations): (K^-1)_ij = sum_{l>=i} U_il U_jl^T  -> written over L_ij.
+// The CTAs of the diagonal tiles stream the whole block row i of U anyway, so they also form
+// alpha_i = (L^-T z)_i = sum_l U_il z_l from the resident panels (no separate pass over U).
 __global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
 k_lauum(const EvalDesc *__restrict__ descs)
 {
     extern __shared__ __align__(128) double smem[];
     __shared__ GemmBars bars;
+    __shared__ double s_al[2 * MEDGP_NB];
     const EvalDesc &e = descs[blockIdx.y];
     int i, j;
     tri_index(blockIdx.x, i, j);
@@ -658,14 +674,30 @@ k_lauum(const EvalDesc *__restrict__ descs)
     acc_zero(acc);
     double *M = e.M;
     const double *XTi = e.dinvT + (size_t)i * kTileElems;
+    const bool diag = (i == j);
+    const int m = threadIdx.x & 63, kh = (threadIdx.x >> 6) * (MEDGP_KC / 2);
+    const double *z = e.rhs + i * MEDGP_NB + kh;
+    double asum = 0.0;
     gemm_nt_tiles(acc, T - i,
                   [&](int l0, const double *&A, const double *&B) {
                       const int l = i + l0;
                       A = (l0 == 0) ? XTi : tile_ptr(M, T, i, l);
                       B = (l == j) ? XTi : tile_ptr(M, T, j, l);  // l == j only when i == j == l
                   },
-                  smem, &bars);
+                  smem, &bars,
+                  [&](int ch, const double *stage) {
+                      if (!diag) return;
+                      const double *zc = z + ch * MEDGP_KC;  // columns (i*64 + 16 ch + kh ..) of block row i
+                      const double *pa = stage + kh * MEDGP_SLD + m;
+#pragma unroll
+                      for (int k = 0; k < MEDGP_KC / 2; k++) asum = fma(pa[k * MEDGP_SLD], __ldg(zc + k), asum);
+                  });
     acc_to_global(acc, tile_ptr(M, T, i, j));
+    if (diag) {
+        s_al[threadIdx.x] = asum;
+        __syncthreads();
+        if (threadIdx.x < MEDGP_NB) e.alpha[i * MEDGP_NB + threadIdx.x] = s_al[threadIdx.x] + s_al[MEDGP_NB + threadIdx.x];
+    }
 }
 
 // ------------------------------------------------------------------ NLML
@@ -690,27 +722,3 @@ k_solve(const EvalDesc *__restrict__ descs, ModelDims md, double *__restrict__ o
     }
 }
 
-// ------------------------------------------------------------------ alpha = L^-T z = U z
-// grid (row blocks, evaluations), 256 threads = 64 rows x 4 column slices
-__global__ void __launch_bounds__(256)
-k_alpha(const EvalDesc *__restrict__ descs)
-{
-    __shared__ double sp[4 * MEDGP_NB];
-    const EvalDesc &e = descs[blockIdx.y];
-    const int j = blockIdx.x;
-    if (j >= e.T) return;
-    const int ld = e.npad, tid = threadIdx.x, r = tid & 63, sl = tid >> 6;
-    const double *z = e.rhs;
-    double s = 0.0;
-    // diagonal block: U_jj = X_jj^T
-    const double *XT = e.dinvT + (size_t)j * kTileElems;
-    for (int c = sl * 16; c < sl * 16 + 16; c++)
-        if (c >= r) s += XT[c * MEDGP_SLD + r] * z[j * MEDGP_NB + c];
-    // strictly upper tiles (j, l), l > j : columns split over the 4 slices
-    for (int c = (j + 1) * MEDGP_NB + sl; c < ld; c += 4)
-        s += e.M[tile_off(e.T, j, c >> 6) + (c & 63) * MEDGP_SLD + r] * z[c];
-    sp[sl * MEDGP_NB + r] = s;
-    __syncthreads();
-    if (tid < MEDGP_NB)
-        e.alpha[j * MEDGP_NB + tid] = sp[tid] + sp[MEDGP_NB + tid] + sp[2 * MEDGP_NB + tid] + sp[3 * MEDGP_NB + tid];
-}

@@ -370,7 +370,6 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
             }
             out.push_back([=]() { k_trtri_row<<<dim3(i, ai), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, i, rl ? 1 : 0); L[MEDGP_STAGE_TRTRI]++; });
         }
-        out.push_back([=]() { k_alpha<<<dim3(Tmax, ncta), 256, 0, st>>>(dd); L[MEDGP_STAGE_TRTRI]++; });
         end(MEDGP_STAGE_TRTRI);
         begin(MEDGP_STAGE_LAUUM);
         out.push_back([=]() { k_lauum<<<dim3(ntri, ncta), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd); L[MEDGP_STAGE_LAUUM]++; });
