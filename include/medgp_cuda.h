@@ -127,6 +127,11 @@ int medgp_cuda_malloc(medgp_ctx *ctx, size_t bytes, void **d_ptr);
 int medgp_cuda_free(medgp_ctx *ctx, void *d_ptr);
 int medgp_cuda_memcpy_h2d(medgp_ctx *ctx, void *d_dst, const void *src, size_t bytes);
 int medgp_cuda_memcpy_d2h(medgp_ctx *ctx, void *dst, const void *d_src, size_t bytes);
+/* Page-locked host memory.  medgp_cuda_nlml_grad copies straight from/to caller buffers that
+ * are page-locked (allocated here, by cudaHostAlloc or registered with cudaHostRegister) and
+ * stages pageable ones through its own pinned buffers. */
+int medgp_cuda_host_alloc(medgp_ctx *ctx, size_t bytes, void **h_ptr);
+int medgp_cuda_host_free(medgp_ctx *ctx, void *h_ptr);
 /* The context's stream as a cudaStream_t (for event timing by the caller). */
 void *medgp_cuda_stream(medgp_ctx *ctx);
 

@@ -25,7 +25,7 @@ SYMBOLS = [
     "medgp_cuda_clear_series", "medgp_cuda_nlml_grad", "medgp_cuda_nlml_grad_device",
     "medgp_cuda_sync", "medgp_cuda_predict", "medgp_cuda_debug_matrices", "medgp_cuda_profile",
     "medgp_cuda_stage_times", "medgp_cuda_malloc", "medgp_cuda_free", "medgp_cuda_memcpy_h2d",
-    "medgp_cuda_memcpy_d2h", "medgp_cuda_stream",
+    "medgp_cuda_memcpy_d2h", "medgp_cuda_host_alloc", "medgp_cuda_host_free", "medgp_cuda_stream",
 ]
 
 
@@ -78,6 +78,8 @@ def load_library():
     lib.medgp_cuda_free.argtypes = [vp, vp]
     lib.medgp_cuda_memcpy_h2d.argtypes = [vp, vp, vp, ctypes.c_size_t]
     lib.medgp_cuda_memcpy_d2h.argtypes = [vp, vp, vp, ctypes.c_size_t]
+    lib.medgp_cuda_host_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp)]
+    lib.medgp_cuda_host_free.argtypes = [vp, vp]
     lib.medgp_cuda_stream.argtypes = [vp]
     lib.medgp_cuda_stream.restype = vp
     _lib = lib
@@ -108,6 +110,7 @@ class Context:
             raise MedgpError(f"medgp_cuda_create failed with status {rc} "
                              "(no sm_100 GPU? there is no CPU fallback)")
         self.Q, self.D, self.R = Q, D, R
+        self._pinned = []
         self._check(self.lib.medgp_cuda_model(self.h, Q, D, R, float(pi)))
         self.P = self.lib.medgp_cuda_num_hyp(self.h)
 
@@ -118,6 +121,9 @@ class Context:
 
     def close(self):
         if self.h:
+            for p in self._pinned:  # arrays from pinned() must not be used after close()
+                self.lib.medgp_cuda_host_free(self.h, p)
+            self._pinned = []
             self.lib.medgp_cuda_destroy(self.h)
             self.h = None
 
@@ -144,13 +150,27 @@ class Context:
         self._check(self.lib.medgp_cuda_clear_series(self.h))
 
     # ------------------------------------------------------------------ hot path, host buffers
-    def nlml_grad(self, series_ids, theta, want_grad=True):
-        """theta: (batch, P).  Returns (nlml[batch], grad[batch,P] or None, status[batch])."""
+    def pinned(self, shape, dtype=np.float64):
+        """A numpy array backed by page-locked host memory (freed with the context)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape))
+        p = ctypes.c_void_p()
+        self._check(self.lib.medgp_cuda_host_alloc(self.h, n * dtype.itemsize, ctypes.byref(p)))
+        self._pinned.append(p)
+        buf = (ctypes.c_char * (n * dtype.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def nlml_grad(self, series_ids, theta, want_grad=True, out=None):
+        """theta: (batch, P).  Returns (nlml[batch], grad[batch,P] or None, status[batch]).
+        out = (nlml, grad, status) reuses caller arrays (page-locked ones are written by DMA)."""
         sids = np.ascontiguousarray(series_ids, dtype=np.int32)
         theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(len(sids), self.P)
-        nlml = np.empty(len(sids))
-        grad = np.empty((len(sids), self.P)) if want_grad else None
-        status = np.empty(len(sids), dtype=np.int32)
+        if out is not None:
+            nlml, grad, status = out
+        else:
+            nlml = np.empty(len(sids))
+            grad = np.empty((len(sids), self.P)) if want_grad else None
+            status = np.empty(len(sids), dtype=np.int32)
         self._check(self.lib.medgp_cuda_nlml_grad(
             self.h, len(sids), _ip(sids), _dp(theta), int(want_grad), _dp(nlml),
             _dp(grad) if want_grad else None, _ip(status)))

@@ -82,6 +82,7 @@ struct medgp_ctx {
     bool use_graphs = true;  // MEDGP_GRAPHS=0 disables CUDA-graph replay of chunk launch sequences
     std::map<uint64_t, GraphEntry> graphs;
     bool fuse_diag = true;   // MEDGP_FUSE_DIAG=0: separate diagonal kernels in the left-looking path
+    int fold_max = 128;     // MEDGP_FOLD_MAX: chunks with fewer matrices fold panel tiles into the diagonal blocks
     int force_rl = -1;  // MEDGP_RL=0/1 forces the left-/right-looking factorisation (experiments)
     cudaStream_t sub_streams[8] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
@@ -437,7 +438,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         if (ctx->force_rl >= 0) rl = ctx->force_rl != 0;
         // left-looking with few matrices: the diagonal kernel (one CTA per matrix) must not carry
         // a k-tile product; the panel CTAs fold their tile into the diagonal block instead
-        const bool fold = !rl && cnt < 128;
+        const bool fold = !rl && cnt < ctx->fold_max;
         std::vector<SubChunk> subs(S);
         // ---- carve the arena and fill descriptors, sub-chunk major
         char *p = ctx->arena;
@@ -614,6 +615,7 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     ctx->arena_bytes = workspace_bytes;
     ctx->max_streams = 8;
     if (const char *ev = getenv("MEDGP_RL")) ctx->force_rl = atoi(ev);
+    if (const char *ev = getenv("MEDGP_FOLD_MAX")) ctx->fold_max = atoi(ev);
     if (const char *ev = getenv("MEDGP_FUSE_DIAG")) ctx->fuse_diag = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_GRAPHS")) ctx->use_graphs = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_STREAMS")) ctx->max_streams = std::max(1, std::min(8, atoi(ev)));
@@ -845,6 +847,32 @@ MEDGP_API int medgp_cuda_nlml_grad_device(medgp_ctx *ctx, int batch, const int *
                      nullptr, nullptr, 0);
 }
 
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+MEDGP_API int medgp_cuda_host_alloc(medgp_ctx *ctx, size_t bytes, void **h_ptr)
+{
+    if (!ctx || !h_ptr) return MEDGP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CU(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_host_free(medgp_ctx *ctx, void *h_ptr)
+{
+    if (!ctx) return MEDGP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    CU(cudaFreeHost(h_ptr));
+    return MEDGP_OK;
+}
+
 MEDGP_API int medgp_cuda_nlml_grad(medgp_ctx *ctx, int batch, const int *series_id,
                                    const double *theta, int want_grad, double *nlml, double *grad,
                                    int *status)
@@ -863,9 +891,23 @@ MEDGP_API int medgp_cuda_nlml_grad(medgp_ctx *ctx, int batch, const int *series_
     if (rc) return rc;
     const size_t P = ctx->md.P;
     cudaStream_t st = ctx->stream;
-    memcpy(ctx->h_theta, theta, (size_t)batch * P * 8);
-    CU(cudaMemcpyAsync(ctx->d_theta, ctx->h_theta, (size_t)batch * P * 8, cudaMemcpyHostToDevice, st));
+    // page-locked caller buffers are copied to/from directly; pageable ones go through the
+    // context's pinned staging buffers
+    const bool pin_in = is_pinned_host(theta);
+    const bool pin_out = is_pinned_host(nlml) && is_pinned_host(status) && (!want_grad || is_pinned_host(grad));
+    if (!pin_in) memcpy(ctx->h_theta, theta, (size_t)batch * P * 8);
+    CU(cudaMemcpyAsync(ctx->d_theta, pin_in ? theta : ctx->h_theta, (size_t)batch * P * 8, cudaMemcpyHostToDevice, st));
     double *d_nlml = ctx->d_out, *d_grad = ctx->d_out + batch;
+    auto fetch_outputs = [&]() -> int {
+        if (pin_out) {
+            CU(cudaMemcpyAsync(nlml, d_nlml, (size_t)batch * 8, cudaMemcpyDeviceToHost, st));
+            if (want_grad) CU(cudaMemcpyAsync(grad, d_grad, (size_t)batch * P * 8, cudaMemcpyDeviceToHost, st));
+        } else {
+            const size_t nout = want_grad ? (size_t)batch * (P + 1) : (size_t)batch;
+            CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, nout * 8, cudaMemcpyDeviceToHost, st));
+        }
+        return MEDGP_OK;
+    };
     std::vector<Request> reqs(batch);
     for (int b = 0; b < batch; b++) reqs[b] = {series_id[b], b, 0, 0, 0};
     for (int round = 0; round <= kMaxJitter && !reqs.empty(); round++) {
@@ -874,6 +916,10 @@ MEDGP_API int medgp_cuda_nlml_grad(medgp_ctx *ctx, int batch, const int *series_
                        nullptr, nullptr, 0);
         if (rc) return rc;
         CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+        // the results ride on the same synchronisation as the status words: in the common case
+        // (nothing needs jitter) the call ends after this one wait
+        rc = fetch_outputs();
+        if (rc) return rc;
         CU(cudaStreamSynchronize(st));
         resolve_marks(ctx);
         // jitter: add sigma^2 to the diagonal again and refactor (c_inference_exact.cpp:99-108)
@@ -886,11 +932,10 @@ MEDGP_API int medgp_cuda_nlml_grad(medgp_ctx *ctx, int batch, const int *series_
             }
         reqs.swap(again);
     }
-    const size_t nout = want_grad ? (size_t)batch * (P + 1) : (size_t)batch;
-    CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, nout * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    memcpy(nlml, ctx->h_out, (size_t)batch * 8);
-    if (want_grad) memcpy(grad, ctx->h_out + batch, (size_t)batch * P * 8);
+    if (!pin_out) {
+        memcpy(nlml, ctx->h_out, (size_t)batch * 8);
+        if (want_grad) memcpy(grad, ctx->h_out + batch, (size_t)batch * P * 8);
+    }
     memcpy(status, ctx->h_status, (size_t)batch * sizeof(int));
     return MEDGP_OK;
 }

@@ -240,3 +240,30 @@ def test_every_factorisation_path(api, oracle, monkeypatch, env, batch):
         f0, g0, _ = oracle.nlml_grad(Q, D, R, *pats[k], thetas[k])
         assert abs(f[k] - f0) <= RTOL * abs(f0)
         assert rel(g[k], g0) <= RTOL
+
+
+def test_pinned_host_buffers_take_the_direct_copy_path(api):
+    """Page-locked caller buffers (medgp_cuda_host_alloc) are copied by DMA without staging;
+    the results must be bit-identical to the pageable path, also when jitter rounds re-run."""
+    Q, D, R = 2, 3, 2
+    ctx = api.Context(Q, D, R, workspace_bytes=1 << 30)
+    sizes = [50, 130, 64, 7]
+    thetas = synth.init_hyp_lmc_sm(Q, D, R, len(sizes), seed=5)
+    thetas[1, :D] = -40.0  # noise ~ 0 on a series with duplicated timestamps: needs jitter or fails
+    sids = []
+    for k, n in enumerate(sizes):
+        meta, x, y = synth.make_patient(D, n, 300 + k)
+        if k == 1:
+            x[1::2] = x[0::2][: len(x[1::2])]
+            meta[:] = 0
+        sids.append(ctx.add_series(meta, x, y))
+    f0, g0, s0 = ctx.nlml_grad(sids, thetas, True)
+    th = ctx.pinned(thetas.shape)
+    th[...] = thetas
+    outs = (ctx.pinned((len(sizes),)), ctx.pinned((len(sizes), ctx.P)), ctx.pinned((len(sizes),), np.int32))
+    f1, g1, s1 = ctx.nlml_grad(sids, th, True, out=outs)
+    assert f1 is outs[0] and g1 is outs[1]
+    assert np.array_equal(s0, s1)
+    assert np.array_equal(f0, f1, equal_nan=True)
+    assert np.array_equal(g0, g1, equal_nan=True)
+    ctx.close()
