@@ -82,6 +82,12 @@ int medgp_cuda_num_hyp(const medgp_ctx *ctx);  /* P, or negative status */
  * Any point order is accepted; results do not depend on it. */
 int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, const float *x,
                           const float *y, int *out_series_id);
+/* Internal point order of an uploaded series.  FEATURE (what medgp_cuda_add_series uses) serves
+ * NLML, gradients and medgp_cuda_predict; TIME serves medgp_cuda_predict_online (and NLML /
+ * medgp_cuda_predict), not gradients.  At most 32 points may share one timestamp with TIME. */
+enum { MEDGP_ORDER_FEATURE = 0, MEDGP_ORDER_TIME = 1 };
+int medgp_cuda_add_series_ordered(medgp_ctx *ctx, int n, const int32_t *meta, const float *x,
+                                  const float *y, int order, int *out_series_id);
 int medgp_cuda_free_series(medgp_ctx *ctx, int series_id);
 int medgp_cuda_clear_series(medgp_ctx *ctx);
 
@@ -110,6 +116,19 @@ int medgp_cuda_sync(medgp_ctx *ctx);
 int medgp_cuda_predict(medgp_ctx *ctx, int batch, const int *series_id, const double *theta,
                        const int *star_offset, const int32_t *meta_star, const float *x_star,
                        double *mean, double *var, int *status);
+
+/* Online one-step-ahead imputation of whole series, the loop of run_test_one without
+ * hyper-parameter updates (main_one_test.cpp:269-444), with ONE factorisation per series instead
+ * of one per observation: for every point j of series_id[b] (uploaded with MEDGP_ORDER_TIME),
+ * mean/var of y_j given all points with an earlier timestamp plus the other points sharing j's
+ * timestamp (:286-306, :354-366), under theta[b*P..].  var includes the noise of j's feature
+ * (core/gp_regression.cpp:185-196).  Outputs are concatenated in batch order, each series'
+ * n values in the caller's point order.  A point with no training data gets mean 0 and its prior
+ * variance.  No jitter on this path: status[b] = -1 (results NaN) when the time-ordered
+ * matrix is not positive definite -- the caller then falls back to medgp_cuda_predict per
+ * observation, which retries with jitter exactly as the reference does. */
+int medgp_cuda_predict_online(medgp_ctx *ctx, int batch, const int *series_id, const double *theta,
+                              double *mean, double *var, int *status);
 
 /* Debug/parity taps (tests only; one evaluation): the assembled K+noise (n*n, row-major,
  * full symmetric) for kernel (1); the Cholesky factor L (n*n row-major lower) and

@@ -15,15 +15,16 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MEDGP_LIB", os.path.join(HERE, "libmedgp_cuda.so"))  # MEDGP_LIB: experiments only
 PI_REF = 3.14159265  # medgpc/src/util/global_settings.h:6
+ORDER_FEATURE, ORDER_TIME = 0, 1  # include/medgp_cuda.h: MEDGP_ORDER_*
 
 STAGES = ["prep", "assemble", "potrf", "diag", "solve", "trtri", "lauum", "grad", "predict"]
 
 # every symbol include/medgp_cuda.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "medgp_cuda_create", "medgp_cuda_destroy", "medgp_cuda_last_error", "medgp_cuda_model",
-    "medgp_cuda_num_hyp", "medgp_cuda_add_series", "medgp_cuda_free_series",
+    "medgp_cuda_num_hyp", "medgp_cuda_add_series", "medgp_cuda_add_series_ordered", "medgp_cuda_free_series",
     "medgp_cuda_clear_series", "medgp_cuda_nlml_grad", "medgp_cuda_nlml_grad_device",
-    "medgp_cuda_sync", "medgp_cuda_predict", "medgp_cuda_debug_matrices", "medgp_cuda_profile",
+    "medgp_cuda_sync", "medgp_cuda_predict", "medgp_cuda_predict_online", "medgp_cuda_debug_matrices", "medgp_cuda_profile",
     "medgp_cuda_stage_times", "medgp_cuda_malloc", "medgp_cuda_free", "medgp_cuda_memcpy_h2d",
     "medgp_cuda_memcpy_d2h", "medgp_cuda_host_alloc", "medgp_cuda_host_free", "medgp_cuda_stream",
 ]
@@ -65,6 +66,8 @@ def load_library():
     lib.medgp_cuda_model.argtypes = [vp, i, i, i, ctypes.c_double]
     lib.medgp_cuda_num_hyp.argtypes = [vp]
     lib.medgp_cuda_add_series.argtypes = [vp, i, ip, fp, fp, ip]
+    lib.medgp_cuda_add_series_ordered.argtypes = [vp, i, ip, fp, fp, i, ip]
+    lib.medgp_cuda_predict_online.argtypes = [vp, i, ip, dp, dp, dp, ip]
     lib.medgp_cuda_free_series.argtypes = [vp, i]
     lib.medgp_cuda_clear_series.argtypes = [vp]
     lib.medgp_cuda_nlml_grad.argtypes = [vp, i, ip, dp, i, dp, dp, ip]
@@ -111,6 +114,7 @@ class Context:
                              "(no sm_100 GPU? there is no CPU fallback)")
         self.Q, self.D, self.R = Q, D, R
         self._pinned = []
+        self._n = {}
         self._check(self.lib.medgp_cuda_model(self.h, Q, D, R, float(pi)))
         self.P = self.lib.medgp_cuda_num_hyp(self.h)
 
@@ -134,13 +138,15 @@ class Context:
             pass
 
     # ------------------------------------------------------------------ series
-    def add_series(self, meta, x, y):
+    def add_series(self, meta, x, y, order=ORDER_FEATURE):
+        """order=ORDER_TIME uploads the series for predict_online (no gradients on it)."""
         meta = np.ascontiguousarray(meta, dtype=np.int32)
         x = np.ascontiguousarray(x, dtype=np.float32)
         y = np.ascontiguousarray(y, dtype=np.float32)
         sid = ctypes.c_int(-1)
-        self._check(self.lib.medgp_cuda_add_series(self.h, len(x), _ip(meta), _fp(x), _fp(y),
-                                                   ctypes.byref(sid)))
+        self._check(self.lib.medgp_cuda_add_series_ordered(self.h, len(x), _ip(meta), _fp(x), _fp(y),
+                                                           int(order), ctypes.byref(sid)))
+        self._n[sid.value] = len(x)
         return sid.value
 
     def free_series(self, sid):
@@ -189,6 +195,20 @@ class Context:
             self.h, len(sids), _ip(sids), _dp(theta), _ip(star_offset), _ip(meta_star),
             _fp(x_star), _dp(mean), _dp(var), _ip(status)))
         return mean, var, status
+
+    def predict_online(self, series_ids, theta):
+        """One-step-ahead imputation of every point of every (time-ordered) series with one
+        factorisation each.  Returns (list of mean arrays, list of var arrays, status)."""
+        sids = np.ascontiguousarray(series_ids, dtype=np.int32)
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(len(sids), self.P)
+        ns = [self._n[int(s)] for s in sids]
+        tot = int(sum(ns))
+        mean, var = np.empty(tot), np.empty(tot)
+        status = np.empty(len(sids), dtype=np.int32)
+        self._check(self.lib.medgp_cuda_predict_online(self.h, len(sids), _ip(sids), _dp(theta),
+                                                       _dp(mean), _dp(var), _ip(status)))
+        cut = np.cumsum(ns)[:-1]
+        return np.split(mean, cut), np.split(var, cut), status
 
     # ------------------------------------------------------------------ device-resident variant
     def malloc(self, nbytes):

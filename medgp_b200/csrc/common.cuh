@@ -47,7 +47,9 @@ struct __align__(16) EvalDesc {
     int star_out;            // offset of this evaluation's predictions in the output arrays
     int pad0;
     double trange2;          // (max t - min t)^2 of the series: bounds every tau^2 of the training block
-    double pad1;
+    const int *gstart;       // time-ordered series: first point of every same-timestamp group (ngroups + 1)
+    const int *perm;         // internal position -> caller's point index
+    int ngroups, pad1;
 };
 
 // tile-major addressing (kTileElems doubles per tile, column pitch MEDGP_SLD)

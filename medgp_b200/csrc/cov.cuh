@@ -506,3 +506,45 @@ k_pred_finish(const EvalDesc *__restrict__ descs, ModelDims md, double *__restri
         out_var[e.star_out + s] = bad ? nanv : e.par[md.oBdiag + ms] - acc[1] + e.par[md.oSig2 + ms];
     }
 }
+
+// ------------------------------------------------------------------ kernel (4'): online imputation
+// One factorisation of the TIME-ordered series serves every step of the reference's sliding
+// window without hyper-parameter updates (main_one_test.cpp:269-444): the training set of point j
+// is "all earlier points plus the other points sharing its timestamp" (:286-306, :354-366), i.e.
+// with G = [a, b) the group of j, all of [0, b) except j.  K_[0,b) = L_b L_b^T is the leading
+// block of the full factor, and the leave-one-out predictive of j within [0, b) is
+//     var_j = 1 / (K_b^-1)_jj,   mean_j = y_j - (K_b^-1 y)_j / (K_b^-1)_jj
+// (var includes the noise of j's feature, as gp_regression.cpp:185-196 adds it).  Only the
+// g x g diagonal block X = L_GG^-1 is needed: (K_b^-1)_jj = sum_{i>=j} X_ij^2 and
+// (K_b^-1 y)_j = sum_{i>=j} X_ij z_i with z = L^-1 y from the fused forward solve.
+// grid (groups, evaluations), one warp per group, lane = column j of X (groups of up to
+// MEDGP_GMAX points; larger ones are rejected when the series is uploaded).
+#define MEDGP_GMAX 32
+
+__global__ void __launch_bounds__(32)
+k_online(const EvalDesc *__restrict__ descs, double *__restrict__ out_mean, double *__restrict__ out_var,
+         const int *__restrict__ fail)
+{
+    __shared__ double sx[MEDGP_GMAX * MEDGP_GMAX];  // sx[i * 32 + lane]: X_ij for this lane's column
+    const EvalDesc &e = descs[blockIdx.y];
+    if ((int)blockIdx.x >= e.ngroups) return;
+    const int a = e.gstart[blockIdx.x], g = e.gstart[blockIdx.x + 1] - a, lane = threadIdx.x;
+    if (lane >= g) return;
+    const int T = e.T, j = a + lane;
+    const double *z = e.rhs;
+    double cc = 0.0, u = 0.0;
+    for (int i = lane; i < g; i++) {
+        double s = (i == lane) ? 1.0 : 0.0;
+        for (int k = lane; k < i; k++) s -= e.M[elem_off(T, a + i, a + k)] * sx[k * MEDGP_GMAX + lane];
+        const double x = s / e.M[elem_off(T, a + i, a + i)];
+        sx[i * MEDGP_GMAX + lane] = x;
+        cc = fma(x, x, cc);
+        u = fma(x, z[a + i], u);
+    }
+    const bool bad = fail[e.out_index] != 0;
+    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+    const int o = e.star_out + e.perm[j];
+    const bool alone = (a == 0 && g == 1);  // no training data at all: the prior, mean exactly 0
+    out_var[o] = bad ? nanv : 1.0 / cc;
+    out_mean[o] = bad ? nanv : (alone ? 0.0 : e.y[j] - u / cc);
+}

@@ -36,6 +36,9 @@ struct Series {
     bool alive = false;
     int n = 0, npad = 0, T = 0, nitems = 0, nseg = 0;
     double trange2 = 0.0;   // (max t - min t)^2
+    bool time_order = false; // points sorted by time (online imputation) instead of by feature
+    int ngroups = 0;         // same-timestamp groups of a time-ordered series
+    int *d_gstart = nullptr, *d_perm = nullptr;
     double *d_t = nullptr, *d_y = nullptr;
     int *d_meta = nullptr, *d_off = nullptr, *d_seg_start = nullptr;
     int4 *d_items = nullptr;
@@ -235,7 +238,7 @@ void resolve_marks(medgp_ctx *ctx)
 // One sub-chunk = a contiguous descriptor range launched on one stream.
 struct SubChunk {
     size_t base = 0, cnt = 0;
-    int Tmax = 0, items_max = 0, nstar_max = 0;
+    int Tmax = 0, items_max = 0, nstar_max = 0, groups_max = 0;
     std::vector<int> T;  // per evaluation, descending
     unsigned act(int k) const  // evaluations with T > k (a prefix: sorted descending)
     {
@@ -390,10 +393,17 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
         out.push_back([=]() { k_pred_finish<<<dim3(nsm, ncta), 256, 0, st>>>(dd, md, d_mean, d_var, d_fail); L[MEDGP_STAGE_PREDICT]++; });
         end(MEDGP_STAGE_PREDICT);
     }
+    if (mode == 3 && sc.groups_max > 0) {
+        const int ng = sc.groups_max;
+        begin(MEDGP_STAGE_PREDICT);
+        out.push_back([=]() { k_online<<<dim3(ng, ncta), 32, 0, st>>>(dd, d_mean, d_var, d_fail); L[MEDGP_STAGE_PREDICT]++; });
+        end(MEDGP_STAGE_PREDICT);
+    }
 }
 
 // The core: run `reqs` (any sizes) through the stage sequence.  d_theta is indexed by
-// out_index.  mode: 0 = NLML only, 1 = NLML + gradient, 2 = prediction.
+// out_index.  mode: 0 = NLML only, 1 = NLML + gradient, 2 = prediction, 3 = online imputation
+// (time-ordered series; star_off of the request = offset of the series in d_mean / d_var).
 // Evaluations are sorted by size, cut into chunks that fit the arena, and every chunk is dealt
 // round-robin into up to kMaxStreams sub-chunks that run on their own streams, so the
 // latency-bound phases of one sub-chunk (diagonal blocks, small trtri rows, tails) overlap the
@@ -473,12 +483,14 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
                 e.n = s.n; e.npad = s.npad; e.T = s.T; e.nitems = s.nitems;
                 e.jitter = rq.jitter; e.nrhs = 1 + rq.nstar; e.nstar = rq.nstar;
                 e.out_index = rq.out_index; e.star_out = rq.star_off;
-                e.pad0 = 0; e.trange2 = s.trange2; e.pad1 = 0.0;
+                e.pad0 = 0; e.trange2 = s.trange2; e.pad1 = 0;
+                e.gstart = s.d_gstart; e.perm = s.d_perm; e.ngroups = s.ngroups;
                 sc.T.push_back(s.T);
                 sc.cnt++;
                 sc.Tmax = std::max(sc.Tmax, s.T);
                 sc.items_max = std::max(sc.items_max, s.nitems);
                 sc.nstar_max = std::max(sc.nstar_max, rq.nstar);
+                sc.groups_max = std::max(sc.groups_max, s.ngroups);
                 // algorithmic work
                 const double n = s.n;
                 ctx->times.flops[MEDGP_STAGE_POTRF] += n * n * n / 3.0;
@@ -529,7 +541,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
             mix((uint64_t)(uintptr_t)d_status); mix((uint64_t)(uintptr_t)d_mean); mix((uint64_t)(uintptr_t)d_var);
             mix((uint64_t)(uintptr_t)ctx->d_fail);
             for (auto &sc : subs) {
-                mix(sc.cnt); mix((uint64_t)sc.items_max); mix((uint64_t)sc.nstar_max);
+                mix(sc.cnt); mix((uint64_t)sc.items_max); mix((uint64_t)sc.nstar_max); mix((uint64_t)sc.groups_max);
                 for (int t : sc.T) mix((uint64_t)t);
             }
             auto it = ctx->graphs.find(key);
@@ -697,10 +709,11 @@ MEDGP_API int medgp_cuda_num_hyp(const medgp_ctx *ctx)
     return (ctx && ctx->model_set) ? ctx->md.P : (int)MEDGP_ERR_ARG;
 }
 
-MEDGP_API int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, const float *x,
-                                    const float *y, int *out_series_id)
+MEDGP_API int medgp_cuda_add_series_ordered(medgp_ctx *ctx, int n, const int32_t *meta, const float *x,
+                                            const float *y, int order, int *out_series_id)
 {
-    if (!ctx || !ctx->model_set || n < 1 || !meta || !x || !y || !out_series_id) {
+    if (!ctx || !ctx->model_set || n < 1 || !meta || !x || !y || !out_series_id ||
+        (order != MEDGP_ORDER_FEATURE && order != MEDGP_ORDER_TIME)) {
         if (ctx) ctx->err = "add_series: bad argument or model not set";
         return MEDGP_ERR_ARG;
     }
@@ -717,10 +730,15 @@ MEDGP_API int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, 
     s.npad = (n + MEDGP_NB - 1) / MEDGP_NB * MEDGP_NB;
     s.T = s.npad / MEDGP_NB;
     // feature-major internal order (stable): results are order independent, and the gradient
-    // kernel's work items need every feature contiguous.
+    // kernel's work items need every feature contiguous.  Time-major (stable) for online
+    // imputation: every sliding-window training set is then a leading block plus its group.
+    s.time_order = (order == MEDGP_ORDER_TIME);
     s.perm.resize(n);
     std::iota(s.perm.begin(), s.perm.end(), 0);
-    std::stable_sort(s.perm.begin(), s.perm.end(), [&](int a, int b) { return meta[a] < meta[b]; });
+    if (s.time_order)
+        std::stable_sort(s.perm.begin(), s.perm.end(), [&](int a, int b) { return x[a] < x[b]; });
+    else
+        std::stable_sort(s.perm.begin(), s.perm.end(), [&](int a, int b) { return meta[a] < meta[b]; });
     std::vector<double> ht(s.npad, 0.0), hy(s.npad, 0.0);
     std::vector<int> hm(s.npad, 0), off(D + 1, 0);
     for (int i = 0; i < n; i++) {
@@ -742,7 +760,7 @@ MEDGP_API int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, 
     std::vector<int4> items;
     std::vector<int> seg_start(D + 1, 0);
     int nseg = 0;
-    for (int i0 = 0; i0 < n; i0 += kGradRows) {
+    for (int i0 = 0; i0 < n && !s.time_order; i0 += kGradRows) {
         const int i1 = std::min(i0 + kGradRows, n);
         int jb = 0;
         for (int f = 0; f < D && off[f] < i1; f++) {
@@ -761,11 +779,26 @@ MEDGP_API int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, 
     for (int d = 0; d < D; d++) seg_start[d + 1] += seg_start[d];
     s.nitems = (int)items.size();
     s.nseg = nseg;
+    // same-timestamp groups (float equality, as main_one_test.cpp:300 compares)
+    std::vector<int> gstart;
+    if (s.time_order) {
+        for (int i = 0; i < n; i++)
+            if (i == 0 || x[s.perm[i]] != x[s.perm[i - 1]]) gstart.push_back(i);
+        gstart.push_back(n);
+        s.ngroups = (int)gstart.size() - 1;
+        for (int g = 0; g < s.ngroups; g++)
+            if (gstart[g + 1] - gstart[g] > MEDGP_GMAX) {
+                ctx->err = "add_series: more than 32 points share one timestamp (online imputation groups)";
+                return MEDGP_ERR_ARG;
+            }
+    }
     // one allocation + one copy per series (test-time workloads upload thousands of short ones)
     const size_t o_t = 0, o_y = o_t + (size_t)s.npad * 8, o_meta = o_y + (size_t)s.npad * 8;
     const size_t o_off = align_up(o_meta + (size_t)s.npad * 4, 16), o_items = align_up(o_off + (size_t)(D + 1) * 4, 16);
     const size_t o_pair = o_items + std::max<size_t>(1, items.size()) * sizeof(int4);
-    const size_t total = o_pair + seg_start.size() * sizeof(int);
+    const size_t o_gs = align_up(o_pair + seg_start.size() * sizeof(int), 16);
+    const size_t o_perm = o_gs + gstart.size() * sizeof(int);
+    const size_t total = o_perm + (s.time_order ? (size_t)n * sizeof(int) : 0);
     std::vector<char> blob(total, 0);
     memcpy(blob.data() + o_t, ht.data(), (size_t)s.npad * 8);
     memcpy(blob.data() + o_y, hy.data(), (size_t)s.npad * 8);
@@ -773,6 +806,10 @@ MEDGP_API int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, 
     memcpy(blob.data() + o_off, off.data(), (size_t)(D + 1) * 4);
     if (!items.empty()) memcpy(blob.data() + o_items, items.data(), items.size() * sizeof(int4));
     memcpy(blob.data() + o_pair, seg_start.data(), seg_start.size() * sizeof(int));
+    if (s.time_order) {
+        memcpy(blob.data() + o_gs, gstart.data(), gstart.size() * sizeof(int));
+        memcpy(blob.data() + o_perm, s.perm.data(), (size_t)n * sizeof(int));
+    }
     char *d_blob = nullptr;
     CU(cudaMalloc(&d_blob, total));
     CU(cudaMemcpy(d_blob, blob.data(), total, cudaMemcpyHostToDevice));
@@ -782,6 +819,10 @@ MEDGP_API int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, 
     s.d_off = (int *)(d_blob + o_off);
     s.d_items = (int4 *)(d_blob + o_items);
     s.d_seg_start = (int *)(d_blob + o_pair);
+    if (s.time_order) {
+        s.d_gstart = (int *)(d_blob + o_gs);
+        s.d_perm = (int *)(d_blob + o_perm);
+    }
     // reuse a dead slot if there is one
     int id = -1;
     for (size_t i = 0; i < ctx->series.size(); i++)
@@ -790,6 +831,12 @@ MEDGP_API int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, 
     ctx->series[id] = std::move(s);
     *out_series_id = id;
     return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, const float *x,
+                                    const float *y, int *out_series_id)
+{
+    return medgp_cuda_add_series_ordered(ctx, n, meta, x, y, MEDGP_ORDER_FEATURE, out_series_id);
 }
 
 MEDGP_API int medgp_cuda_free_series(medgp_ctx *ctx, int series_id)
@@ -886,6 +933,12 @@ MEDGP_API int medgp_cuda_nlml_grad(medgp_ctx *ctx, int batch, const int *series_
     cudaSetDevice(ctx->device);
     int rc = check_series_ids(ctx, batch, series_id);
     if (rc) return rc;
+    if (want_grad)
+        for (int b = 0; b < batch; b++)
+            if (ctx->series[series_id[b]].time_order) {
+                ctx->err = "nlml_grad: gradients need a feature-ordered series (medgp_cuda_add_series)";
+                return MEDGP_ERR_ARG;
+            }
     CU(cudaStreamSynchronize(ctx->stream));
     rc = ensure_staging(ctx, batch, 0);
     if (rc) return rc;
@@ -997,6 +1050,49 @@ MEDGP_API int medgp_cuda_predict(medgp_ctx *ctx, int batch, const int *series_id
     CU(cudaStreamSynchronize(st));
     memcpy(mean, ctx->h_out + batch, (size_t)nstar * 8);
     memcpy(var, ctx->h_out + batch + nstar, (size_t)nstar * 8);
+    memcpy(status, ctx->h_status, (size_t)batch * sizeof(int));
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_predict_online(medgp_ctx *ctx, int batch, const int *series_id,
+                                        const double *theta, double *mean, double *var, int *status)
+{
+    if (!ctx || !ctx->model_set || batch < 0 || !series_id || !theta || !mean || !var || !status) {
+        if (ctx) ctx->err = "predict_online: bad argument";
+        return MEDGP_ERR_ARG;
+    }
+    if (batch == 0) return MEDGP_OK;
+    cudaSetDevice(ctx->device);
+    int rc = check_series_ids(ctx, batch, series_id);
+    if (rc) return rc;
+    size_t ntot = 0;
+    std::vector<Request> reqs(batch);
+    for (int b = 0; b < batch; b++) {
+        const Series &s = ctx->series[series_id[b]];
+        if (!s.time_order) {
+            ctx->err = "predict_online: series must be uploaded with MEDGP_ORDER_TIME";
+            return MEDGP_ERR_ARG;
+        }
+        reqs[b] = {series_id[b], b, 0, 0, (int)ntot};
+        ntot += (size_t)s.n;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    rc = ensure_staging(ctx, batch, ntot);
+    if (rc) return rc;
+    const size_t P = ctx->md.P;
+    cudaStream_t st = ctx->stream;
+    memcpy(ctx->h_theta, theta, (size_t)batch * P * 8);
+    CU(cudaMemcpyAsync(ctx->d_theta, ctx->h_theta, (size_t)batch * P * 8, cudaMemcpyHostToDevice, st));
+    double *d_nlml = ctx->d_out, *d_mean = ctx->d_out + batch, *d_var = d_mean + ntot;
+    CU(cudaMemsetAsync(ctx->d_fail, 0, batch * sizeof(int), st));
+    rc = run_batch(ctx, reqs, ctx->d_theta, 3, d_nlml, nullptr, ctx->d_status, d_mean, d_var, 0);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, ((size_t)batch + 2 * ntot) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    resolve_marks(ctx);
+    memcpy(mean, ctx->h_out + batch, ntot * 8);
+    memcpy(var, ctx->h_out + batch + ntot, ntot * 8);
     memcpy(status, ctx->h_status, (size_t)batch * sizeof(int));
     return MEDGP_OK;
 }

@@ -29,11 +29,29 @@ static double now_s()
 
 namespace {
 struct HeldOut {            // one imputation task
-    vector<int> meta;       // training set
+    vector<int> meta;       // training set (filled when the task is predicted on its own)
     vector<float> time, value;
-    int test_meta;
+    int test_meta, index;   // index: position of the held-out observation in the patient's arrays
     float test_time, test_value, stamp;
+    bool has_training;
 };
+
+// training set of a task without hyper-parameter updates: every earlier observation, then the
+// other observations sharing its time stamp (main_one_test.cpp:286-306, :354-366)
+void fill_training(HeldOut &h, const vector<int> &meta_array, const vector<float> &time_array,
+                   const vector<float> &value_array)
+{
+    h.meta.clear(); h.time.clear(); h.value.clear();
+    for (int pass = 0; pass < 2; pass++)
+        for (size_t ii = 0; ii < time_array.size(); ii++) {
+            const bool take = pass == 0 ? time_array[ii] < h.stamp : (time_array[ii] == h.stamp && (int)ii != h.index);
+            if (take) {
+                h.meta.push_back(meta_array[ii]);
+                h.time.push_back(time_array[ii]);
+                h.value.push_back(value_array[ii]);
+            }
+        }
+}
 
 // predicts every task with `theta`; fills pred / ok.  Tasks without training data stay !ok.
 void predict_tasks(medgp_ctx *ctx, const vector<double> &theta, const vector<HeldOut> &tasks, size_t b, size_t e,
@@ -112,7 +130,7 @@ static void run_test_one(c_experiment &curr_exp, const string &PAN, int fold, bo
         float last_update_time = unique_time_array[0];
         for (int tt = 0; tt < (int)unique_time_array.size(); tt++) {
             const float stamp = unique_time_array[tt];
-            vector<int> past_m, curr_m;
+            vector<int> past_m, curr_m, curr_i;
             vector<float> past_t, past_v, curr_t, curr_v;
             for (size_t ii = 0; ii < time_array.size(); ii++) {
                 if (time_array[ii] < stamp) {
@@ -123,6 +141,7 @@ static void run_test_one(c_experiment &curr_exp, const string &PAN, int fold, bo
                     }
                 } else if (time_array[ii] == stamp) {
                     curr_m.push_back(meta_array[ii]);
+                    curr_i.push_back((int)ii);
                     curr_t.push_back(time_array[ii]);
                     curr_v.push_back(value_array[ii]);
                 }
@@ -153,13 +172,17 @@ static void run_test_one(c_experiment &curr_exp, const string &PAN, int fold, bo
             const size_t first_task = tasks.size();
             for (size_t jj = 0; jj < curr_t.size(); jj++) {
                 HeldOut h;
-                h.meta = past_m; h.time = past_t; h.value = past_v;
-                for (size_t kk = 0; kk < curr_m.size(); kk++)
-                    if (kk != jj) {  // same-time observations of other covariates join the training set
-                        h.meta.push_back(curr_m[kk]);
-                        h.time.push_back(curr_t[kk]);
-                        h.value.push_back(curr_v[kk]);
-                    }
+                if (flag_update) {
+                    h.meta = past_m; h.time = past_t; h.value = past_v;
+                    for (size_t kk = 0; kk < curr_m.size(); kk++)
+                        if (kk != jj) {  // same-time observations of other covariates join the training set
+                            h.meta.push_back(curr_m[kk]);
+                            h.time.push_back(curr_t[kk]);
+                            h.value.push_back(curr_v[kk]);
+                        }
+                }
+                h.has_training = past_t.size() + curr_t.size() > 1;
+                h.index = curr_i[jj];
                 h.test_meta = curr_m[jj]; h.test_time = curr_t[jj]; h.test_value = curr_v[jj]; h.stamp = stamp;
                 tasks.push_back(h);
             }
@@ -170,9 +193,42 @@ static void run_test_one(c_experiment &curr_exp, const string &PAN, int fold, bo
             if ((tt % 100) == 0) cout << "finish testing " << tt << "/" << unique_time_array.size() << " time stamps" << endl;
         }
         if (!flag_update) {
-            const size_t step = 512;  // training sets per library call
-            for (size_t b = 0; b < tasks.size(); b += step)
-                predict_tasks(ctx, best_parameter, tasks, b, std::min(tasks.size(), b + step), mean, var, status);
+            // Without updates every training set is "the earlier observations plus the rest of the
+            // time stamp": ONE factorisation of the time-ordered patient serves all of them
+            // (medgp_cuda_predict_online).  If that matrix is not positive definite, or a time
+            // stamp holds too many observations, fall back to one training set per observation,
+            // which retries with jitter exactly as the reference does.
+            bool online = false;
+            int sid = -1;
+            if (medgp_cuda_add_series_ordered(ctx, (int)time_array.size(), (const int32_t *)meta_array.data(),
+                                              time_array.data(), value_array.data(), MEDGP_ORDER_TIME, &sid) == MEDGP_OK) {
+                vector<double> m(time_array.size()), v(time_array.size());
+                int st = -1;
+                if (medgp_cuda_predict_online(ctx, 1, &sid, best_parameter.data(), m.data(), v.data(), &st) != MEDGP_OK) {
+                    std::cerr << "ERROR: medgp_cuda_predict_online: " << medgp_cuda_last_error(ctx) << endl;
+                    exit(1);
+                }
+                medgp_cuda_free_series(ctx, sid);
+                if (st == 0) {
+                    online = true;
+                    for (size_t k = 0; k < tasks.size(); k++) {
+                        if (!tasks[k].has_training) continue;  // status stays -1: zero-mean branch below
+                        mean[k] = (double)(float)m[tasks[k].index];  // the reference returns float moments
+                        var[k] = (double)(float)v[tasks[k].index];
+                        status[k] = 0;
+                    }
+                }
+            }
+            if (!online) {
+                cout << "Warning: one-factorisation imputation not applicable; refitting per observation" << endl;
+                const size_t step = 512;  // training sets per library call
+                for (size_t b = 0; b < tasks.size(); b += step) {
+                    const size_t e = std::min(tasks.size(), b + step);
+                    for (size_t k = b; k < e; k++) fill_training(tasks[k], meta_array, time_array, value_array);
+                    predict_tasks(ctx, best_parameter, tasks, b, e, mean, var, status);
+                    for (size_t k = b; k < e; k++) { tasks[k].meta.clear(); tasks[k].time.clear(); tasks[k].value.clear(); }
+                }
+            }
         }
         vector<int> out_feature, out_ci;
         vector<double> out_etime, out_error, out_pred;

@@ -89,4 +89,47 @@ int medgp_cuda_predict(medgp_ctx *c, int batch, const int *sid, const double *th
     }
     return MEDGP_OK;
 }
+int medgp_cuda_add_series_ordered(medgp_ctx *c, int n, const int32_t *meta, const float *x, const float *y,
+                                  int order, int *id)
+{
+    (void)order;  /* the oracle keeps the caller's order; results do not depend on it */
+    return medgp_cuda_add_series(c, n, meta, x, y, id);
+}
+/* The reference's loop restated literally (main_one_test.cpp:269-444 without updates): one fit per
+ * observation on "earlier points + the other points of the same time stamp".  The CUDA library
+ * gets the same numbers from one factorisation per series. */
+int medgp_cuda_predict_online(medgp_ctx *c, int batch, const int *sid, const double *theta, double *mean,
+                              double *var, int *status)
+{
+    size_t o = 0;
+    for (int b = 0; b < batch; b++) {
+        const series_t *s = &c->s[sid[b]];
+        const int n = s->n;
+        int32_t *tm = (int32_t *)malloc(sizeof(int32_t) * n);
+        float *tx = (float *)malloc(sizeof(float) * n), *ty = (float *)malloc(sizeof(float) * n);
+        status[b] = 0;
+        for (int j = 0; j < n; j++) {
+            int m = 0;
+            for (int pass = 0; pass < 2; pass++)
+                for (int i = 0; i < n; i++)
+                    if (pass == 0 ? s->x[i] < s->x[j] : (s->x[i] == s->x[j] && i != j)) {
+                        tm[m] = s->meta[i]; tx[m] = s->x[i]; ty[m] = s->y[i]; m++;
+                    }
+            int st = 0;
+            if (m == 0) {  /* prior: zero mean, k** + sigma^2, from a far-away dummy point */
+                const float far = s->x[j] + 1e9f;
+                medgp_oracle_predict(c->Q, c->D, c->R, c->pi, 1, &s->meta[j], &far, &s->y[j], theta + (size_t)b * c->P, 1,
+                                     &s->meta[j], &s->x[j], &mean[o + j], &var[o + j], &st);
+                mean[o + j] = 0.0;
+            } else {
+                medgp_oracle_predict(c->Q, c->D, c->R, c->pi, m, tm, tx, ty, theta + (size_t)b * c->P, 1, &s->meta[j],
+                                     &s->x[j], &mean[o + j], &var[o + j], &st);
+            }
+            if (st != 0) status[b] = -1;  /* no jitter on this path */
+        }
+        free(tm); free(tx); free(ty);
+        o += (size_t)n;
+    }
+    return MEDGP_OK;
+}
 int medgp_cuda_sync(medgp_ctx *c) { (void)c; return MEDGP_OK; }

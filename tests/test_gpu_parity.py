@@ -267,3 +267,58 @@ def test_pinned_host_buffers_take_the_direct_copy_path(api):
     assert np.array_equal(f0, f1, equal_nan=True)
     assert np.array_equal(g0, g1, equal_nan=True)
     ctx.close()
+
+
+def sliding_window_reference(oracle, Q, D, R, meta, x, y, theta):
+    """The reference's imputation loop without updates (main_one_test.cpp:269-444), one oracle
+    fit per observation: train = earlier points + same-timestamp points other than the target."""
+    n = len(x)
+    mean, var = np.zeros(n), np.zeros(n)
+    for tt in np.unique(x):
+        past = np.flatnonzero(x < tt)
+        curr = np.flatnonzero(x == tt)
+        for j in curr:
+            tr = np.concatenate([past, curr[curr != j]])
+            if len(tr) == 0:
+                mean[j] = np.nan  # reference: "no training observations" branch, handled on the host
+                continue
+            mu, v, _ = oracle.predict(Q, D, R, meta[tr], x[tr], y[tr], theta, meta[j:j + 1], x[j:j + 1])
+            mean[j], var[j] = mu[0], v[0]
+    return mean, var
+
+
+def test_online_imputation_one_factorisation_per_series(api, oracle):
+    """medgp_cuda_predict_online (prefix Cholesky + leave-one-out inside a timestamp group)
+    against the per-observation refits of the reference's loop."""
+    Q, D, R = 2, 4, 2
+    ctx = api.Context(Q, D, R, workspace_bytes=1 << 30)
+    thetas = synth.init_hyp_lmc_sm(Q, D, R, 3, seed=33)
+    cases = []
+    for k, n in enumerate([40, 150, 97]):
+        meta, x, y = synth.make_patient(D, n, 500 + k)
+        rng = np.random.default_rng(k)
+        # several features measured at the same instant, as a lab panel is: groups of 1..4
+        x = np.round(x, 0 if k == 1 else 1).astype(np.float32)
+        perm = rng.permutation(n)
+        cases.append((meta[perm], x[perm], y[perm]))
+    sids = [ctx.add_series(m, x, y, order=api.ORDER_TIME) for m, x, y in cases]
+    mean, var, st = ctx.predict_online(sids, thetas)
+    assert (st == 0).all()
+    for k, (m, x, y) in enumerate(cases):
+        rm, rv = sliding_window_reference(oracle, Q, D, R, m, x, y, thetas[k])
+        has = ~np.isnan(rm)
+        assert has.sum() >= len(x) - 1
+        assert rel(mean[k][has], rm[has]) <= RTOL
+        assert rel(var[k][has], rv[has]) <= RTOL
+        # a first point without any training data: zero mean, prior variance (B_ff + sigma_f^2)
+        for j in np.flatnonzero(~has):
+            assert mean[k][j] == 0.0
+            _, v0, _ = oracle.predict(Q, D, R, m[:1], x[:1] + 1e9, y[:1], thetas[k], m[j:j + 1], x[j:j + 1])
+            assert abs(var[k][j] - v0[0]) <= 1e-6 * v0[0]
+    # gradients are refused on a time-ordered series; NLML is not
+    f, _, s0 = ctx.nlml_grad(sids[:1], thetas[:1], want_grad=False)
+    f_ref = oracle.nlml_grad(Q, D, R, *cases[0], thetas[0], want_grad=False)[0]
+    assert s0[0] == 0 and abs(f[0] - f_ref) <= RTOL * abs(f_ref)
+    with pytest.raises(api.MedgpError):
+        ctx.nlml_grad(sids[:1], thetas[:1], want_grad=True)
+    ctx.close()
