@@ -722,3 +722,17 @@ k_solve(const EvalDesc *__restrict__ descs, ModelDims md, double *__restrict__ o
     }
 }
 
+
+// ------------------------------------------------------------------ stream stagger
+// Holds a sub-chunk's stream back for `ns` nanoseconds at the start of a step, so that the
+// sub-chunks do not march through the latency-bound phases (diagonal blocks, short row kernels)
+// in lock-step but interleave them with the other streams' tensor-core phases.
+__global__ void k_delay(unsigned long long ns)
+{
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(500);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < ns);
+}

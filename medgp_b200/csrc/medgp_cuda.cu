@@ -52,6 +52,7 @@ struct Request {
 struct StageMark {
     int stage;
     cudaEvent_t a, b;
+    int stream;  // sub-stream index, -1 = the context's stream (timeline dumps only)
 };
 
 struct GraphEntry {
@@ -85,10 +86,14 @@ struct medgp_ctx {
     bool use_graphs = true;  // MEDGP_GRAPHS=0 disables CUDA-graph replay of chunk launch sequences
     std::map<uint64_t, GraphEntry> graphs;
     bool fuse_diag = true;   // MEDGP_FUSE_DIAG=0: separate diagonal kernels in the left-looking path
+    int gemm_smem_pad = 0;  // MEDGP_GEMM_SMEM_PAD: extra dynamic smem of the tile-GEMM kernels (lowers their CTAs/SM; experiments)
+    int stagger_us = 0;     // MEDGP_STAGGER_US: start sub-chunk stream s that many microseconds x s late
     int fold_max = 128;     // MEDGP_FOLD_MAX: chunks with fewer matrices fold panel tiles into the diagonal blocks
     int force_rl = -1;  // MEDGP_RL=0/1 forces the left-/right-looking factorisation (experiments)
     cudaStream_t sub_streams[8] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
+    cudaEvent_t ev_t0 = nullptr;      // MEDGP_TIMELINE: origin of the dumped stage intervals
+    const char *timeline = nullptr;   // MEDGP_TIMELINE=<file>: with profiling on, keep the sub-streams and dump every stage interval
     // profiling
     bool profile = false;
     std::vector<StageMark> marks, open_marks;
@@ -207,14 +212,21 @@ void stage_begin(medgp_ctx *ctx, int stage, cudaStream_t st)
     if (!ctx->profile) return;
     cudaEvent_t a = get_event(ctx);
     cudaEventRecord(a, st);
-    ctx->open_marks.push_back({stage, a, nullptr});
+    int sidx = -1;
+    for (int i = 0; i < 8; i++)
+        if (ctx->sub_streams[i] == st) sidx = i;
+    ctx->open_marks.push_back({stage, a, nullptr, sidx});
 }
 
 void stage_end(medgp_ctx *ctx, int stage, cudaStream_t st)
 {
     if (!ctx->profile) return;
     for (size_t i = ctx->open_marks.size(); i-- > 0;)
-        if (ctx->open_marks[i].stage == stage) {
+        if (ctx->open_marks[i].stage == stage && ctx->open_marks[i].stream == [&]() {
+                int sidx = -1;
+                for (int q = 0; q < 8; q++)
+                    if (ctx->sub_streams[q] == st) sidx = q;
+                return sidx; }()) {
             StageMark m = ctx->open_marks[i];
             ctx->open_marks.erase(ctx->open_marks.begin() + i);
             m.b = get_event(ctx);
@@ -226,11 +238,21 @@ void stage_end(medgp_ctx *ctx, int stage, cudaStream_t st)
 
 void resolve_marks(medgp_ctx *ctx)
 {
+    FILE *tl = (ctx->timeline && ctx->ev_t0 && !ctx->marks.empty()) ? fopen(ctx->timeline, "a") : nullptr;
     for (auto &m : ctx->marks) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, m.a, m.b) == cudaSuccess) ctx->times.ms[m.stage] += ms;
+        if (tl) {
+            float t_a = 0.f;
+            cudaEventElapsedTime(&t_a, ctx->ev_t0, m.a);
+            fprintf(tl, "%d %d %.4f %.4f\n", m.stream, m.stage, t_a, t_a + ms);
+        }
         ctx->event_pool.push_back(m.a);
         ctx->event_pool.push_back(m.b);
+    }
+    if (tl) {
+        fprintf(tl, "# end of call\n");
+        fclose(tl);
     }
     ctx->marks.clear();
 }
@@ -304,11 +326,12 @@ void launch_grad(int Q, dim3 gg, cudaStream_t st, const EvalDesc *dd, const Mode
 typedef std::vector<std::function<void()> > LaunchList;
 
 void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStream_t st, const double *d_theta, int mode,
-               double *d_nlml, double *d_grad, int *d_status, double *d_mean, double *d_var, LaunchList &out)
+               double *d_nlml, double *d_grad, int *d_status, double *d_mean, double *d_var, LaunchList &out,
+               int stagger_slot = 0)
 {
     const ModelDims md = ctx->md;
     const bool grad = (mode == 1), pred = (mode == 2);
-    const int gemm_smem = kGemmSmemBytes;
+    const int gemm_smem = kGemmSmemBytes + ctx->gemm_smem_pad;
     const int asm_smem = (md.Q * md.D * md.D + md.Q) * 8;
     const int npairs = md.D * (md.D + 1) / 2;
     const int fin_smem = (md.Q * md.D * md.D + 2 * npairs * md.Q + md.D) * 8;
@@ -322,6 +345,10 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     auto begin = [&](int stage) { out.push_back([=]() { stage_begin(ctx, stage, st); }); };
     auto end = [&](int stage) { out.push_back([=]() { stage_end(ctx, stage, st); }); };
 
+    if (stagger_slot > 0 && ctx->stagger_us > 0) {
+        const unsigned long long ns = 1000ULL * (unsigned long long)ctx->stagger_us * (unsigned long long)stagger_slot;
+        out.push_back([=]() { k_delay<<<1, 1, 0, st>>>(ns); });
+    }
     begin(MEDGP_STAGE_PREP);
     out.push_back([=]() { k_prep<<<ncta, 256, 0, st>>>(dd, md, d_theta); L[MEDGP_STAGE_PREP]++; });
     end(MEDGP_STAGE_PREP);
@@ -419,6 +446,10 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         return ctx->series[a.series].npad > ctx->series[b.series].npad;
     });
     size_t pos = 0, dpos = desc_base;
+    if (ctx->profile && ctx->timeline) {
+        if (!ctx->ev_t0) cudaEventCreate(&ctx->ev_t0);
+        cudaEventRecord(ctx->ev_t0, st);
+    }
     while (pos < reqs.size()) {
         // ---- form a chunk
         size_t used = 0, cnt = 0;
@@ -438,7 +469,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         // ---- deal the chunk into sub-chunks (one stream each)
         const int Tbig = ctx->series[reqs[first].series].T;
         int S = 1;
-        if (!ctx->profile && ctx->max_streams > 1) {
+        if ((!ctx->profile || ctx->timeline) && ctx->max_streams > 1) {
             S = Tbig >= 16 ? (int)std::min<size_t>(cnt, ctx->max_streams)
                            : (int)std::min<size_t>(std::max<size_t>(1, cnt / 32), ctx->max_streams);
         }
@@ -513,7 +544,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
             std::vector<LaunchList> prog(S);
             for (int sidx = 0; sidx < S; sidx++)
                 build_sub(ctx, subs[sidx], rl, fold, S == 1 ? st : ctx->sub_streams[sidx], d_theta, mode, d_nlml,
-                          d_grad, d_status, d_mean, d_var, prog[sidx]);
+                          d_grad, d_status, d_mean, d_var, prog[sidx], S > 1 ? sidx : 0);
             if (S > 1) {
                 CU(cudaEventRecord(ctx->ev_fork, st));
                 for (int sidx = 0; sidx < S; sidx++) CU(cudaStreamWaitEvent(ctx->sub_streams[sidx], ctx->ev_fork, 0));
@@ -536,7 +567,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         } else {
             uint64_t key = 1469598103934665603ULL;
             auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ULL; };
-            mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
+            mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)ctx->stagger_us); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
             mix((uint64_t)(uintptr_t)d_theta); mix((uint64_t)(uintptr_t)d_nlml); mix((uint64_t)(uintptr_t)d_grad);
             mix((uint64_t)(uintptr_t)d_status); mix((uint64_t)(uintptr_t)d_mean); mix((uint64_t)(uintptr_t)d_var);
             mix((uint64_t)(uintptr_t)ctx->d_fail);
@@ -628,6 +659,9 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     ctx->max_streams = 8;
     if (const char *ev = getenv("MEDGP_RL")) ctx->force_rl = atoi(ev);
     if (const char *ev = getenv("MEDGP_FOLD_MAX")) ctx->fold_max = atoi(ev);
+    if (const char *ev = getenv("MEDGP_STAGGER_US")) ctx->stagger_us = atoi(ev);
+    if (const char *ev = getenv("MEDGP_GEMM_SMEM_PAD")) ctx->gemm_smem_pad = atoi(ev);
+    ctx->timeline = getenv("MEDGP_TIMELINE");
     if (const char *ev = getenv("MEDGP_FUSE_DIAG")) ctx->fuse_diag = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_GRAPHS")) ctx->use_graphs = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_STREAMS")) ctx->max_streams = std::max(1, std::min(8, atoi(ev)));
@@ -636,13 +670,13 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
-    cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
-    cudaFuncSetAttribute(k_potrf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
-    cudaFuncSetAttribute(k_trtri_row, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
-    cudaFuncSetAttribute(k_lauum, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
-    cudaFuncSetAttribute(k_potrf_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
-    cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
-    cudaFuncSetAttribute(k_trtri_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
+    cudaFuncSetAttribute(k_potrf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
+    cudaFuncSetAttribute(k_trtri_row, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
+    cudaFuncSetAttribute(k_lauum, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
+    cudaFuncSetAttribute(k_potrf_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
+    cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
+    cudaFuncSetAttribute(k_trtri_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
     *out = ctx;
     return MEDGP_OK;
 }

@@ -30,6 +30,8 @@ CASES = [
     (3, 4, 2, 130, 4),     # two tiles + 2 rows
     (5, 24, 8, 300, 5),    # C2 shape, small n
     (5, 24, 8, 500, 6),    # C2
+    (8, 3, 2, 150, 7),     # Q = MEDGP_QMAX: widest kernel templates (gradient stage > 48 KB of dynamic smem)
+    (7, 2, 1, 90, 8),
 ]
 
 
@@ -321,4 +323,20 @@ def test_online_imputation_one_factorisation_per_series(api, oracle):
     assert s0[0] == 0 and abs(f[0] - f_ref) <= RTOL * abs(f_ref)
     with pytest.raises(api.MedgpError):
         ctx.nlml_grad(sids[:1], thetas[:1], want_grad=True)
+    ctx.close()
+
+
+def test_online_imputation_rejects_oversized_timestamp_groups(api):
+    """More than 32 observations on one time stamp cannot use the one-factorisation path: the
+    time-ordered upload is refused (the front-end then refits per observation)."""
+    Q, D, R = 1, 2, 1
+    ctx = api.Context(Q, D, R, workspace_bytes=1 << 28)
+    n = 40
+    meta = (np.arange(n) % D).astype(np.int32)
+    x = np.full(n, 3.5, dtype=np.float32)
+    y = np.linspace(-1, 1, n).astype(np.float32)
+    with pytest.raises(api.MedgpError):
+        ctx.add_series(meta, x, y, order=api.ORDER_TIME)
+    sid = ctx.add_series(meta, x, y)  # feature order is unaffected
+    assert sid >= 0
     ctx.close()
