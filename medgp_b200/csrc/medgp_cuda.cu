@@ -86,6 +86,7 @@ struct medgp_ctx {
     bool use_graphs = true;  // MEDGP_GRAPHS=0 disables CUDA-graph replay of chunk launch sequences
     std::map<uint64_t, GraphEntry> graphs;
     bool fuse_diag = true;   // MEDGP_FUSE_DIAG=0: separate diagonal kernels in the left-looking path
+    bool chain_diag = false; // MEDGP_CHAIN_DIAG=1: diagonal blocks k >= 1 are factored inside the panel kernel of step k-1
     int gemm_smem_pad = 0;  // MEDGP_GEMM_SMEM_PAD: extra dynamic smem of the tile-GEMM kernels (lowers their CTAs/SM; experiments)
     int stagger_us = 0;     // MEDGP_STAGGER_US: start sub-chunk stream s that many microseconds x s late
     int fold_max = 128;     // MEDGP_FOLD_MAX: chunks with fewer matrices fold panel tiles into the diagonal blocks
@@ -375,11 +376,17 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
             end(MEDGP_STAGE_POTRF);
             continue;
         }
-        const int depth = (rl || fold) ? 0 : k;
-        const int pdepth = rl ? 0 : k, pfold = (!rl && fold) ? 1 : 0;
-        begin(MEDGP_STAGE_DIAG);
-        out.push_back([=]() { k_potrf_diag<<<a0, MEDGP_DIAG_THREADS, gemm_smem, st>>>(dd, k, depth, d_fail); L[MEDGP_STAGE_DIAG]++; });
-        end(MEDGP_STAGE_DIAG);
+        // chain_diag: the panel CTA of row k+1 folds its tile into K_{k+1,k+1} and factors that
+        // block on the spot, so only block 0 needs a diagonal launch and the 64-pivot chain of
+        // block k+1 hides behind the other panel CTAs of step k
+        const bool chain_diag = !rl && ctx->chain_diag;
+        const int depth = (rl || fold || chain_diag) ? 0 : k;
+        const int pdepth = rl ? 0 : k, pfold = chain_diag ? 2 : ((!rl && fold) ? 1 : 0);
+        if (!chain_diag || k == 0) {
+            begin(MEDGP_STAGE_DIAG);
+            out.push_back([=]() { k_potrf_diag<<<a0, MEDGP_DIAG_THREADS, gemm_smem, st>>>(dd, k, depth, d_fail); L[MEDGP_STAGE_DIAG]++; });
+            end(MEDGP_STAGE_DIAG);
+        }
         if (rem > 0) {
             begin(MEDGP_STAGE_POTRF);
             out.push_back([=]() { k_potrf_panel<<<dim3(rem, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, pdepth, pfold, d_fail); L[MEDGP_STAGE_POTRF]++; });
@@ -567,7 +574,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         } else {
             uint64_t key = 1469598103934665603ULL;
             auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ULL; };
-            mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)ctx->stagger_us); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
+            mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)ctx->stagger_us); mix(ctx->chain_diag); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
             mix((uint64_t)(uintptr_t)d_theta); mix((uint64_t)(uintptr_t)d_nlml); mix((uint64_t)(uintptr_t)d_grad);
             mix((uint64_t)(uintptr_t)d_status); mix((uint64_t)(uintptr_t)d_mean); mix((uint64_t)(uintptr_t)d_var);
             mix((uint64_t)(uintptr_t)ctx->d_fail);
@@ -661,6 +668,7 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     if (const char *ev = getenv("MEDGP_FOLD_MAX")) ctx->fold_max = atoi(ev);
     if (const char *ev = getenv("MEDGP_STAGGER_US")) ctx->stagger_us = atoi(ev);
     if (const char *ev = getenv("MEDGP_GEMM_SMEM_PAD")) ctx->gemm_smem_pad = atoi(ev);
+    if (const char *ev = getenv("MEDGP_CHAIN_DIAG")) ctx->chain_diag = atoi(ev) != 0;
     ctx->timeline = getenv("MEDGP_TIMELINE");
     if (const char *ev = getenv("MEDGP_FUSE_DIAG")) ctx->fuse_diag = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_GRAPHS")) ctx->use_graphs = atoi(ev) != 0;

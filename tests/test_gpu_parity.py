@@ -224,6 +224,8 @@ def test_long_stay_patient(api):
     ({"MEDGP_RL": "0", "MEDGP_FUSE_DIAG": "0"}, 6),         # left-looking, separate kernels, folded diagonal update
     ({"MEDGP_RL": "0"}, 140),                               # left-looking, separate kernels, large batch
     ({"MEDGP_RL": "0", "MEDGP_STREAMS": "1", "MEDGP_GRAPHS": "0"}, 140),   # single stream, no CUDA graph
+    ({"MEDGP_RL": "0", "MEDGP_CHAIN_DIAG": "1"}, 140),     # diagonal blocks factored inside the panel kernel
+    ({"MEDGP_RL": "0", "MEDGP_STAGGER_US": "15", "MEDGP_GEMM_SMEM_PAD": "8192"}, 140),  # scheduling knobs
 ])
 def test_every_factorisation_path(api, oracle, monkeypatch, env, batch):
     """all scheduling variants of kernel (2) give the oracle's numbers (n = 330: T = 6)"""
