@@ -91,3 +91,28 @@ def test_test_front_end_gpu_vs_oracle_build(tmp_path):
         assert len(outs["gpu"][n]) == 40
         assert np.abs(outs["gpu"][n] - outs["orc"][n]).max() <= 1e-6
     assert outs["gpu"]["ci"] == outs["orc"]["ci"]
+
+
+def test_cohort_test_front_end_gpu_vs_oracle_build(tmp_path):
+    """main_cohort_test on the GPU (one factorisation per patient, one call per shard) against
+    the same source on the oracle backend (one refit per observation)."""
+    Q, D, R = 2, 3, 2
+    pats = {f"p{k}": synth.make_patient(D, n, seed=400 + k, T=150.0) for k, n in enumerate([60, 131, 47, 90])}
+    for m, x, y in pats.values():
+        x[5] = x[17]
+        x[6] = x[17]
+    theta = synth.init_hyp_lmc_sm(Q, D, R, 1, seed=9)[0]
+    outs = {}
+    for tag, bindir in (("gpu", HOST), ("orc", BUILD)):
+        top = str(tmp_path / tag)
+        cfg = expfiles.write_experiment(top, Q, D, R, [1, 3, 4], pats)
+        expfiles.write_mode_kernel(top, Q, theta)
+        run([os.path.join(bindir, "main_cohort_test"), "--cfg", cfg, "--pans", os.path.join(top, "data", "cohort.txt"),
+             "--fold", "0", "--kernclust-alg", "None"])
+        outs[tag] = {pan: (expfiles.read_double_bin(os.path.join(top, "test", f"test_mean_wo_update_pred_{pan}.bin")),
+                           expfiles.read_int_txt(os.path.join(top, "test", f"test_mean_wo_update_ci_{pan}.txt")))
+                     for pan in pats}
+    for pan, (m, x, y) in pats.items():
+        assert len(outs["gpu"][pan][0]) == len(x)
+        assert np.abs(outs["gpu"][pan][0] - outs["orc"][pan][0]).max() <= 1e-6
+        assert outs["gpu"][pan][1] == outs["orc"][pan][1]

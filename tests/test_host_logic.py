@@ -201,3 +201,35 @@ def test_main_one_test_matches_python_replay(tmp_path, oracle):
         assert np.abs(got - np.array(preds)).max() <= tol
         assert np.abs(expfiles.read_double_bin(os.path.join(td, f"test_{name}_error_p0.bin")) - np.array(errs)).max() <= tol
         assert expfiles.read_int_txt(os.path.join(td, f"test_{name}_ci_p0.txt")) == cis
+
+
+def test_cohort_test_front_end_writes_what_main_one_test_writes(tmp_path):
+    """main_cohort_test (one batched online-imputation call per shard) against main_one_test run
+    patient by patient: identical test_mean_wo_update_* files, shards cover every patient."""
+    Q, D, R = 2, 2, 1
+    pats = _patients(D, [22, 35, 28], 60)
+    for k, (m, x, y) in enumerate(pats.values()):
+        x[2 + k] = x[9 + k]                          # shared time stamps
+    theta = synth.init_hyp_lmc_sm(Q, D, R, 1, seed=3)[0]
+    tops = {}
+    for tag in ("cohort", "single"):
+        top = tops[tag] = str(tmp_path / tag)
+        cfg = expfiles.write_experiment(top, Q, D, R, [18, 19], pats, online_learn_rate=1e-3)
+        expfiles.write_mode_kernel(top, Q, theta)
+        if tag == "cohort":
+            for s in range(2):
+                run([os.path.join(BUILD, "main_cohort_test"), "--cfg", cfg, "--pans", os.path.join(top, "data", "cohort.txt"),
+                     "--fold", "0", "--kernclust-alg", "None", "--shard", f"{s}/2"])
+        else:
+            for pan in pats:
+                run([os.path.join(BUILD, "main_one_test"), "--cfg", cfg, "--pan", pan, "--thread", "1", "--fold", "0",
+                     "--kernclust-alg", "None"])
+    for pan in pats:
+        for kind in ("pred", "error", "etime"):
+            a = expfiles.read_double_bin(os.path.join(tops["cohort"], "test", f"test_mean_wo_update_{kind}_{pan}.bin"))
+            b = expfiles.read_double_bin(os.path.join(tops["single"], "test", f"test_mean_wo_update_{kind}_{pan}.bin"))
+            assert len(a) == len(pats[pan][1]) and np.array_equal(a, b)
+        for kind in ("ci", "feature", "flag"):
+            a = expfiles.read_int_txt(os.path.join(tops["cohort"], "test", f"test_mean_wo_update_{kind}_{pan}.txt"))
+            b = expfiles.read_int_txt(os.path.join(tops["single"], "test", f"test_mean_wo_update_{kind}_{pan}.txt"))
+            assert a == b
