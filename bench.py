@@ -357,8 +357,8 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * P * 8),
-                    "d2h_bytes_per_step": int(B * (P + 1) * 8 + B * 4)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * B * P * 8),
+                    "d2h_bytes_per_step": int(world * (B * (P + 1) * 8 + B * 4))},
             "gpu_launches": int(sum(stages[k]["launches"] for k in names)),
             "roofline": roofline, "cpu_baseline": cpu,
         }

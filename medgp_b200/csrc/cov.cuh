@@ -118,7 +118,10 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
 #pragma unroll 2
     for (int u = 0; u < 16; u++) {
         const int c = g * 16 + u, gj = tj * MEDGP_NB + c;
-        if (gj > gi) continue;  // strictly upper part of a diagonal tile: not needed
+        if (gj > gi) {  // strictly upper part of a diagonal tile: never used as data, kept defined
+            out[c * MEDGP_SLD] = 0.0;
+            continue;
+        }
         double val;
         if (gi >= n || gj >= n) {
             val = (gi == gj) ? 1.0 : 0.0;

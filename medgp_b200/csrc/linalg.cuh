@@ -150,6 +150,7 @@ __device__ __forceinline__ void chol16_warp(double *sA, double *s_rs, int c0, in
     double a[16];
 #pragma unroll
     for (int c = 0; c < 16; c++) a[c] = (c <= r) ? sA[(c0 + c) * MEDGP_SLD + c0 + r] : 0.0;
+    __syncwarp();  // the mirror lanes have read the block before its columns are overwritten below
     double rs = rsqrt_fast(a[0]), rs_mine = rs;
     bool bad = false;
 #pragma unroll
@@ -181,8 +182,10 @@ __device__ __forceinline__ void chol16_warp(double *sA, double *s_rs, int c0, in
             }
         }
     }
-    if (bad) *s_fail = 1;
-    if (lane < 16) s_rs[c0 + r] = rs_mine;
+    if (lane < 16) {
+        if (bad) *s_fail = 1;
+        s_rs[c0 + r] = rs_mine;
+    }
 }
 
 // (b) one row below the diagonal block: l_rj = (s_rj - sum_{c<j} l_rc L_jc) / L_jj, right-looking
