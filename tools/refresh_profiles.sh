@@ -27,5 +27,6 @@ python bench.py --impl reference > "gpurun_out/${TAG}_bench_reference_arm.json" 
 python bench.py > "gpurun_out/${TAG}_bench_n1.json" 2> "gpurun_out/${TAG}_bench_n1.err"
 python tools/bench_predict.py 16 500 > "gpurun_out/${TAG}_online_imputation.json" 2> /dev/null
 python tools/bench_cholesky.py > "gpurun_out/${TAG}_cholesky_n4000.json" 2> /dev/null
+python tools/bench_latency.py 2> /dev/null | tail -1 > "gpurun_out/${TAG}_latency.json"
 python tools/bench_c3.py 256 5 3 2> /dev/null | tail -1 > "gpurun_out/${TAG}_c3_ragged.json"
 ls -la gpurun_out | tail -30

@@ -21,7 +21,7 @@ def run(*cmd):
 
 
 for name in ("launches_c2_step.csv", "dram_traffic_c2_step.csv", "bench_n1.json", "bench_reference_arm.json",
-             "online_imputation.json", "cholesky_n4000.json", "c3_ragged.json"):
+             "online_imputation.json", "cholesky_n4000.json", "c3_ragged.json", "latency.json"):
     f = os.path.join(SRC, f"{TAG}_{name}")
     if os.path.exists(f) and os.path.getsize(f) > 0:
         shutil.copy(f, os.path.join(DST, f"{TAG}_{name}"))
