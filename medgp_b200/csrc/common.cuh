@@ -156,37 +156,47 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // component per point pair; libdevice's exp() gets serialised per component, which leaves the
 // FP64 pipe waiting on its own dependent chains.  Writing the NV range reductions and Horner
 // steps side by side gives the scheduler NV independent chains.
-// x = k (ln2/32) + r, |r| <= ln2/64 (Cody-Waite, k*HI exact for |k| < 2^16), so
-// exp(x) = 2^(k>>5) * 2^((k&31)/32) * exp(r): a 32-entry table (correctly rounded, staged in
-// shared memory) and a degree-6 Taylor polynomial (truncation 4e-18 relative); the power of two
-// goes straight into the exponent field.  x < -708 flushes to 0 (true value below 1e-307).
-// 11 FP64 operations per value; max observed error vs exp(): 1.5 ulp.
+// x = k (ln2/64) + r, |r| <= ln2/128 (Cody-Waite, k*HI exact for |k| < 2^20), so
+// exp(x) = 2^(k>>6) * 2^((k&63)/64) * exp(r): a 64-entry table (correctly rounded, staged in
+// shared memory) and a degree-5 Taylor polynomial (truncation 3.5e-17 relative, below half an
+// ulp); the power of two goes straight into the exponent field.  x < -708 flushes to 0 (true
+// value below 1e-307).  10 FP64 operations per value; max observed error vs expl(): 1.5 ulp.
 // ---------------------------------------------------------------------------------------
-__constant__ double c_exp2_tab[32] = {
-    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924,
-    1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484,
-    1.2690509571917332, 1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,
-    1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228, 1.5422108254079407,
-    1.5759808451078865, 1.6104903319492543, 1.645755478153965, 1.681792830507429, 1.718619298122478,
-    1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103, 1.9152065613971474,
-    1.9571441241754002};
+#define MEDGP_EXP_TAB 64
+__constant__ double c_exp2_tab[MEDGP_EXP_TAB] = {
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
 
-__device__ __forceinline__ void exp_tab_stage(double *s_tab)  // call by >= 32 threads, then barrier
+__device__ __forceinline__ void exp_tab_stage(double *s_tab)  // call by the whole CTA, then barrier
 {
-    if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+    for (int i = threadIdx.x; i < MEDGP_EXP_TAB; i += blockDim.x) s_tab[i] = c_exp2_tab[i];
 }
 
 // polynomial and reduction constants live in constant memory so that the DFMAs take them as
 // constant-bank operands instead of re-materialising 64-bit immediates in registers
-__constant__ double c_expc[10] = {
-    46.16624130844683,        // 0: 32/ln2
-    0.021660849391992087,     // 1: ln2/32 high part (low 18 mantissa bits zero)
-    5.062034433330175e-13,    // 2: ln2/32 low part
-    1.38888888888888888889e-03, 8.33333333333333333333e-03, 4.16666666666666666667e-02,
-    1.66666666666666666667e-01, 0.5, 1.0, 1.0};  // 3..9: 1/6! .. 1/0!
+__constant__ double c_expc[9] = {
+    92.33248261689366,        // 0: 64/ln2
+    0.010830424695086549,     // 1: ln2/64 high part (low 20 mantissa bits zero)
+    1.162596423439437e-12,    // 2: ln2/64 low part
+    8.33333333333333333333e-03, 4.16666666666666666667e-02, 1.66666666666666666667e-01,
+    0.5, 1.0, 1.0};           // 3..8: 1/5! .. 1/0!
 
 // Largest |x| for which the unchecked variant is valid (k = x*32/ln2 must fit 32 bits).
-#define MEDGP_EXP_UNCHECKED_MAX 4.0e7
+#define MEDGP_EXP_UNCHECKED_MAX 2.0e7
 
 // CHECKED: any x <= 0 (x < -708 gives exactly 0).  !CHECKED: requires x >= -MEDGP_EXP_UNCHECKED_MAX;
 // results below 2^-1022 come out as some value < 2^-1021 instead of exactly 0 (the exponent
@@ -207,13 +217,13 @@ __device__ __forceinline__ void exp_nonpos(const double (&x)[NV], double (&out)[
         p[i] = c_expc[3];
     }
 #pragma unroll
-    for (int c = 4; c < 10; c++)
+    for (int c = 4; c < 9; c++)
 #pragma unroll
         for (int i = 0; i < NV; i++) p[i] = fma(p[i], r[i], c_expc[c]);
 #pragma unroll
     for (int i = 0; i < NV; i++) {
-        const double tj = s_tab[k[i] & 31];
-        int m = k[i] >> 5;
+        const double tj = s_tab[k[i] & (MEDGP_EXP_TAB - 1)];
+        int m = k[i] >> 6;
         if (!CHECKED) m = max(m, -1023);  // exponent field saturates at 0
         const double v = p[i] * __hiloint2double(__double2hiint(tj) + (m << 20), __double2loint(tj));
         out[i] = (CHECKED && x[i] < -708.0) ? 0.0 : v;

@@ -73,7 +73,7 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
     __shared__ double s_tr[MEDGP_NB], s_tc[MEDGP_NB];
     __shared__ int s_mr[MEDGP_NB], s_mc[MEDGP_NB];
     __shared__ double2 s_csr[MEDGP_QMAX][MEDGP_NB], s_csc[MEDGP_QMAX][MEDGP_NB];
-    __shared__ double s_tab[32];
+    __shared__ double s_tab[MEDGP_EXP_TAB];
     const EvalDesc &e = descs[blockIdx.y];
     int ti, tj;
     tri_index(blockIdx.x, ti, tj);
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(32 * MEDGP_GW, MEDGP_GOCC / MEDGP_GW)
 k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
-    __shared__ double s_tab[32];
+    __shared__ double s_tab[MEDGP_EXP_TAB];
     exp_tab_stage(s_tab);
     __syncthreads();
     const EvalDesc &e = descs[blockIdx.y];
