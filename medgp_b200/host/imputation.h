@@ -164,6 +164,56 @@ inline void impute_without_update(medgp_ctx *ctx, const vector<double> &theta, c
     }
 }
 
+// One time stamp of the with-update mode: tasks [first, end) are the observations `curr` of the
+// stamp, each trained on `past` (the 72 h history) plus the other observations of the stamp
+// (main_one_test.cpp:354-366).  With two or more observations one factorisation of past + curr
+// serves them all; otherwise, or if it fails, every training set is fitted on its own.
+inline void impute_time_stamp(medgp_ctx *ctx, const vector<double> &theta, const vector<int> &past_m,
+                              const vector<float> &past_t, const vector<float> &past_v, const vector<int> &curr_m,
+                              const vector<float> &curr_t, const vector<float> &curr_v, vector<HeldOut> &tasks,
+                              size_t first, vector<double> &mean, vector<double> &var, vector<int> &status)
+{
+    const size_t g = curr_t.size(), np = past_t.size();
+    if (g >= 2) {
+        vector<int> m(past_m);
+        vector<float> t(past_t), v(past_v);
+        m.insert(m.end(), curr_m.begin(), curr_m.end());
+        t.insert(t.end(), curr_t.begin(), curr_t.end());
+        v.insert(v.end(), curr_v.begin(), curr_v.end());
+        int sid = -1;
+        if (medgp_cuda_add_series_ordered(ctx, (int)t.size(), (const int32_t *)m.data(), t.data(), v.data(),
+                                          MEDGP_ORDER_TIME, &sid) == MEDGP_OK) {
+            vector<double> pm(t.size()), pv(t.size());
+            int st = -1;
+            if (medgp_cuda_predict_online(ctx, 1, &sid, theta.data(), pm.data(), pv.data(), &st) != MEDGP_OK) {
+                std::cerr << "ERROR: medgp_cuda_predict_online: " << medgp_cuda_last_error(ctx) << std::endl;
+                exit(1);
+            }
+            medgp_cuda_free_series(ctx, sid);
+            if (st == 0) {
+                for (size_t jj = 0; jj < g; jj++) {
+                    mean[first + jj] = (double)(float)pm[np + jj];  // the reference returns float moments
+                    var[first + jj] = (double)(float)pv[np + jj];
+                    status[first + jj] = 0;
+                }
+                return;
+            }
+        }
+    }
+    for (size_t jj = 0; jj < g; jj++) {
+        HeldOut &h = tasks[first + jj];
+        h.meta = past_m; h.time = past_t; h.value = past_v;
+        for (size_t kk = 0; kk < g; kk++)
+            if (kk != jj) {  // same-time observations of other covariates join the training set
+                h.meta.push_back(curr_m[kk]);
+                h.time.push_back(curr_t[kk]);
+                h.value.push_back(curr_v[kk]);
+            }
+    }
+    predict_tasks(ctx, theta, tasks, first, first + g, mean, var, status);
+    for (size_t jj = 0; jj < g; jj++) { tasks[first + jj].meta.clear(); tasks[first + jj].time.clear(); tasks[first + jj].value.clear(); }
+}
+
 // test_<mode>_{feature,ci}_<PAN>.txt and _{etime,error,pred}_<PAN>.bin (main_one_test.cpp:400-472)
 inline void write_imputation_outputs(c_experiment &curr_exp, const std::string &output_prefix, const std::string &PAN,
                                      const vector<HeldOut> &tasks, const vector<double> &mean, const vector<double> &var,

@@ -3,9 +3,11 @@
 // medgpc/src/main_one_test.cpp:45-480).
 //   main_one_test --cfg exp_setup.json --pan <PAN> --thread <T> --fold <F> --kernclust-alg <A>
 // Every held-out observation (tt, jj) trains on past + same-time observations and predicts
-// one point.  Without updates theta is fixed, so ALL training sets of the patient are
-// independent and go to the GPU in batches; with updates theta moves at each update time, so
-// the batch is the set of held-out points of one time stamp.
+// one point.  Without updates theta is fixed and ONE factorisation of the time-ordered patient
+// yields every prediction (medgp_cuda_predict_online); with updates theta moves at each update
+// time, so the unit is one time stamp: its observations are predicted from one factorisation of
+// "72 h history + this time stamp" (leave-one-out inside the time stamp).  Whenever that path
+// does not apply, the training sets are refitted one by one as the reference does.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -105,15 +107,6 @@ static void run_test_one(c_experiment &curr_exp, const string &PAN, int fold, bo
             const size_t first_task = tasks.size();
             for (size_t jj = 0; jj < curr_t.size(); jj++) {
                 HeldOut h;
-                if (flag_update) {
-                    h.meta = past_m; h.time = past_t; h.value = past_v;
-                    for (size_t kk = 0; kk < curr_m.size(); kk++)
-                        if (kk != jj) {  // same-time observations of other covariates join the training set
-                            h.meta.push_back(curr_m[kk]);
-                            h.time.push_back(curr_t[kk]);
-                            h.value.push_back(curr_v[kk]);
-                        }
-                }
                 h.has_training = past_t.size() + curr_t.size() > 1;
                 h.index = curr_i[jj];
                 h.test_meta = curr_m[jj]; h.test_time = curr_t[jj]; h.test_value = curr_v[jj]; h.stamp = stamp;
@@ -122,7 +115,9 @@ static void run_test_one(c_experiment &curr_exp, const string &PAN, int fold, bo
             mean.resize(tasks.size(), 0.0);
             var.resize(tasks.size(), 0.0);
             status.resize(tasks.size(), -1);
-            if (flag_update) predict_tasks(ctx, best_parameter, tasks, first_task, tasks.size(), mean, var, status);
+            if (flag_update)
+                impute_time_stamp(ctx, best_parameter, past_m, past_t, past_v, curr_m, curr_t, curr_v, tasks, first_task,
+                                  mean, var, status);
             if ((tt % 100) == 0) cout << "finish testing " << tt << "/" << unique_time_array.size() << " time stamps" << endl;
         }
         if (!flag_update) impute_without_update(ctx, best_parameter, meta_array, time_array, value_array, tasks, mean, var, status);

@@ -76,6 +76,9 @@ def test_train_front_ends_gpu_vs_oracle_build(tmp_path, oracle, prior_index, bud
 def test_test_front_end_gpu_vs_oracle_build(tmp_path):
     Q, D, R = 2, 2, 1
     meta, x, y = synth.make_patient(D, 40, seed=5, T=120.0)
+    x[3] = x[14]          # time stamps shared by two and three observations: the leave-one-out
+    x[20] = x[31]         # path inside a time stamp, in both modes
+    x[21] = x[31]
     theta = synth.init_hyp_lmc_sm(Q, D, R, 1, seed=3)[0]
     outs = {}
     for tag, bindir in (("gpu", HOST), ("orc", BUILD)):
