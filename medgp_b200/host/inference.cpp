@@ -257,6 +257,18 @@ bool c_objective_one::compute_objective(const bool &flag_grad, const vector<doub
     return true;
 }
 
+void c_objective_batch::release()
+{
+    if (!cap_) return;
+    medgp_cuda_host_free(ctx_, h_theta_);
+    medgp_cuda_host_free(ctx_, h_nlml_);
+    medgp_cuda_host_free(ctx_, h_grad_);
+    medgp_cuda_host_free(ctx_, h_status_);
+    h_theta_ = h_nlml_ = h_grad_ = nullptr;
+    h_status_ = nullptr;
+    cap_ = 0;
+}
+
 void c_objective_batch::compute(const bool &flag_grad, const vector<medgp_eval_request> &reqs,
                                 vector<medgp_eval_result> &out)
 {
@@ -264,23 +276,37 @@ void c_objective_batch::compute(const bool &flag_grad, const vector<medgp_eval_r
     const int P = medgp_cuda_num_hyp(ctx_);
     out.assign(B, medgp_eval_result());
     if (B == 0) return;
-    vector<int> sids(B), status(B);
-    vector<double> theta((size_t)B * P), nlml(B), grad(flag_grad ? (size_t)B * P : 0);
+    if ((size_t)B > cap_) {
+        release();
+        cap_ = std::max<size_t>(2 * (size_t)B, 64);
+        void *p[4] = {nullptr, nullptr, nullptr, nullptr};
+        const size_t bytes[4] = {cap_ * P * sizeof(double), cap_ * sizeof(double), cap_ * P * sizeof(double), cap_ * sizeof(int)};
+        for (int i = 0; i < 4; i++) {
+            const int rc = medgp_cuda_host_alloc(ctx_, bytes[i], &p[i]);
+            if (rc != MEDGP_OK) die("medgp_cuda_host_alloc", ctx_, rc);
+        }
+        h_theta_ = (double *)p[0]; h_nlml_ = (double *)p[1]; h_grad_ = (double *)p[2]; h_status_ = (int *)p[3];
+    }
+    vector<int> sids(B);
+    double *theta = h_theta_, *nlml = h_nlml_, *grad = h_grad_;
+    int *status = h_status_;
+#pragma omp parallel for schedule(static)
     for (int b = 0; b < B; b++) {
         sids[b] = reqs[b].series_id;
         memcpy(&theta[(size_t)b * P], reqs[b].theta->data(), sizeof(double) * P);
     }
-    int rc = medgp_cuda_nlml_grad(ctx_, B, sids.data(), theta.data(), flag_grad ? 1 : 0, nlml.data(),
-                                  flag_grad ? grad.data() : nullptr, status.data());
+    int rc = medgp_cuda_nlml_grad(ctx_, B, sids.data(), theta, flag_grad ? 1 : 0, nlml, flag_grad ? grad : nullptr, status);
     if (rc != MEDGP_OK) die("medgp_cuda_nlml_grad", ctx_, rc);
     const int nlik = D_, nA = Q_ * D_ * R_;
+    // per-request epilogue (copy out, prior terms): independent requests, read-only priors
+#pragma omp parallel for schedule(static)
     for (int b = 0; b < B; b++) {
         medgp_eval_result &r = out[b];
         r.status = status[b];
         r.ok = status[b] >= 0;
         if (!r.ok) continue;
         r.value = nlml[b];
-        if (flag_grad) r.grad.assign(grad.begin() + (size_t)b * P, grad.begin() + (size_t)(b + 1) * P);
+        if (flag_grad) r.grad.assign(grad + (size_t)b * P, grad + (size_t)(b + 1) * P);
         if (reqs[b].prior) {
             const double *th = &theta[(size_t)b * P];
             vector<double> lik(nlik), cov(P - nlik), mean;

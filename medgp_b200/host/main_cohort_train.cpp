@@ -179,7 +179,9 @@ int main(int argc, const char *argv[])
         if (reqs.empty() || (max_evals >= 0 && grad_evals >= max_evals)) break;
         vector<medgp_eval_result> res;
         batch.compute(true, reqs, res);
-        for (size_t q = 0; q < reqs.size(); q++) owner[q]->feed(res[q].ok, res[q].value, res[q].grad);
+        // every request of a super-step belongs to a different patient: the steppers advance independently
+#pragma omp parallel for schedule(dynamic, 8)
+        for (long q = 0; q < (long)reqs.size(); q++) owner[q]->feed(res[q].ok, res[q].value, res[q].grad);
         grad_evals += (long)reqs.size();
         super_steps++;
     }
@@ -201,6 +203,7 @@ int main(int argc, const char *argv[])
     }
     total_evals += grad_evals;
     cout << "Finish all jobs. " << total_evals << " evaluations, total elapsed time = " << now_s() - t0 << " seconds" << endl;
+    batch.release();
     medgp_backend::shutdown();
     return 0;
 }

@@ -367,14 +367,24 @@ struct medgp_eval_result {
 };
 class c_objective_batch {
   public:
-    c_objective_batch(medgp_ctx *ctx, int Q, int D, int R) : ctx_(ctx), Q_(Q), D_(D), R_(R) {}
+    c_objective_batch(medgp_ctx *ctx, int Q, int D, int R)
+        : ctx_(ctx), Q_(Q), D_(D), R_(R), cap_(0), h_theta_(nullptr), h_nlml_(nullptr), h_grad_(nullptr), h_status_(nullptr) {}
+    ~c_objective_batch() { release(); }
+    c_objective_batch(const c_objective_batch &) = delete;
+    c_objective_batch &operator=(const c_objective_batch &) = delete;
     // evaluates every request (NLML + prior terms, gradient when flag_grad); never throws
     void compute(const bool &flag_grad, const std::vector<medgp_eval_request> &reqs,
                  std::vector<medgp_eval_result> &out);
+    // frees the page-locked staging buffers; call before the backend context is shut down
+    void release();
 
   private:
     medgp_ctx *ctx_;
     int Q_, D_, R_;
+    // theta / results live in page-locked memory that the library copies to and from directly
+    size_t cap_;
+    double *h_theta_, *h_nlml_, *h_grad_;
+    int *h_status_;
 };
 
 // ------------------------------------------------------------------------------------------

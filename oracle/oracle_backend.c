@@ -133,3 +133,5 @@ int medgp_cuda_predict_online(medgp_ctx *c, int batch, const int *sid, const dou
     return MEDGP_OK;
 }
 int medgp_cuda_sync(medgp_ctx *c) { (void)c; return MEDGP_OK; }
+int medgp_cuda_host_alloc(medgp_ctx *c, size_t bytes, void **p) { (void)c; *p = malloc(bytes ? bytes : 1); return *p ? MEDGP_OK : MEDGP_ERR_NOMEM; }
+int medgp_cuda_host_free(medgp_ctx *c, void *p) { (void)c; free(p); return MEDGP_OK; }
