@@ -297,14 +297,20 @@ __device__ __forceinline__ void mma_panels(double (&acc)[4][4][2], const double 
 struct NoStageFn {
     __device__ __forceinline__ void operator()(int, const double *) const {}
 };
+struct NoSkipFn {
+    __device__ __forceinline__ bool operator()(int, int, int) const { return false; }
+};
 
 // TileFn: void operator()(int l, const double*& A, const double*& B) -> tile base pointers.
 // StageFn: void operator()(int ch, const double *stage): extra work of every thread on the
 // resident k-panel pair ch (A panel at stage, B panel at stage + kPanelElems, [k][row] with pitch
 // SLD) before it is handed back to the copy engine.
-template <class TileFn, class StageFn = NoStageFn>
+// SkipFn: bool operator()(int ch, int wm, int wn): true when the 32x32 quadrant (wm, wn) of this
+// warp gets nothing from k-panel ch (a zero block of a triangular operand): its DMMAs are skipped.
+template <class TileFn, class StageFn = NoStageFn, class SkipFn = NoSkipFn>
 __device__ __forceinline__ void gemm_nt_tiles(double (&acc)[4][4][2], int nl, TileFn tiles,
-                                              double *smem, GemmBars *bars, StageFn stagefn = StageFn())
+                                              double *smem, GemmBars *bars, StageFn stagefn = StageFn(),
+                                              SkipFn skipfn = SkipFn())
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wm = warp & 1, wn = warp >> 1;
@@ -340,7 +346,7 @@ __device__ __forceinline__ void gemm_nt_tiles(double (&acc)[4][4][2], int nl, Ti
         }
         mbar_wait(&bars->full[s], (ch / MEDGP_NSTAGE) & 1);
         const double *stage = smem + s * kStageElems;
-        mma_panels(acc, stage, stage + kPanelElems, MEDGP_KC / 4, wm, wn, lane);
+        if (!skipfn(ch, wm, wn)) mma_panels(acc, stage, stage + kPanelElems, MEDGP_KC / 4, wm, wn, lane);
         stagefn(ch, stage);
         // The stage is about to be handed back to the async proxy (bulk copy): order this
         // thread's generic-proxy reads before it.  Without the fence the refill was observed

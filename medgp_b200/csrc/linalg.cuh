@@ -577,7 +577,9 @@ k_trtri_row(const EvalDesc *__restrict__ descs, int i, int right_looking)
                           A = (l0 == 0) ? XTj : tile_ptr(M, T, j, l);
                           B = tile_ptr(M, T, i, l);
                       },
-                      smem, &bars);
+                      smem, &bars, NoStageFn(),
+                      // U_jj = X_jj^T is upper triangular: rows 32..63 vanish in k-panels 0 and 1
+                      [](int ch, int wm, int) { return ch < 2 && wm == 1; });
     }
     __syncthreads();
     double *sP = smem, *sX = smem + kTileElems;
@@ -694,6 +696,13 @@ k_lauum(const EvalDesc *__restrict__ descs)
                       const double *pa = stage + kh * MEDGP_SLD + m;
 #pragma unroll
                       for (int k = 0; k < MEDGP_KC / 2; k++) asum = fma(pa[k * MEDGP_SLD], __ldg(zc + k), asum);
+                  },
+                  // the first tile of the row is U_ii = X_ii^T, upper triangular: its rows 32..63 are
+                  // zero in columns 0..31, i.e. in k-panels 0 and 1 (also as the B operand when i == j)
+                  // Diagonal tiles are symmetric and only their lower part is ever read, so their
+                  // upper-right quadrant (rows 0..31, columns 32..63) is not computed at all.
+                  [&](int ch, int wm, int wn) {
+                      return (diag && wm == 0 && wn == 1) || (ch < 2 && (wm == 1 || (diag && wn == 1)));
                   });
     acc_to_global(acc, tile_ptr(M, T, i, j));
     if (diag) {
