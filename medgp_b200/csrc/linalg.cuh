@@ -414,7 +414,9 @@ k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int depth, int *__restri
                           A = tile_ptr(M, T, k, l);
                           B = A;
                       },
-                      smem, &bars);
+                      smem, &bars, NoStageFn(),
+                      // only the lower part of the symmetric product is used
+                      [](int, int wm, int wn) { return wm == 0 && wn == 1; });
         __syncthreads();  // all warps are done with the ring before it is reused as sD
         acc_to_smem(acc, sD, 1.0);
     }
@@ -468,7 +470,8 @@ k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_dia
         acc_to_smem(acc, sP, 1.0);  // (acc_matvec_rhs ended with a block barrier: GEMM2 is done with sP)
         __syncthreads();
         acc_zero(acc);
-        mma_panels(acc, sP, sP, MEDGP_NB / 4, warp & 1, warp >> 1, lane);
+        if (!((warp & 1) == 0 && (warp >> 1) == 1))  // symmetric product: the upper-right quadrant is never used
+            mma_panels(acc, sP, sP, MEDGP_NB / 4, warp & 1, warp >> 1, lane);
         if (fold_diag == 2 && i == k + 1) {
             __shared__ __align__(16) GjBufs gjb;
             __shared__ int s_fail;
@@ -545,7 +548,8 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail)
     acc_to_smem(acc, sP, 1.0);
     __syncthreads();
     acc_zero(acc);
-    mma_panels(acc, sP, sP, MEDGP_NB / 4, warp & 1, warp >> 1, lane);
+    if (!((warp & 1) == 0 && (warp >> 1) == 1))  // symmetric product: the upper-right quadrant is never used
+            mma_panels(acc, sP, sP, MEDGP_NB / 4, warp & 1, warp >> 1, lane);
     double *Kii = tile_ptr(M, T, i, i);
     acc_rsub_global(acc, Kii);
     acc_to_global(acc, Kii);
@@ -612,12 +616,15 @@ k_syrk_update(const EvalDesc *__restrict__ descs, int k)
     double acc[4][4][2];
     acc_zero(acc);
     double *M = e.M;
+    const bool diag = (i == j);
     gemm_nt_tiles(acc, 1,
                   [&](int, const double *&A, const double *&B) {
                       A = tile_ptr(M, T, i, k);
                       B = tile_ptr(M, T, j, k);
                   },
-                  smem, &bars);
+                  smem, &bars, NoStageFn(),
+                  // diagonal tiles: only the lower part of the symmetric update is used
+                  [=](int, int wm, int wn) { return diag && wm == 0 && wn == 1; });
     double *Cij = tile_ptr(M, T, i, j);
     acc_rsub_global(acc, Cij);
     acc_to_global(acc, Cij);
@@ -642,7 +649,9 @@ k_trtri_update(const EvalDesc *__restrict__ descs, int k)
                       A = (j == k) ? XTk : tile_ptr(M, T, j, k);  // U_jk (U_kk = X_kk^T)
                       B = tile_ptr(M, T, i, k);                   // L_ik
                   },
-                  smem, &bars);
+                  smem, &bars, NoStageFn(),
+                  // U_kk is upper triangular: rows 32..63 vanish in k-panels 0 and 1
+                  [=](int ch, int wm, int) { return j == k && ch < 2 && wm == 1; });
     double *Aji = tile_ptr(M, T, j, i);
     if (j != k) {  // first touch (j == k) initialises the accumulator tile
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
