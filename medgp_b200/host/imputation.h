@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -138,13 +139,22 @@ inline void refit_per_observation(medgp_ctx *ctx, const vector<double> &theta, c
 // (medgp_cuda_predict_online).  If that matrix is not positive definite, or a time stamp holds
 // too many observations, fall back to one training set per observation, which retries with
 // jitter exactly as the reference does.
+// MEDGP_NO_ONLINE=1 forces the reference's literal procedure (one fit per observation) everywhere;
+// used to validate the one-factorisation paths against it.
+inline bool online_paths_enabled()
+{
+    const char *ev = getenv("MEDGP_NO_ONLINE");
+    return !(ev && atoi(ev) != 0);
+}
+
 inline void impute_without_update(medgp_ctx *ctx, const vector<double> &theta, const vector<int> &meta_array,
                                   const vector<float> &time_array, const vector<float> &value_array,
                                   vector<HeldOut> &tasks, vector<double> &mean, vector<double> &var, vector<int> &status)
 {
     bool online = false;
     int sid = -1;
-    if (medgp_cuda_add_series_ordered(ctx, (int)time_array.size(), (const int32_t *)meta_array.data(), time_array.data(),
+    if (online_paths_enabled() &&
+        medgp_cuda_add_series_ordered(ctx, (int)time_array.size(), (const int32_t *)meta_array.data(), time_array.data(),
                                       value_array.data(), MEDGP_ORDER_TIME, &sid) == MEDGP_OK) {
         vector<double> m(time_array.size()), v(time_array.size());
         int st = -1;
@@ -174,7 +184,7 @@ inline void impute_time_stamp(medgp_ctx *ctx, const vector<double> &theta, const
                               size_t first, vector<double> &mean, vector<double> &var, vector<int> &status)
 {
     const size_t g = curr_t.size(), np = past_t.size();
-    if (g >= 2) {
+    if (g >= 2 && online_paths_enabled()) {
         vector<int> m(past_m);
         vector<float> t(past_t), v(past_v);
         m.insert(m.end(), curr_m.begin(), curr_m.end());

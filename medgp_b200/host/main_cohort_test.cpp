@@ -112,7 +112,8 @@ int main(int argc, const char *argv[])
         p->mean.assign(p->tasks.size(), 0.0);
         p->var.assign(p->tasks.size(), 0.0);
         p->status.assign(p->tasks.size(), -1);
-        if (medgp_cuda_add_series_ordered(ctx, (int)p->time.size(), (const int32_t *)p->meta.data(), p->time.data(),
+        if (!online_paths_enabled() ||
+            medgp_cuda_add_series_ordered(ctx, (int)p->time.size(), (const int32_t *)p->meta.data(), p->time.data(),
                                           p->value.data(), MEDGP_ORDER_TIME, &p->series_id) != MEDGP_OK) {
             p->series_id = -1;  // e.g. too many observations on one time stamp: refit below
             continue;

@@ -119,3 +119,33 @@ def test_cohort_test_front_end_gpu_vs_oracle_build(tmp_path):
         assert len(outs["gpu"][pan][0]) == len(x)
         assert np.abs(outs["gpu"][pan][0] - outs["orc"][pan][0]).max() <= 1e-6
         assert outs["gpu"][pan][1] == outs["orc"][pan][1]
+
+
+def test_one_factorisation_imputation_vs_per_observation_refits_on_the_gpu(tmp_path):
+    """Both front-ends on the GPU with and without MEDGP_NO_ONLINE=1: the one-factorisation paths
+    (whole patient without updates, one time stamp with updates) against the reference's literal
+    one-fit-per-observation procedure run through the same library."""
+    Q, D, R = 2, 3, 2
+    pats = {f"p{k}": synth.make_patient(D, n, seed=600 + k, T=150.0) for k, n in enumerate([70, 45])}
+    for m, x, y in pats.values():
+        x[5] = x[17]
+        x[6] = x[17]
+        x[30] = x[29]
+    theta = synth.init_hyp_lmc_sm(Q, D, R, 1, seed=12)[0]
+    outs = {}
+    for tag in ("online", "refit"):
+        top = str(tmp_path / tag)
+        cfg = expfiles.write_experiment(top, Q, D, R, [1, 3, 4], pats, online_learn_rate=1e-3)
+        expfiles.write_mode_kernel(top, Q, theta)
+        env = dict(os.environ, MEDGP_NO_ONLINE="1" if tag == "refit" else "0")
+        subprocess.run([os.path.join(HOST, "main_one_test"), "--cfg", cfg, "--pan", "p0", "--thread", "1", "--fold", "0",
+                        "--kernclust-alg", "None"], check=True, capture_output=True, timeout=900, env=env)
+        subprocess.run([os.path.join(HOST, "main_cohort_test"), "--cfg", cfg, "--pans", os.path.join(top, "data", "cohort.txt"),
+                        "--fold", "0", "--kernclust-alg", "None"], check=True, capture_output=True, timeout=900, env=env)
+        outs[tag] = {(pan, mode): expfiles.read_double_bin(os.path.join(top, "test", f"test_{mode}_pred_{pan}.bin"))
+                     for pan in pats for mode in ("mean_wo_update", "mean_w_update")
+                     if not (mode == "mean_w_update" and pan != "p0")}
+    for key, a in outs["online"].items():
+        b = outs["refit"][key]
+        assert len(a) == len(pats[key[0]][1])
+        assert np.abs(a - b).max() <= 2e-6 * max(1.0, np.abs(b).max())   # float-rounded outputs of FP64 results

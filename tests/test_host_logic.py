@@ -233,3 +233,31 @@ def test_cohort_test_front_end_writes_what_main_one_test_writes(tmp_path):
             a = expfiles.read_int_txt(os.path.join(tops["cohort"], "test", f"test_mean_wo_update_{kind}_{pan}.txt"))
             b = expfiles.read_int_txt(os.path.join(tops["single"], "test", f"test_mean_wo_update_{kind}_{pan}.txt"))
             assert a == b
+
+
+def test_per_observation_fallback_writes_the_same_files(tmp_path):
+    """MEDGP_NO_ONLINE=1 forces one fit per observation (the path taken when the one-factorisation
+    imputation does not apply); both front-ends must write the same files either way."""
+    Q, D, R = 2, 2, 1
+    pats = _patients(D, [24, 31], 61)
+    for k, (m, x, y) in enumerate(pats.values()):
+        x[1 + k] = x[8 + k]
+        x[12] = x[8 + k]
+    theta = synth.init_hyp_lmc_sm(Q, D, R, 1, seed=4)[0]
+    tops = {}
+    for tag in ("online", "refit"):
+        top = tops[tag] = str(tmp_path / tag)
+        cfg = expfiles.write_experiment(top, Q, D, R, [18, 19], pats, online_learn_rate=1e-3)
+        expfiles.write_mode_kernel(top, Q, theta)
+        env = dict(os.environ, MEDGP_NO_ONLINE="1" if tag == "refit" else "0")
+        subprocess.run([os.path.join(BUILD, "main_one_test"), "--cfg", cfg, "--pan", "p0", "--thread", "1", "--fold", "0",
+                        "--kernclust-alg", "None"], check=True, capture_output=True, env=env)
+        subprocess.run([os.path.join(BUILD, "main_cohort_test"), "--cfg", cfg, "--pans", os.path.join(top, "data", "cohort.txt"),
+                        "--fold", "0", "--kernclust-alg", "None"], check=True, capture_output=True, env=env)
+    for pan in pats:
+        for mode in ("mean_wo_update", "mean_w_update"):
+            if mode == "mean_w_update" and pan != "p0":
+                continue
+            a = expfiles.read_double_bin(os.path.join(tops["online"], "test", f"test_{mode}_pred_{pan}.bin"))
+            b = expfiles.read_double_bin(os.path.join(tops["refit"], "test", f"test_{mode}_pred_{pan}.bin"))
+            assert len(a) == len(pats[pan][1]) and np.array_equal(a, b)
