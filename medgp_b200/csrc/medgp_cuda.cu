@@ -29,7 +29,7 @@
 namespace {
 
 constexpr int kGradRows = 32;   // rows per gradient work item (= one warp, lane per row)
-constexpr int kGradCols = 96;   // target columns per gradient work item
+constexpr int kGradCols = 64;   // target columns per gradient work item
 constexpr int kMaxJitter = 10;  // inference/c_inference_exact.cpp:99
 
 struct Series {
