@@ -114,3 +114,37 @@ def test_numpy_large_n_oracle_agrees_with_c_oracle(oracle):
     f1, g1 = oracle_np.nlml_grad_np(Q, D, R, meta[perm], x[perm], y[perm], theta)
     assert abs(f1 - f0) <= 1e-11 * abs(f0)
     assert np.abs(g1 - g0).max() <= 1e-10 * np.abs(g0).max()
+
+
+def test_prefix_cholesky_leave_one_out_identity(oracle):
+    """The identity behind medgp_cuda_predict_online, checked on the CPU with the oracle's own
+    matrices: with points in time order and G = [a, b) the time-stamp group of j, the reference's
+    per-observation refit (train = earlier points + the rest of G, main_one_test.cpp:286-366) equals
+        var_j = 1 / (K_b^-1)_jj,  mean_j = y_j - (K_b^-1 y)_j / (K_b^-1)_jj,
+    where only X = inv(L_GG) of the full factor is needed:
+        (K_b^-1)_jj = sum_{i>=j} X_ij^2,  (K_b^-1 y)_j = sum_{i>=j} X_ij z_i,  z = L^-1 y."""
+    Q, D, R, n = 2, 3, 2, 48
+    meta, x, y = synth.make_patient(D, n, seed=91)
+    x = np.round(x, 0).astype(np.float32)             # shared time stamps
+    theta = synth.init_hyp_lmc_sm(Q, D, R, 1, seed=8)[0]
+    order = np.argsort(x, kind="stable")
+    meta, x, y = meta[order], x[order], y[order]
+    K = oracle.gram(Q, D, R, meta, x, theta, add_noise=True)
+    L = np.linalg.cholesky(K)
+    z = np.linalg.solve(L, y.astype(np.float64))
+    starts = [0] + [i for i in range(1, n) if x[i] != x[i - 1]] + [n]
+    checked = 0
+    for a, b in zip(starts[:-1], starts[1:]):
+        X = np.linalg.inv(L[a:b, a:b])
+        for j in range(a, b):
+            tr = [i for i in range(b) if i != j]
+            if not tr:
+                continue
+            cc = float(np.sum(X[j - a:, j - a] ** 2))
+            u = float(np.sum(X[j - a:, j - a] * z[j:b]))
+            mu, var, st = oracle.predict(Q, D, R, meta[tr], x[tr], y[tr], theta, meta[j:j + 1], x[j:j + 1])
+            assert st == 0
+            assert abs(1.0 / cc - var[0]) <= 1e-10 * var[0]
+            assert abs((float(y[j]) - u / cc) - mu[0]) <= 1e-9 * max(1.0, abs(mu[0]))
+            checked += 1
+    assert checked >= n - 1 and len(starts) - 1 < n    # at least one shared time stamp was exercised
