@@ -1150,6 +1150,10 @@ MEDGP_API int medgp_cuda_debug_matrices(medgp_ctx *ctx, int series_id, const dou
     rc = ensure_staging(ctx, 1, 0);
     if (rc) return rc;
     const Series &s = ctx->series[series_id];
+    if (s.time_order && (alpha || Kinv)) {
+        ctx->err = "debug_matrices: alpha / K^-1 need a feature-ordered series (they come from the gradient path)";
+        return MEDGP_ERR_ARG;
+    }
     const ModelDims &md = ctx->md;
     cudaStream_t st = ctx->stream;
     const size_t np = s.npad, n = s.n;
