@@ -1,17 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- cohort NLML+gradient evaluations per second (BASELINE.json metric).
 
-Workload at every N (weak scaling, per-GPU work fixed): configs[1] of BASELINE.json --
-24-feature SM-LMC (D=24, Q=5, R=8, P=1114), 256 synthetic patients of n=500 points per GPU,
-one theta per patient drawn from the reference's initialisation distribution.  One "step" is
-one NLML+gradient evaluation of every patient of the shard (256 evaluations per GPU).
+Workload: configs[2] of BASELINE.json ("C3"), the configuration the metric is worded on --
+a cohort of 4096 synthetic patients x 5 hyper-parameter vectors each (20480 evaluations per
+step), 24-feature SM-LMC (D=24, Q=5, R=8, P=1114), series lengths n ~ U{300..1500} (seeded).
+One "step" is one NLML+gradient evaluation of every (patient, theta) pair of the cohort.
+The SAME cohort is run at every N (strong scaling): patients are dealt to the N ranks by
+longest-processing-time-first on n^3 (medgp_b200/shard.py), each rank evaluates its shard on
+its own GPU, and there is no collective on the data path.
 
-  value  evaluations/s, theta resident in HBM, CUDA events on the library's stream
+  value  evaluations/s, theta resident in HBM (medgp_cuda_nlml_grad_device: no host round trip
+         inside a step), CUDA events on the library's stream, max over ranks
   e2e    evaluations/s through medgp_cuda_nlml_grad with HOST buffers (theta H2D and
          nlml/grad/status D2H inside the timed region)
+  c2     the same two numbers on configs[1] (256 patients x n=500, one theta each), rank 0
   --impl reference   the reference's own CPU implementation (oracle/_ref/ref_eval, the
          unmodified reference compiled against OpenBLAS) on the box's host cores, one
-         single-thread process per core as the reference is deployed.
+         single-thread process per core as the reference is deployed, on a size-stratified
+         sample of the same cohort.
 """
 from __future__ import annotations
 
@@ -30,38 +36,47 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from medgp_b200 import synth  # noqa: E402
+from medgp_b200 import shard, synth  # noqa: E402
 
-Q, D, R, N_POINTS, PATIENTS_PER_GPU = 5, 24, 8, 500, 256
+Q, D, R = 5, 24, 8
+N_PATIENTS, N_INITS, N_MIN, N_MAX = 4096, 5, 300, 1500
+THETA_POOL = 64          # distinct theta vectors (reference init distribution), cycled over the evaluations
+SIZE_SEED = 3
 METRIC = "cohort NLML+gradient evals/sec"
 UNIT = "evals/s"
+# size strata of the CPU sample: bin mid-points of U{300..1500} (mean n^2 0.9225e6 vs 0.93e6 of
+# the distribution; the reference's cost is ~ P_cov n^2)
+REF_STRATA = (450, 750, 1050, 1350)
+
+
+def cohort_sizes():
+    return np.random.default_rng(SIZE_SEED).integers(N_MIN, N_MAX + 1, N_PATIENTS)
+
+
+def cohort_patient(i, n):
+    """Patient i of the cohort: observation density as in C2 (n points over 240 h * n / 500)."""
+    return synth.make_patient(D, int(n), seed=100000 + i, T=240.0 * n / 500.0)
 
 
 def workload_config(n_gpus):
+    sizes = cohort_sizes()
     return {
-        "workload": "C2: 24-feature SM-LMC (feature_all.json shape), Q=5 R=8 P=1114, "
-                    f"{PATIENTS_PER_GPU} synthetic patients x n={N_POINTS} per GPU, "
-                    "1 NLML+gradient eval per patient per step",
-        "patients_per_gpu": PATIENTS_PER_GPU, "n_points": N_POINTS, "Q": Q, "D": D, "R": R,
-        "sharding": f"patients sharded over {n_gpus} GPU(s), no collective on the data path",
-        "l2": "inputs_exceed_l2 (256 x 2 MiB matrices per step vs 126 MB L2)",
+        "workload": f"C3 (BASELINE.json configs[2]): cohort of {N_PATIENTS} synthetic patients x {N_INITS} theta, "
+                    f"n ~ U{{{N_MIN}..{N_MAX}}} (seed {SIZE_SEED}; mean {sizes.mean():.0f}), 24-feature SM-LMC "
+                    f"Q=5 R=8 P=1114, {N_PATIENTS * N_INITS} NLML+gradient evals per step",
+        "patients": N_PATIENTS, "inits": N_INITS, "n_min": N_MIN, "n_max": N_MAX, "Q": Q, "D": D, "R": R,
+        "evals_per_step": N_PATIENTS * N_INITS,
+        "sharding": f"the same cohort LPT-sharded by n^3 over {n_gpus} GPU(s) (strong scaling), one process per GPU, "
+                    "no collective on the data path",
+        "l2": "inputs_exceed_l2 (the matrices of one step total >150 GB vs 126 MB L2)",
     }
 
 
-def make_shard(rank):
-    """Patients rank*256 .. rank*256+255 of the synthetic cohort and their thetas."""
-    patients = [synth.make_patient(D, N_POINTS, seed=rank * PATIENTS_PER_GPU + i)
-                for i in range(PATIENTS_PER_GPU)]
-    thetas = synth.init_hyp_lmc_sm(Q, D, R, PATIENTS_PER_GPU, seed=718 + rank)
-    return patients, thetas
-
-
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread
-    every ~2 ms (the timed region is tens of milliseconds, too short for `nvidia-smi -lms`)."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML polled from a thread)."""
 
-    def __init__(self, index):
-        self.index, self.thread, self.stop_flag = index, None, False
+    def __init__(self, index, period=0.02):
+        self.index, self.thread, self.stop_flag, self.period = index, None, False, period
         self.sm, self.reasons, self.smax, self.err = [], 0, None, None
 
     def start(self):
@@ -86,7 +101,7 @@ class ClockSampler:
             except Exception as ex:  # noqa: BLE001
                 self.err = str(ex)
                 return
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def stop(self):
         if self.thread is None:
@@ -99,13 +114,14 @@ class ClockSampler:
                  ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
                  ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)]
         reasons = sorted(nm for nm, bit in names if self.reasons & int(bit))
-        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.smax,
-                "reasons": reasons, "samples": len(self.sm)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
+                "sm_max_mhz": self.smax, "reasons": reasons, "samples": len(self.sm)}
 
 
-def measure_fp64_peak(torch, device):
+def measure_fp64_peak(torch, device, seconds=0.0):
     """cuBLAS DGEMM 8192^3 through torch.matmul: the FP64 yardstick (MEASURED_PEAKS.json has
-    no FP64 entry).  Returns TFLOP/s (best of 5)."""
+    no FP64 entry).  Returns (burst TFLOP/s: best of 5; sustained TFLOP/s: back to back for
+    `seconds`, or None)."""
     n = 8192
     a = torch.randn(n, n, dtype=torch.float64, device=device)
     b = torch.randn(n, n, dtype=torch.float64, device=device)
@@ -119,90 +135,188 @@ def measure_fp64_peak(torch, device):
         e1.record()
         torch.cuda.synchronize(device)
         best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    sustained = None
+    if seconds > 0:
+        reps = max(5, int(seconds / (2.0 * n ** 3 / (best * 1e12))))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize(device)
+        sustained = reps * 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
     del a, b
-    return best
+    return best, sustained
 
 
-def cholesky_metric(api, fp64_peak, n=4000, count=32, reps=3):
-    """BASELINE.json secondary metric, 'FP64 % of peak (Cholesky)' on a long-stay series:
+def cholesky_metric(api, fp64_peak, n=4000, counts=(1, 5, 32), reps=3):
+    """BASELINE.json secondary metric, 'FP64 % of peak (Cholesky)' on a long-stay series (C4):
     `count` initialisations of one n-point 24-feature series in flight, NLML only; potrf time
-    from per-stage CUDA events; flops = n^3/3 per matrix."""
+    from per-stage CUDA events (diagonal-block kernels included); flops = n^3/3 per matrix."""
     meta, x, y = synth.make_patient(D, n, seed=4000, T=1200.0)
-    thetas = synth.init_hyp_lmc_sm(Q, D, R, count, seed=4)
     ctx = api.Context(Q, D, R, workspace_bytes=12 << 30)
     sid = ctx.add_series(meta, x, y)
-    for _ in range(2):
-        ctx.nlml_grad([sid] * count, thetas, False)
-    ctx.stage_times(reset=True)
-    ctx.profile(True)
-    for _ in range(reps):
-        _, _, st = ctx.nlml_grad([sid] * count, thetas, False)
-    t = ctx.stage_times()
+    out = {"n": n, "peak_tflops": fp64_peak, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (burst)",
+           "in_flight": {}}
+    for count in counts:
+        thetas = synth.init_hyp_lmc_sm(Q, D, R, count, seed=4)
+        for _ in range(2):
+            ctx.nlml_grad([sid] * count, thetas, False)
+        ctx.stage_times(reset=True)
+        ctx.profile(True)
+        for _ in range(reps):
+            _, _, st = ctx.nlml_grad([sid] * count, thetas, False)
+        t = ctx.stage_times(reset=True)
+        ctx.profile(False)
+        ms = (t["potrf"]["ms"] + t["diag"]["ms"]) / reps
+        tf = count * n ** 3 / 3.0 / (ms * 1e-3) / 1e12
+        out["in_flight"][str(count)] = {"potrf_ms": ms, "tflops": tf, "frac": tf / fp64_peak, "ok": bool((st == 0).all())}
     ctx.close()
-    ms = t["potrf"]["ms"] / reps
-    tf = count * n ** 3 / 3.0 / (ms * 1e-3) / 1e12
-    return {"n": n, "matrices_in_flight": count, "potrf_ms": ms, "tflops": tf, "peak_tflops": fp64_peak,
-            "frac": tf / fp64_peak, "ok": bool((st == 0).all()),
-            "peak_source": "cuBLAS DGEMM 8192^3 measured in this run"}
+    top = out["in_flight"][str(counts[-1])]
+    out.update({"matrices_in_flight": counts[-1], "potrf_ms": top["potrf_ms"], "tflops": top["tflops"],
+                "frac": top["frac"], "ok": all(v["ok"] for v in out["in_flight"].values())})
+    return out
 
 
-def reference_sample(n_evals, want_grad=True):
-    """Times `n_evals` evaluations of the workload with the compiled reference, one
-    single-thread process per evaluation, all concurrently.  Returns (evals/s, cores, text)."""
+# ------------------------------------------------------------------------------ reference arm
+def reference_sample(sizes, want_grad=True):
+    """One NLML+gradient evaluation per entry of `sizes` with the compiled reference, one
+    single-thread process per evaluation, all started together.  Returns (per-process seconds,
+    wall seconds) or None when the reference is not built."""
     from oracle import oracle
     if not oracle.have_ref():
-        return None, 0, "oracle/_ref/ref_eval missing"
-    patients, thetas = make_shard(0)
+        return None
+    thetas = synth.init_hyp_lmc_sm(Q, D, R, 4, seed=718)
     tmp = tempfile.mkdtemp(prefix="medgp_ref_")
     paths = []
-    for i in range(n_evals):
-        meta, x, y = patients[i % PATIENTS_PER_GPU]
+    for i, n in enumerate(sizes):
+        meta, x, y = cohort_patient(i, n)
         p = os.path.join(tmp, f"case{i}.txt")
-        oracle.write_case(p, Q, D, R, meta, x, y, thetas[i % PATIENTS_PER_GPU])
+        oracle.write_case(p, Q, D, R, meta, x, y, thetas[i % 4])
         paths.append(p)
     t0 = time.perf_counter()
     procs = [subprocess.Popen([oracle.REF_EVAL, p, "1" if want_grad else "0", "1", "1"],
                               stdout=subprocess.DEVNULL, env=oracle.ref_env()) for p in paths]
-    for pr in procs:
-        pr.wait()
-    dt = time.perf_counter() - t0
+    done = [None] * len(procs)
+    while any(d is None for d in done):
+        for k, pr in enumerate(procs):
+            if done[k] is None and pr.poll() is not None:
+                done[k] = time.perf_counter() - t0
+        time.sleep(0.01)
+    wall = time.perf_counter() - t0
     for p in paths:
         os.unlink(p)
     os.rmdir(tmp)
-    return n_evals / dt, n_evals, (f"{n_evals} concurrent single-thread ref_eval processes, one "
-                                  f"NLML+grad eval each (n={N_POINTS}, D={D}, Q={Q}, R={R}), "
-                                  f"{dt:.1f} s wall")
+    return done, wall
+
+
+REF_NOTE = ("reference built with g++ -O2 + OpenBLAS (not icpc/MKL); one single-thread process per host core, as "
+            "the reference is deployed (scripts/slurm_della.json)")
 
 
 def run_reference(args):
+    """Every step: `cores` concurrent single-thread evaluations, all of ONE size, the size cycling
+    through the four strata of the cohort's size distribution (a multiple of 4 steps weighs them
+    equally).  value = evaluations / wall time over the K timed steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    for _ in range(args.warmup):
-        reference_sample(cores)
-    t0 = time.perf_counter()
-    total = 0
-    sample = ""
-    for _ in range(args.steps):
-        v, used, sample = reference_sample(cores)
-        if v is None:
-            print(json.dumps({"impl": "reference", "unavailable": sample}))
+    for _ in range(args.warmup):  # untimed; the cheapest stratum
+        if reference_sample([REF_STRATA[0]] * cores) is None:
+            break
+    total, wall_total, per_size = 0, 0.0, {}
+    for k in range(args.steps):
+        n = REF_STRATA[k % len(REF_STRATA)]
+        r = reference_sample([n] * cores)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_eval missing"}))
             return 0
-        total += used
-    dt = time.perf_counter() - t0
-    value = total / dt
+        total += cores
+        wall_total += r[1]
+        per_size.setdefault(n, []).append(r[1])
+    value = total / wall_total
+    sample = (f"{args.steps} steps x {cores} concurrent single-thread ref_eval processes, one NLML+grad eval each "
+              f"(D={D}, Q={Q}, R={R}), step k at n = {list(REF_STRATA)}[k % 4] (size strata of the C3 cohort, "
+              f"seconds per step: { {n: round(float(np.mean(v)), 2) for n, v in per_size.items()} }); {REF_NOTE}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": wall_total / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": sample + "; reference built with g++ -O2 + OpenBLAS (not icpc/MKL)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
     return 0
+
+
+def cpu_baseline_sample():
+    """Bounded sample for the `cpu_baseline` key of our own line: cores/4 evaluations of each
+    size stratum at once; throughput of the box = cores / mean single-thread evaluation time
+    (every core kept busy by a queue of evaluations)."""
+    cores = os.cpu_count() or 1
+    per = max(1, cores // len(REF_STRATA))
+    sizes = [n for n in REF_STRATA for _ in range(per)]
+    r = reference_sample(sizes)
+    if r is None:
+        return None
+    secs, wall = r
+    value = min(cores, len(sizes)) / float(np.mean(secs))
+    return {"value": value, "unit": UNIT, "cores": min(cores, len(sizes)), "kind": "reference",
+            "sample": f"{len(sizes)} concurrent single-thread ref_eval processes, {per} at each of n = {list(REF_STRATA)} "
+                      f"(size strata of the C3 cohort), one NLML+grad eval each, {wall:.1f} s wall; value = cores / mean "
+                      f"evaluation time ({float(np.mean(secs)):.1f} s); {REF_NOTE}"}
+
+
+# ------------------------------------------------------------------------------------ our arm
+def time_device_steps(torch, ctx, stream, step, steps, barrier):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    ctx.sync()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def run_c2(torch, api, dev, local, steps):
+    """configs[1]: 256 patients x n=500, one theta each (last round's headline), this rank only."""
+    n_pat, n = 256, 500
+    patients = [synth.make_patient(D, n, seed=i) for i in range(n_pat)]
+    thetas = synth.init_hyp_lmc_sm(Q, D, R, n_pat, seed=718)
+    ctx = api.Context(Q, D, R, device=local, workspace_bytes=8 << 30)
+    sids = np.array([ctx.add_series(*p) for p in patients], dtype=np.int32)
+    P, B = ctx.P, n_pat
+    d_theta, d_nlml, d_grad, d_status = ctx.malloc(B * P * 8), ctx.malloc(B * 8), ctx.malloc(B * P * 8), ctx.malloc(B * 4)
+    ctx.h2d(d_theta, thetas)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+
+    def step():
+        ctx.nlml_grad_device(sids, d_theta, True, d_nlml, d_grad, d_status)
+
+    for _ in range(5):
+        step()
+    ctx.sync()
+    ms = time_device_steps(torch, ctx, stream, step, steps, lambda: None)
+    theta_pin = ctx.pinned(thetas.shape)
+    theta_pin[...] = thetas
+    outs = (ctx.pinned((B,)), ctx.pinned((B, P)), ctx.pinned((B,), np.int32))
+    for _ in range(3):
+        ctx.nlml_grad(sids, theta_pin, True, out=outs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, _, st = ctx.nlml_grad(sids, theta_pin, True, out=outs)
+    t_e2e = time.perf_counter() - t0
+    ok = bool((st == 0).all())
+    for p in (d_theta, d_nlml, d_grad, d_status):
+        ctx.free(p)
+    ctx.close()
+    return {"workload": "C2 (BASELINE.json configs[1]): 256 patients x n=500, 1 theta each, one GPU",
+            "steps": steps, "value": B * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+            "e2e": B * steps / t_e2e, "unit": UNIT, "ok": ok}
 
 
 def run_ours(args):
@@ -224,10 +338,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    patients, thetas = make_shard(rank)
-    ctx = api.Context(Q, D, R, device=local, workspace_bytes=8 << 30)
-    sids = np.array([ctx.add_series(*p) for p in patients], dtype=np.int32)
+    # ---- this rank's shard of the cohort (LPT on n^3; every rank computes the same assignment)
+    sizes = cohort_sizes()
+    owner = shard.lpt_assign(sizes, world)
+    mine = np.nonzero(owner == rank)[0]
+    pool = synth.init_hyp_lmc_sm(Q, D, R, THETA_POOL, seed=718)
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    ctx = api.Context(Q, D, R, device=local, workspace_bytes=int(0.80 * free_b))
+    sid_of = [ctx.add_series(*cohort_patient(int(i), int(sizes[i]))) for i in mine]
+    sids = np.repeat(np.array(sid_of, dtype=np.int32), N_INITS)
+    theta_idx = (np.repeat(mine, N_INITS) * N_INITS + np.tile(np.arange(N_INITS), len(mine))) % THETA_POOL
+    thetas = pool[theta_idx]
     P, B = ctx.P, len(sids)
+    shard_flops = float(np.sum(sizes[mine].astype(np.float64) ** 3)) * N_INITS
     d_theta, d_nlml = ctx.malloc(B * P * 8), ctx.malloc(B * 8)
     d_grad, d_status = ctx.malloc(B * P * 8), ctx.malloc(B * 4)
     ctx.h2d(d_theta, thetas)
@@ -239,44 +362,39 @@ def run_ours(args):
     for _ in range(args.warmup):
         step_device()
     ctx.sync()
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    e1.record(stream)
-    ctx.sync()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
-    # ---- the same K steps again with per-stage CUDA events (single stream, stages serialised):
-    #      source of the roofline numbers and of the launch count
     ctx.stage_times(reset=True)
-    ctx.profile(True)
-    ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ep0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    ep1.record(stream)
-    ctx.sync()
-    ms_profiled = ep0.elapsed_time(ep1)
-    stages = ctx.stage_times(reset=True)
-    ctx.profile(False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = time_device_steps(torch, ctx, stream, step_device, args.steps, barrier)
+    clocks = sampler.stop()
+    launches_timed = ctx.stage_times(reset=True)
     status = np.empty(B, dtype=np.int32)
     ctx.d2h(status, d_status)
     nlml_dev = np.empty(B)
     ctx.d2h(nlml_dev, d_nlml)
     assert (status == 0).all() and np.isfinite(nlml_dev).all(), "device path produced failures"
 
+    # ---- a few of the same steps again with per-stage CUDA events (one stream, stages
+    #      serialised): source of the roofline numbers
+    prof_steps = min(args.steps, 3)
+    ctx.profile(True)
+    ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ep0.record(stream)
+    for _ in range(prof_steps):
+        step_device()
+    ep1.record(stream)
+    ctx.sync()
+    ms_profiled = ep0.elapsed_time(ep1)
+    stages = ctx.stage_times(reset=True)
+    ctx.profile(False)
+
     # ---- e2e: host buffers through the public C ABI call, copies inside the timed region
-    # (theta and the result arrays live in page-locked host memory, as an optimiser loop
-    # that calls the backend every iteration would keep them)
+    # (theta and the result arrays live in page-locked host memory, as an optimiser loop that
+    # calls the backend every iteration keeps them)
     theta_pin = ctx.pinned(thetas.shape)
     theta_pin[...] = thetas
     outs = (ctx.pinned((B,)), ctx.pinned((B, P)), ctx.pinned((B,), np.int32))
-    for _ in range(3):
+    for _ in range(2):
         ctx.nlml_grad(sids, theta_pin, True, out=outs)
     barrier()
     t0 = time.perf_counter()
@@ -284,20 +402,30 @@ def run_ours(args):
         nlml_h, grad_h, st_h = ctx.nlml_grad(sids, theta_pin, True, out=outs)
     t_e2e = time.perf_counter() - t0
     barrier()
-    assert np.allclose(nlml_h, nlml_dev, rtol=1e-12, atol=0)
+    assert np.allclose(nlml_h, nlml_dev, rtol=1e-12, atol=0) and (st_h == 0).all()
+
+    for p in (d_theta, d_nlml, d_grad, d_status):
+        ctx.free(p)
+    del theta_pin, outs, nlml_h, grad_h, st_h
+    ctx.close()
 
     t = torch.tensor([ms, t_e2e * 1e3], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(B), shard_flops, float(sum(launches_timed[k]["launches"] for k in launches_timed if k != "evals"))],
+                       dtype=torch.float64, device=dev)
+    per_rank = torch.zeros(world, 2, dtype=torch.float64, device=dev)
+    per_rank[rank, 0], per_rank[rank, 1] = ms, shard_flops
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
     ms_max, e2e_ms_max = float(t[0]), float(t[1])
-    total_evals = world * B * args.steps
-    value = total_evals / (ms_max * 1e-3)
-    e2e_value = total_evals / (e2e_ms_max * 1e-3)
+    evals_per_step = int(round(float(tot[0])))
+    assert evals_per_step == N_PATIENTS * N_INITS
+    value = evals_per_step * args.steps / (ms_max * 1e-3)
+    e2e_value = evals_per_step * args.steps / (e2e_ms_max * 1e-3)
 
     if rank == 0:
-        # ---- roofline of the dominant kernel (by device time in the profiled pass)
         names = [k for k in stages if k != "evals"]
-        dom = max(names, key=lambda k: stages[k]["ms"])
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -305,70 +433,86 @@ def run_ours(args):
             pass
         hbm = peaks.get("hbm_gbs", 6650.0)
         hbm_src = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        fp64_peak = measure_fp64_peak(torch, dev)
-        kernel_of = {"potrf": "k_potrf_panel + k_potrf_diag", "diag": "k_potrf_diag", "trtri": "k_trtri_row", "lauum": "k_lauum",
-                     "grad": "k_grad (+k_grad_finish)", "assemble": "k_assemble", "prep": "k_prep",
+        fp64_burst, fp64_sustained = measure_fp64_peak(torch, dev, seconds=3.0)
+        # the kernel is timed inside a step that lasts seconds: the sustained figure is the peak
+        fp64_peak = fp64_sustained or fp64_burst
+        kernel_of = {"potrf": "k_potrf_panel + k_potrf_diag (+k_potrf_step / k_syrk_update)", "trtri": "k_trtri_row",
+                     "lauum": "k_lauum", "grad": "k_grad (+k_grad_finish)", "assemble": "k_assemble", "prep": "k_prep",
                      "solve": "k_solve", "predict": "k_cross/k_pred_finish"}
         traffic = {}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         except OSError:
             pass
+        # the factorisation is ONE stage: its diagonal-block and panel kernels alternate
+        merged = {k: dict(stages[k]) for k in names if k != "diag"}
+        for f in ("ms", "launches"):
+            merged["potrf"][f] += stages["diag"][f]
 
         def stage_roofline(name):
-            st = dict(stages[name])
-            if name == "potrf":  # the diagonal-block kernel belongs to the factorisation
-                st["ms"] += stages["diag"]["ms"]
-                st["launches"] += stages["diag"]["launches"]
+            st = merged[name]
             launches = max(1, st["launches"])
             avg_s = max(st["ms"], 1e-9) * 1e-3 / launches
-            if name in ("potrf", "diag", "trtri", "lauum", "solve"):
+            if name in ("potrf", "trtri", "lauum", "solve"):
                 a = st["flops"] / launches / avg_s / 1e12
                 return {"kernel": kernel_of[name], "bound": "tensor", "achieved": a, "peak": fp64_peak,
-                        "unit": "TFLOP/s", "frac": a / fp64_peak}
+                        "unit": "TFLOP/s", "frac": a / fp64_peak, "launches_per_step": launches / prof_steps}
             a = st["bytes"] / launches / avg_s / 1e9
             return {"kernel": kernel_of[name], "bound": "hbm", "achieved": a, "peak": hbm, "unit": "GB/s",
-                    "frac": a / hbm}
+                    "frac": a / hbm, "launches_per_step": launches / prof_steps}
 
+        dom = max(merged, key=lambda k: merged[k]["ms"])
         roofline = stage_roofline(dom)
-        roofline["traffic"] = traffic.get(dom)
-        roofline["peak_source"] = ("FP64 tensor (DMMA): cuBLAS DGEMM 8192^3 measured in this run; "
-                                   "MEASURED_PEAKS.json has no FP64 entry" if roofline["bound"] == "tensor" else hbm_src)
-        roofline["algorithmic_work"] = ("SURVEY.md section 8d: potrf n^3/3 flop (panel + diagonal kernels together), trtri/lauum n^3/3 "
-                                        "flop each, assembly 8n(n+1)/2+12n B, gradient 8n(n+1)/2+8P B per evaluation, n=500")
-        if dom == "grad":
-            roofline["fp64_pipe_active_pct_ncu"] = traffic.get("grad_fp64_pipe_pct")
-        roofline["measured_in"] = ("second pass of the same K steps with per-stage CUDA events on one "
-                                   f"stream ({ms_profiled / args.steps:.3f} ms/step serialised vs "
-                                   f"{ms_max / args.steps:.3f} ms/step in the timed multi-stream region)")
-        roofline["stage_ms_per_step"] = {k: stages[k]["ms"] / args.steps for k in names}
-        roofline["stage_launches_per_step"] = {k: stages[k]["launches"] / args.steps for k in names}
-        roofline["all_stages"] = {k: stage_roofline(k) for k in names if stages[k]["ms"] > 0 and k not in ("prep", "solve", "diag")}
+        tr = traffic.get(dom)
+        roofline["traffic"] = tr.get("bytes_per_launch") if isinstance(tr, dict) else tr
+        roofline["traffic_source"] = (traffic.get("source", "profiles/traffic.json") + " (imported from a committed ncu "
+                                      "capture, not measured in this run)") if tr is not None else None
+        roofline["peak_source"] = ((f"FP64 tensor (DMMA): cuBLAS DGEMM 8192^3 measured in this run, "
+                                    f"{'sustained over 3 s' if fp64_sustained else 'burst (best of 5)'} "
+                                    f"(burst {fp64_burst:.1f}, sustained {fp64_sustained if fp64_sustained else float('nan'):.1f} TFLOP/s); "
+                                    "MEASURED_PEAKS.json has no FP64 entry") if roofline["bound"] == "tensor" else hbm_src)
+        roofline["algorithmic_work"] = ("SURVEY.md section 8d per evaluation: potrf n^3/3 flop (panel + diagonal kernels together), "
+                                        "trtri and lauum n^3/3 flop each, assembly 8n(n+1)/2+12n B, gradient 8n(n+1)/2+8P B, summed "
+                                        "over the evaluations a launch processes")
+        roofline["measured_in"] = (f"{prof_steps} of the same steps again with per-stage CUDA events on one stream "
+                                   f"({ms_profiled / prof_steps:.1f} ms/step serialised vs {ms / args.steps:.1f} ms/step in the "
+                                   "timed multi-stream region), rank 0's shard")
+        roofline["stage_ms_per_step"] = {k: merged[k]["ms"] / prof_steps for k in merged}
+        roofline["all_stages"] = {k: stage_roofline(k) for k in merged if merged[k]["ms"] > 0 and k not in ("prep", "solve")}
+        la_flop = float(tot[1])  # potrf + trtri + lauum = n^3 per evaluation
+        roofline["whole_step_linear_algebra"] = {
+            "tflops": la_flop * args.steps / (ms_max * 1e-3) / 1e12 / world, "peak": fp64_peak,
+            "frac": la_flop * args.steps / (ms_max * 1e-3) / 1e12 / world / fp64_peak,
+            "note": "sum n^3 of the cohort / step time / GPUs: the tensor-core work against the DGEMM yardstick with the "
+                    "FP64-pipe-bound assembly and gradient kernels inside the same time"}
         roofline["note"] = ("assembly and gradient kernels are FP64-pipe bound at Q=5 (about 19 FMA per byte against a "
                             "2.6 FMA/B machine balance), so their HBM fraction is low by construction; DESIGN.md section 4")
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            v, used, sample = reference_sample(os.cpu_count() or 1)
-            if v is not None:
-                cpu = {"value": v, "unit": UNIT, "cores": used, "kind": "reference",
-                       "sample": sample + "; reference built with g++ -O2 + OpenBLAS (not icpc/MKL)"}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * B * P * 8),
-                    "d2h_bytes_per_step": int(world * (B * (P + 1) * 8 + B * 4))},
-            "gpu_launches": int(sum(stages[k]["launches"] for k in names)),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(evals_per_step * P * 8),
+                    "d2h_bytes_per_step": int(evals_per_step * ((P + 1) * 8 + 4))},
+            "gpu_launches": int(round(float(tot[2]))),
+            "roofline": roofline,
         }
-        if world == 1 and not args.no_cholesky:
-            out["cholesky_fp64"] = cholesky_metric(api, fp64_peak)
+        if world > 1:
+            pr = per_rank.cpu().numpy()
+            out["balance"] = {"ms_per_step_by_rank": [float(v) / args.steps for v in pr[:, 0]],
+                              "n3_share_by_rank": [float(v) / la_flop for v in pr[:, 1]],
+                              "limiter": "max over ranks of the shard's step time; LPT residual on n^3 plus the n^2 "
+                                         "(assembly, gradient) work that LPT does not weigh"}
+        if world == 1:
+            if not args.no_c2:
+                out["c2"] = run_c2(torch, api, dev, local, 20)
+            if not args.no_cholesky:
+                out["cholesky_fp64"] = cholesky_metric(api, fp64_burst)
+            if not args.no_cpu_baseline:
+                out["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(out))
-    for p in (d_theta, d_nlml, d_grad, d_status):
-        ctx.free(p)
-    ctx.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -376,11 +520,12 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cholesky", action="store_true")
+    ap.add_argument("--no-c2", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

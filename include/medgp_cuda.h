@@ -101,8 +101,11 @@ int medgp_cuda_nlml_grad(medgp_ctx *ctx, int batch, const int *series_id, const 
 
 /* Same work with theta already resident in HBM and results left there (d_theta: batch*P,
  * d_nlml: batch, d_grad: batch*P or NULL, d_status: batch ints); asynchronous on the
- * context's stream -- call medgp_cuda_sync before reading.  Evaluations that fail the
- * Cholesky are NOT retried with jitter on this path (status -1). */
+ * context's stream, with no host synchronisation inside the call -- call medgp_cuda_sync
+ * before reading.  Jitter retries (inference/c_inference_exact.cpp:99-108) run on the device:
+ * the launch sequence of a chunk is the body of a CUDA-graph WHILE node that re-runs the failed
+ * evaluations with one more noise addition until none is left, so status is final (0, k, or -1
+ * after 10 additions) exactly as on the host path. */
 int medgp_cuda_nlml_grad_device(medgp_ctx *ctx, int batch, const int *series_id,
                                 const double *d_theta, int want_grad, double *d_nlml,
                                 double *d_grad, int *d_status);
@@ -136,6 +139,13 @@ int medgp_cuda_predict_online(medgp_ctx *ctx, int batch, const int *series_id, c
  * All in the caller's original point order. */
 int medgp_cuda_debug_matrices(medgp_ctx *ctx, int series_id, const double *theta,
                               double *K, double *L, double *alpha, double *Kinv);
+
+/* Tests of the jitter path: declare the first `attempts` factorisation attempts of every
+ * evaluation failed, whatever their pivots (0 = off).  An evaluation then comes back with
+ * status == attempts and the values of K + (1 + attempts) sigma^2 -- what the reference computes
+ * when spotrf fails that many times.  MEDGP_FORCE_FAIL=<attempts> sets it at context creation
+ * (for the executables). */
+int medgp_cuda_debug_force_fail(medgp_ctx *ctx, int attempts);
 
 /* Per-stage device timings and algorithmic work counters since the last reset. */
 int medgp_cuda_profile(medgp_ctx *ctx, int enable);  /* enabling adds event records */

@@ -24,7 +24,7 @@ SYMBOLS = [
     "medgp_cuda_create", "medgp_cuda_destroy", "medgp_cuda_last_error", "medgp_cuda_model",
     "medgp_cuda_num_hyp", "medgp_cuda_add_series", "medgp_cuda_add_series_ordered", "medgp_cuda_free_series",
     "medgp_cuda_clear_series", "medgp_cuda_nlml_grad", "medgp_cuda_nlml_grad_device",
-    "medgp_cuda_sync", "medgp_cuda_predict", "medgp_cuda_predict_online", "medgp_cuda_debug_matrices", "medgp_cuda_profile",
+    "medgp_cuda_sync", "medgp_cuda_predict", "medgp_cuda_predict_online", "medgp_cuda_debug_matrices", "medgp_cuda_debug_force_fail", "medgp_cuda_profile",
     "medgp_cuda_stage_times", "medgp_cuda_malloc", "medgp_cuda_free", "medgp_cuda_memcpy_h2d",
     "medgp_cuda_memcpy_d2h", "medgp_cuda_host_alloc", "medgp_cuda_host_free", "medgp_cuda_stream",
 ]
@@ -75,6 +75,7 @@ def load_library():
     lib.medgp_cuda_sync.argtypes = [vp]
     lib.medgp_cuda_predict.argtypes = [vp, i, ip, dp, ip, ip, fp, dp, dp, ip]
     lib.medgp_cuda_debug_matrices.argtypes = [vp, i, dp, dp, dp, dp, dp]
+    lib.medgp_cuda_debug_force_fail.argtypes = [vp, i]
     lib.medgp_cuda_profile.argtypes = [vp, i]
     lib.medgp_cuda_stage_times.argtypes = [vp, ctypes.POINTER(StageTimes), i]
     lib.medgp_cuda_malloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp)]
@@ -253,6 +254,10 @@ class Context:
             if v is not None:
                 out[k] = v
         return out
+
+    def force_fail(self, attempts):
+        """Tests of the jitter path: the first `attempts` factorisation attempts count as failed."""
+        self._check(self.lib.medgp_cuda_debug_force_fail(self.h, int(attempts)))
 
     def profile(self, enable=True):
         self._check(self.lib.medgp_cuda_profile(self.h, int(enable)))

@@ -45,7 +45,7 @@ struct __align__(16) EvalDesc {
     int n, npad, T, nitems;
     int jitter, nrhs, nstar, out_index;
     int star_out;            // offset of this evaluation's predictions in the output arrays
-    int pad0;
+    int skip;                // device-side jitter loop (k_retry_decide): 1 = this evaluation is final, every kernel passes over it
     double trange2;          // (max t - min t)^2 of the series: bounds every tau^2 of the training block
     const int *gstart;       // time-ordered series: first point of every same-timestamp group (ngroups + 1)
     const int *perm;         // internal position -> caller's point index

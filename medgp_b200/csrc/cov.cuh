@@ -16,9 +16,14 @@
 // (likelihoods/c_likelihood.cpp:38-43, kernel/c_kernel_LMC_SM.cpp:51-62,72-115), then the
 // per-point (cos, sin)(w_q t_i) tables.
 __global__ void __launch_bounds__(256)
-k_prep(const EvalDesc *__restrict__ descs, ModelDims md, const double *__restrict__ thetas)
+k_prep(const EvalDesc *__restrict__ descs, ModelDims md, const double *__restrict__ thetas,
+       int *__restrict__ tickets, int ntickets)
 {
+    // the role counters of this sub-chunk's k_potrf_step launches (one per block column)
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < ntickets; i += blockDim.x) tickets[i] = 0;
     const EvalDesc &e = descs[blockIdx.x];
+    if (e.skip) return;
     const int Q = md.Q, D = md.D, R = md.R, tid = threadIdx.x;
     const double *th = thetas + (size_t)e.out_index * md.P;
     const double *cov = th + D;
@@ -77,7 +82,7 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
     const EvalDesc &e = descs[blockIdx.y];
     int ti, tj;
     tri_index(blockIdx.x, ti, tj);
-    if (ti >= e.T) return;
+    if (ti >= e.T || e.skip) return;
     exp_tab_stage(s_tab);
     const int Q = md.Q, D = md.D, tid = threadIdx.x, n = e.n, ld = e.npad;
     double *sB = sm, *sC = sm + Q * D * D;
@@ -370,7 +375,7 @@ k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
     const EvalDesc &e = descs[blockIdx.y];
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const int item = blockIdx.x * MEDGP_GW + wp;
-    if (item >= e.nitems) return;
+    if (item >= e.nitems || e.skip) return;
     const int4 it = e.items[item];  // (row block, first column, column end, first segment id)
     GradStage<QT> *stage = reinterpret_cast<GradStage<QT> *>(dsm) + 2 * wp;
     double cmax = 0.0;
@@ -397,6 +402,7 @@ k_grad_finish(const EvalDesc *__restrict__ descs, ModelDims md, double *__restri
 {
     extern __shared__ __align__(16) double sm[];
     const EvalDesc &e = descs[blockIdx.x];
+    if (e.skip) return;
     const int Q = md.Q, D = md.D, R = md.R, tid = threadIdx.x;
     const int npairs = D * (D + 1) / 2, W = 3 * Q + 1;
     double *S = sm, *gm = S + Q * D * D, *gv = gm + npairs * Q, *dg = gv + npairs * Q;
@@ -458,7 +464,7 @@ k_cross(const EvalDesc *__restrict__ descs, ModelDims md)
 {
     const EvalDesc &e = descs[blockIdx.y];
     const int s = blockIdx.x;
-    if (s >= e.nstar) return;
+    if (s >= e.nstar || e.skip) return;
     const int Q = md.Q, D = md.D, ld = e.npad;
     const double ts = e.star_t[s];
     const int ms = e.star_meta[s];
@@ -491,7 +497,7 @@ k_pred_finish(const EvalDesc *__restrict__ descs, ModelDims md, double *__restri
     __shared__ double scratch[64];
     const EvalDesc &e = descs[blockIdx.y];
     const int s = blockIdx.x;
-    if (s >= e.nstar) return;
+    if (s >= e.nstar || e.skip) return;
     const int ld = e.npad;
     const double *z = e.rhs, *v = e.rhs + (size_t)(1 + s) * ld;
     double acc[2] = {0.0, 0.0};
@@ -530,7 +536,7 @@ k_online(const EvalDesc *__restrict__ descs, double *__restrict__ out_mean, doub
 {
     __shared__ double sx[MEDGP_GMAX * MEDGP_GMAX];  // sx[i * 32 + lane]: X_ij for this lane's column
     const EvalDesc &e = descs[blockIdx.y];
-    if ((int)blockIdx.x >= e.ngroups) return;
+    if ((int)blockIdx.x >= e.ngroups || e.skip) return;
     const int a = e.gstart[blockIdx.x], g = e.gstart[blockIdx.x + 1] - a, lane = threadIdx.x;
     if (lane >= g) return;
     const int T = e.T, j = a + lane;

@@ -399,7 +399,7 @@ k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int depth, int *__restri
     __shared__ __align__(16) GjBufs gjb;
     __shared__ int s_fail;
     const EvalDesc &e = descs[blockIdx.x];
-    if (k >= e.T) return;
+    if (k >= e.T || e.skip) return;
     const int T = e.T, tid = threadIdx.x;
     if (depth > 0) prefetch_tile_l2(tile_ptr(e.M, T, k, k));  // wanted right after the products
     gemm_bars_init(&bars);
@@ -433,7 +433,7 @@ k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_dia
     __shared__ GemmBars bars;
     const EvalDesc &e = descs[blockIdx.y];
     const int i = k + 1 + blockIdx.x;
-    if (i >= e.T) return;
+    if (i >= e.T || e.skip) return;
     const int T = e.T;
     double *M = e.M;
     double *Tik = tile_ptr(M, T, i, k);
@@ -489,25 +489,36 @@ k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_dia
 }
 
 // ------------------------------------------------------------------ potrf: one left-looking step
-// grid (evaluations, 1 + rows below).  CTA y == 0 factors diagonal block k (already complete:
-// every earlier panel CTA folded its tile into it) while the CTAs y >= 1 run the k-tile
-// products of their panel tiles; they then wait on flags[k] (set by the diagonal CTA of the same
-// evaluation, which was dispatched before them), finish L_ik = P X_kk^T, push it into the
-// right-hand sides and fold it into their own diagonal block.  One launch per block column,
-// with the latency-bound diagonal factorisation hidden behind the tensor-core work.
+// One launch per block column for chunks of few matrices.  A CTA's ROLE is not its block index
+// but a ticket drawn from a per-launch counter when it starts running: tickets 0 .. ndiag-1
+// factor diagonal block k of evaluation `ticket` (already complete: every earlier panel CTA
+// folded its tile into it); later tickets are panel tiles (evaluation, row), which run their
+// k-tile products, then wait on flags[k] of their evaluation, finish L_ik = P X_kk^T, push it
+// into the right-hand sides and fold it into their own diagonal block.  Because a ticket is only
+// ever held by a CTA that is already executing, every flag a panel CTA can wait for belongs to a
+// diagonal role that is running or finished -- forward progress does not depend on the order in
+// which the hardware dispatches blocks, whatever the grid size.  The latency-bound diagonal
+// factorisation hides behind the tensor-core work of the panel roles.
+// *ticket must be 0 at launch (k_prep zeroes the sub-chunk's counters).
 __global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
-k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail)
+k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, int *__restrict__ ticket)
 {
     extern __shared__ __align__(128) double smem[];
     __shared__ GemmBars bars;
     __shared__ __align__(16) GjBufs gjb;
     __shared__ double red[2 * MEDGP_NB];
-    __shared__ int s_fail;
-    const EvalDesc &e = descs[blockIdx.x];  // x = evaluation: ALL diagonal CTAs (y == 0) are dispatched first
+    __shared__ int s_fail, s_role;
+    if (threadIdx.x == 0) s_role = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int ndiag = gridDim.x, role = s_role;
+    const int ev = role < ndiag ? role : (role - ndiag) % ndiag;
+    const int row = role < ndiag ? 0 : 1 + (role - ndiag) / ndiag;
+    const EvalDesc &e = descs[ev];
+    if (e.skip) return;
     const int T = e.T;
     double *M = e.M;
     double *sP = smem, *sX = smem + kTileElems;
-    if (blockIdx.y == 0) {
+    if (row == 0) {
         if (k >= T) return;
         if (threadIdx.x == 0) s_fail = 0;
         __syncthreads();
@@ -517,7 +528,7 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail)
         if (threadIdx.x == 0) flag_release(e.flags + k);
         return;
     }
-    const int i = k + blockIdx.y;
+    const int i = k + row;
     if (i >= T) return;
     double *Tik = tile_ptr(M, T, i, k);
     const double *Xk = e.dinv + (size_t)k * kTileElems;
@@ -549,10 +560,40 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail)
     __syncthreads();
     acc_zero(acc);
     if (!((warp & 1) == 0 && (warp >> 1) == 1))  // symmetric product: the upper-right quadrant is never used
-            mma_panels(acc, sP, sP, MEDGP_NB / 4, warp & 1, warp >> 1, lane);
+        mma_panels(acc, sP, sP, MEDGP_NB / 4, warp & 1, warp >> 1, lane);
     double *Kii = tile_ptr(M, T, i, i);
     acc_rsub_global(acc, Kii);
     acc_to_global(acc, Kii);
+}
+
+// ------------------------------------------------------------------ device-side jitter loop
+// Last node of a chunk's launch sequence, which is the body of a CUDA-graph WHILE node.  For
+// every evaluation of the chunk: a failed factorisation with jitter left gets one more noise
+// addition (K_ii += sigma^2 again, inference/c_inference_exact.cpp:99-108) and runs again in the
+// next pass; everything else is final and is skipped from now on.  The loop ends when no
+// evaluation is left.  One CTA.
+__global__ void __launch_bounds__(1024)
+k_retry_decide(EvalDesc *__restrict__ descs, int count, int *__restrict__ fail, int max_jitter,
+               cudaGraphConditionalHandle handle)
+{
+    __shared__ int s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    int any = 0;
+    for (int b = threadIdx.x; b < count; b += blockDim.x) {
+        EvalDesc &e = descs[b];
+        if (e.skip) continue;
+        if (fail[e.out_index] != 0 && e.jitter < max_jitter) {
+            e.jitter++;
+            fail[e.out_index] = 0;
+            any = 1;
+        } else {
+            e.skip = 1;
+        }
+    }
+    if (any) atomicOr(&s_any, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) cudaGraphSetConditional(handle, (unsigned)s_any);
 }
 
 // ------------------------------------------------------------------ trtri: block row i of L^-1
@@ -564,7 +605,7 @@ k_trtri_row(const EvalDesc *__restrict__ descs, int i, int right_looking)
     __shared__ GemmBars bars;
     const EvalDesc &e = descs[blockIdx.y];
     const int j = blockIdx.x;
-    if (i >= e.T || j >= i) return;
+    if (i >= e.T || j >= i || e.skip) return;
     const int T = e.T;
     gemm_bars_init(&bars);
     double acc[4][4][2];
@@ -611,7 +652,7 @@ k_syrk_update(const EvalDesc *__restrict__ descs, int k)
     int a, b;
     tri_index(blockIdx.x, a, b);
     const int i = k + 1 + a, j = k + 1 + b, T = e.T;
-    if (i >= T) return;
+    if (i >= T || e.skip) return;
     gemm_bars_init(&bars);
     double acc[4][4][2];
     acc_zero(acc);
@@ -638,7 +679,7 @@ k_trtri_update(const EvalDesc *__restrict__ descs, int k)
     const EvalDesc &e = descs[blockIdx.y];
     const int T = e.T;
     const int j = blockIdx.x % (k + 1), i = k + 1 + blockIdx.x / (k + 1);
-    if (i >= T) return;
+    if (i >= T || e.skip) return;
     gemm_bars_init(&bars);
     double acc[4][4][2];
     acc_zero(acc);
@@ -681,7 +722,7 @@ k_lauum(const EvalDesc *__restrict__ descs)
     const EvalDesc &e = descs[blockIdx.y];
     int i, j;
     tri_index(blockIdx.x, i, j);
-    if (i >= e.T) return;
+    if (i >= e.T || e.skip) return;
     const int T = e.T;
     gemm_bars_init(&bars);
     double acc[4][4][2];
@@ -726,17 +767,20 @@ k_lauum(const EvalDesc *__restrict__ descs)
 //   nlml = 1/2 z^T z + sum log L_ii + n log(2 PI)/2     (c_inference_exact.cpp:118-120,146-152)
 __global__ void __launch_bounds__(256)
 k_solve(const EvalDesc *__restrict__ descs, ModelDims md, double *__restrict__ out_nlml,
-        int *__restrict__ out_status, const int *__restrict__ fail)
+        int *__restrict__ out_status, int *__restrict__ fail, int force_fail)
 {
     __shared__ double scratch[64];
     const EvalDesc &e = descs[blockIdx.x];
+    if (e.skip) return;
     const int ld = e.npad, tid = threadIdx.x;
     double v[2] = {0.0, 0.0};
     for (int i = tid; i < ld; i += blockDim.x) v[0] += e.rhs[i] * e.rhs[i];
     for (int k = tid; k < e.T; k += blockDim.x) v[1] += e.blk[k];
     block_reduce_sum<2>(v, scratch);
     if (tid == 0) {
-        const bool bad = fail[e.out_index] != 0;
+        // force_fail (tests of the jitter path): the first attempts count as failed factorisations
+        const bool bad = fail[e.out_index] != 0 || e.jitter < force_fail;
+        if (bad) fail[e.out_index] = 1;
         const double nlml = 0.5 * v[0] + v[1] + e.n * log(2.0 * md.pi) / 2.0;
         out_nlml[e.out_index] = bad ? __longlong_as_double(0x7ff8000000000000LL) : nlml;
         out_status[e.out_index] = bad ? -1 : e.jitter;

@@ -58,7 +58,12 @@ struct StageMark {
 struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     long long launches[MEDGP_STAGE_COUNT] = {};
+    uint64_t last_use = 0;  // LRU stamp
 };
+
+constexpr int kDescSlots = 4;      // ring of page-locked descriptor staging buffers
+constexpr int kTicketsPerSub = 256; // role counters of k_potrf_step, one per block column
+constexpr size_t kGraphCacheMax = 128;
 
 }  // namespace
 
@@ -72,8 +77,19 @@ struct medgp_ctx {
     std::vector<Series> series;
     std::string err;
     // staging owned by the context (grown on demand)
+    // h_descs is the current slot of a ring: a call fills its own slot, so the next call need
+    // not wait for this call's descriptor upload (no host synchronisation on the device path)
     EvalDesc *h_descs = nullptr, *d_descs = nullptr;
+    EvalDesc *h_desc_ring[kDescSlots] = {};
+    cudaEvent_t desc_ev[kDescSlots] = {};
+    bool desc_ev_pending[kDescSlots] = {};
+    int desc_slot = 0;
     size_t desc_cap = 0;
+    int *d_tickets = nullptr;  // 8 sub-chunk streams x kTicketsPerSub
+    bool device_retry = true;  // MEDGP_DEVICE_RETRY=0: jitter retries are driven by the host instead of the graph's WHILE node
+    bool retry_on_device = false;  // set by run_batch: the last chunk sequence carried its own jitter loop
+    int force_fail = 0;        // medgp_cuda_debug_force_fail: the first attempts of every evaluation are declared failed
+    uint64_t graph_clock = 0;
     double *h_theta = nullptr, *d_theta = nullptr, *h_out = nullptr, *d_out = nullptr;
     size_t theta_cap = 0, out_cap = 0;
     int *h_status = nullptr, *d_status = nullptr, *d_fail = nullptr;
@@ -147,15 +163,28 @@ size_t eval_bytes(const ModelDims &md, const Series &s, int nrhs, bool grad)
     return b;
 }
 
+// Grows the context-owned staging buffers.  Growing means freeing buffers the stream may still
+// be using, so the stream is drained first; the steady state (same batch size as before) does
+// not synchronise.
 int ensure_staging(medgp_ctx *ctx, size_t nreq, size_t nstar)
 {
     const size_t P = ctx->md.P;
+    const size_t need_out = nreq * (P + 1) + 2 * nstar;  // nlml (nreq) + grad (nreq*P) + mean/var (2*nstar)
+    if (nreq > ctx->desc_cap || nreq * P > ctx->theta_cap || need_out > ctx->out_cap || nreq > ctx->status_cap ||
+        nreq > ctx->fail_cap || nstar > ctx->star_cap) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < kDescSlots; i++) ctx->desc_ev_pending[i] = false;
+    }
     if (nreq > ctx->desc_cap) {
-        if (ctx->h_descs) cudaFreeHost(ctx->h_descs);
+        for (int i = 0; i < kDescSlots; i++)
+            if (ctx->h_desc_ring[i]) cudaFreeHost(ctx->h_desc_ring[i]);
         if (ctx->d_descs) cudaFree(ctx->d_descs);
         ctx->desc_cap = std::max(nreq, 2 * ctx->desc_cap);
-        CU(cudaMallocHost(&ctx->h_descs, ctx->desc_cap * sizeof(EvalDesc)));
+        for (int i = 0; i < kDescSlots; i++) CU(cudaMallocHost(&ctx->h_desc_ring[i], ctx->desc_cap * sizeof(EvalDesc)));
         CU(cudaMalloc(&ctx->d_descs, ctx->desc_cap * sizeof(EvalDesc)));
+        // the descriptor array is baked into the captured launch sequences
+        for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second.exec);
+        ctx->graphs.clear();
     }
     if (nreq * P > ctx->theta_cap) {
         if (ctx->h_theta) cudaFreeHost(ctx->h_theta);
@@ -164,8 +193,6 @@ int ensure_staging(medgp_ctx *ctx, size_t nreq, size_t nstar)
         CU(cudaMallocHost(&ctx->h_theta, ctx->theta_cap * 8));
         CU(cudaMalloc(&ctx->d_theta, ctx->theta_cap * 8));
     }
-    // results: nlml (nreq) + grad (nreq*P) + mean/var (2*nstar)
-    const size_t need_out = nreq * (P + 1) + 2 * nstar;
     if (need_out > ctx->out_cap) {
         if (ctx->h_out) cudaFreeHost(ctx->h_out);
         if (ctx->d_out) cudaFree(ctx->d_out);
@@ -192,6 +219,21 @@ int ensure_staging(medgp_ctx *ctx, size_t nreq, size_t nstar)
         CU(cudaMalloc(&ctx->d_star_t, ctx->star_cap * 8));
         CU(cudaMalloc(&ctx->d_star_meta, ctx->star_cap * sizeof(int)));
     }
+    // this call's descriptor slot: wait until the upload that last used it has been consumed
+    ctx->desc_slot = (ctx->desc_slot + 1) % kDescSlots;
+    if (ctx->desc_ev_pending[ctx->desc_slot]) {
+        CU(cudaEventSynchronize(ctx->desc_ev[ctx->desc_slot]));
+        ctx->desc_ev_pending[ctx->desc_slot] = false;
+    }
+    ctx->h_descs = ctx->h_desc_ring[ctx->desc_slot];
+    return MEDGP_OK;
+}
+
+// after the last descriptor upload of a call has been enqueued
+int release_desc_slot(medgp_ctx *ctx)
+{
+    CU(cudaEventRecord(ctx->desc_ev[ctx->desc_slot], ctx->stream));
+    ctx->desc_ev_pending[ctx->desc_slot] = true;
     return MEDGP_OK;
 }
 
@@ -342,6 +384,8 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     long long *L = ctx->times.launches;
     int *d_fail = ctx->d_fail;
     const SubChunk *scp = &sc;
+    int *tickets = ctx->d_tickets + (size_t)stagger_slot * kTicketsPerSub;  // stagger_slot = sub-chunk index
+    const int force_fail = ctx->force_fail;
     // stage markers (profiling): begin/end closures record events on the stream
     auto begin = [&](int stage) { out.push_back([=]() { stage_begin(ctx, stage, st); }); };
     auto end = [&](int stage) { out.push_back([=]() { stage_end(ctx, stage, st); }); };
@@ -351,7 +395,7 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
         out.push_back([=]() { k_delay<<<1, 1, 0, st>>>(ns); });
     }
     begin(MEDGP_STAGE_PREP);
-    out.push_back([=]() { k_prep<<<ncta, 256, 0, st>>>(dd, md, d_theta); L[MEDGP_STAGE_PREP]++; });
+    out.push_back([=]() { k_prep<<<ncta, 256, 0, st>>>(dd, md, d_theta, tickets, kTicketsPerSub); L[MEDGP_STAGE_PREP]++; });
     end(MEDGP_STAGE_PREP);
     begin(MEDGP_STAGE_ASSEMBLE);
     out.push_back([=]() { launch_assemble(md.Q, dim3(ntri, ncta), asm_smem, st, dd, md); L[MEDGP_STAGE_ASSEMBLE]++; });
@@ -366,13 +410,13 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     // diagonal CTA factors block k while the panel CTAs run their k-tile products, then wait on
     // its flag).  Large batches keep separate diagonal / panel kernels: their sub-chunk streams
     // already overlap, and CTAs spinning on a flag would hold slots the other streams can use.
-    const bool step_kernel = !rl && fold && ctx->fuse_diag;  // fold <=> few matrices in the chunk
+    const bool step_kernel = !rl && fold && ctx->fuse_diag && Tmax <= kTicketsPerSub;  // fold <=> few matrices in the chunk
     for (int k = 0; k < Tmax; k++) {
         const unsigned a0 = sc.act(k), a1 = k + 1 < Tmax ? sc.act(k + 1) : 0;
         const int rem = Tmax - k - 1;
         if (step_kernel) {
             begin(MEDGP_STAGE_POTRF);
-            out.push_back([=]() { k_potrf_step<<<dim3(a0, rem + 1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, d_fail); L[MEDGP_STAGE_POTRF]++; });
+            out.push_back([=]() { k_potrf_step<<<dim3(a0, rem + 1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, d_fail, tickets + k); L[MEDGP_STAGE_POTRF]++; });
             end(MEDGP_STAGE_POTRF);
             continue;
         }
@@ -396,7 +440,7 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
         }
     }
     begin(MEDGP_STAGE_SOLVE);
-    out.push_back([=]() { k_solve<<<ncta, 256, 0, st>>>(dd, md, d_nlml, d_status, d_fail); L[MEDGP_STAGE_SOLVE]++; });
+    out.push_back([=]() { k_solve<<<ncta, 256, 0, st>>>(dd, md, d_nlml, d_status, d_fail, force_fail); L[MEDGP_STAGE_SOLVE]++; });
     end(MEDGP_STAGE_SOLVE);
     if (grad) {
         begin(MEDGP_STAGE_TRTRI);
@@ -521,7 +565,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
                 e.n = s.n; e.npad = s.npad; e.T = s.T; e.nitems = s.nitems;
                 e.jitter = rq.jitter; e.nrhs = 1 + rq.nstar; e.nstar = rq.nstar;
                 e.out_index = rq.out_index; e.star_out = rq.star_off;
-                e.pad0 = 0; e.trange2 = s.trange2; e.pad1 = 0;
+                e.skip = 0; e.trange2 = s.trange2; e.pad1 = 0;
                 e.gstart = s.d_gstart; e.perm = s.d_perm; e.ngroups = s.ngroups;
                 sc.T.push_back(s.T);
                 sc.cnt++;
@@ -568,7 +612,15 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
                 }
             return MEDGP_OK;
         };
-        if (ctx->profile || !ctx->use_graphs) {
+        // Jitter retries (c_inference_exact.cpp:99-108) run ON THE DEVICE: the chunk's launch
+        // sequence is the body of a graph WHILE node whose last kernel (k_retry_decide) bumps the
+        // jitter of the failed evaluations, retires the others, and keeps the loop alive while
+        // any evaluation is left.  The common case (nothing fails) is one pass plus that kernel.
+        const int max_jitter = (mode == 3) ? 0 : kMaxJitter;  // online imputation never retries (see the header)
+        const bool graph_mode = !ctx->profile && ctx->use_graphs;
+        const bool loop = graph_mode && ctx->device_retry && max_jitter > 0;
+        ctx->retry_on_device = loop;
+        if (!graph_mode) {
             const int rc = issue_all();
             if (rc) return rc;
         } else {
@@ -578,6 +630,10 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
             mix((uint64_t)(uintptr_t)d_theta); mix((uint64_t)(uintptr_t)d_nlml); mix((uint64_t)(uintptr_t)d_grad);
             mix((uint64_t)(uintptr_t)d_status); mix((uint64_t)(uintptr_t)d_mean); mix((uint64_t)(uintptr_t)d_var);
             mix((uint64_t)(uintptr_t)ctx->d_fail);
+            // the launches bake in the model (ModelDims by value, Q-templated kernels, smem sizes)
+            mix((uint64_t)md.Q); mix((uint64_t)md.D); mix((uint64_t)md.R); mix((uint64_t)md.P); mix((uint64_t)md.parLen);
+            { uint64_t pib; memcpy(&pib, &md.pi, 8); mix(pib); }
+            mix((uint64_t)ctx->gemm_smem_pad); mix((uint64_t)ctx->force_fail); mix((uint64_t)max_jitter); mix(loop);
             for (auto &sc : subs) {
                 mix(sc.cnt); mix((uint64_t)sc.items_max); mix((uint64_t)sc.nstar_max); mix((uint64_t)sc.groups_max);
                 for (int t : sc.T) mix((uint64_t)t);
@@ -586,25 +642,61 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
             if (it == ctx->graphs.end()) {
                 long long before[MEDGP_STAGE_COUNT];
                 memcpy(before, ctx->times.launches, sizeof(before));
-                CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                const int rc = issue_all();
                 cudaGraph_t graph = nullptr;
-                cudaError_t ce = cudaStreamEndCapture(st, &graph);
-                if (rc) return rc;
-                if (ce != cudaSuccess) { ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return MEDGP_ERR_CUDA; }
                 GraphEntry ge;
-                CU(cudaGraphInstantiate(&ge.exec, graph, 0));
-                cudaGraphDestroy(graph);
+                auto build = [&]() -> int {
+                    if (!loop) {  // plain capture of one pass
+                        CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                        const int rc = issue_all();
+                        const cudaError_t ce = cudaStreamEndCapture(st, &graph);  // always: leaves no stream in capture mode
+                        if (rc) return rc;
+                        if (ce != cudaSuccess) { ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return MEDGP_ERR_CUDA; }
+                        CU(cudaGraphInstantiate(&ge.exec, graph, 0));
+                        return MEDGP_OK;
+                    }
+                    CU(cudaGraphCreate(&graph, 0));
+                    cudaGraphConditionalHandle handle;
+                    CU(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));
+                    cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+                    np.type = cudaGraphNodeTypeConditional;
+                    np.conditional.handle = handle;
+                    np.conditional.type = cudaGraphCondTypeWhile;
+                    np.conditional.size = 1;
+                    cudaGraphNode_t node;
+                    CU(cudaGraphAddNode(&node, graph, nullptr, 0, &np));
+                    cudaGraph_t body = np.conditional.phGraph_out[0];
+                    CU(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+                    const int rc = issue_all();
+                    if (rc == MEDGP_OK)
+                        k_retry_decide<<<1, 1024, 0, st>>>(ctx->d_descs + dpos, (int)cnt, ctx->d_fail, max_jitter, handle);
+                    cudaGraph_t captured = nullptr;
+                    const cudaError_t ce = cudaStreamEndCapture(st, &captured);  // always: leaves no stream in capture mode
+                    if (rc) return rc;
+                    if (ce != cudaSuccess) { ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return MEDGP_ERR_CUDA; }
+                    CU(cudaGraphInstantiate(&ge.exec, graph, 0));
+                    return MEDGP_OK;
+                };
+                const int rc = build();
+                if (graph) cudaGraphDestroy(graph);
                 for (int i = 0; i < MEDGP_STAGE_COUNT; i++) {
                     ge.launches[i] = ctx->times.launches[i] - before[i];
                     ctx->times.launches[i] = before[i];
                 }
-                if (ctx->graphs.size() >= 128) {  // bounded cache
-                    for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second.exec);
-                    ctx->graphs.clear();
+                if (rc) {
+                    cudaGetLastError();
+                    return rc;
+                }
+                if (ctx->graphs.size() >= kGraphCacheMax) {  // bounded cache: evict the least recently used entry
+                    auto victim = ctx->graphs.begin();
+                    for (auto g = ctx->graphs.begin(); g != ctx->graphs.end(); ++g)
+                        if (g->second.last_use < victim->second.last_use) victim = g;
+                    // an exec may still be running: destruction is deferred by the runtime until it has completed
+                    cudaGraphExecDestroy(victim->second.exec);
+                    ctx->graphs.erase(victim);
                 }
                 it = ctx->graphs.emplace(key, ge).first;
             }
+            it->second.last_use = ++ctx->graph_clock;
             CU(cudaGraphLaunch(it->second.exec, st));
             for (int i = 0; i < MEDGP_STAGE_COUNT; i++) ctx->times.launches[i] += it->second.launches[i];
         }
@@ -672,12 +764,20 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     ctx->timeline = getenv("MEDGP_TIMELINE");
     if (const char *ev = getenv("MEDGP_FUSE_DIAG")) ctx->fuse_diag = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_GRAPHS")) ctx->use_graphs = atoi(ev) != 0;
+    if (const char *ev = getenv("MEDGP_DEVICE_RETRY")) ctx->device_retry = atoi(ev) != 0;
+    if (const char *ev = getenv("MEDGP_FORCE_FAIL")) ctx->force_fail = std::max(0, atoi(ev));  // tests of the jitter path through the executables
     if (const char *ev = getenv("MEDGP_STREAMS")) ctx->max_streams = std::max(1, std::min(8, atoi(ev)));
     for (int i = 0; i < 8; i++) {
         cudaStreamCreateWithFlags(&ctx->sub_streams[i], cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < kDescSlots; i++) cudaEventCreateWithFlags(&ctx->desc_ev[i], cudaEventDisableTiming);
+    if (cudaMalloc(&ctx->d_tickets, 8 * kTicketsPerSub * sizeof(int)) != cudaSuccess ||
+        cudaMemset(ctx->d_tickets, 0, 8 * kTicketsPerSub * sizeof(int)) != cudaSuccess) {
+        medgp_cuda_destroy(ctx);
+        return MEDGP_ERR_NOMEM;
+    }
     cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
     cudaFuncSetAttribute(k_potrf_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
     cudaFuncSetAttribute(k_trtri_row, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
@@ -705,7 +805,12 @@ MEDGP_API void medgp_cuda_destroy(medgp_ctx *ctx)
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     cudaFree(ctx->arena);
-    cudaFreeHost(ctx->h_descs); cudaFree(ctx->d_descs);
+    cudaFree(ctx->d_tickets);
+    for (int i = 0; i < kDescSlots; i++) {
+        if (ctx->h_desc_ring[i]) cudaFreeHost(ctx->h_desc_ring[i]);
+        if (ctx->desc_ev[i]) cudaEventDestroy(ctx->desc_ev[i]);
+    }
+    cudaFree(ctx->d_descs);
     cudaFreeHost(ctx->h_theta); cudaFree(ctx->d_theta);
     cudaFreeHost(ctx->h_out); cudaFree(ctx->d_out);
     cudaFreeHost(ctx->h_status); cudaFree(ctx->d_status); cudaFree(ctx->d_fail);
@@ -732,6 +837,11 @@ MEDGP_API int medgp_cuda_model(medgp_ctx *ctx, int Q, int D, int R, double pi_co
             return MEDGP_ERR_ARG;
         }
     cudaSetDevice(ctx->device);
+    // captured launch sequences bake in the model (ModelDims by value, Q-templated kernels,
+    // shared-memory sizes): none of them survives a change of model
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second.exec);
+    ctx->graphs.clear();
     fill_dims(ctx->md, Q, D, R, pi_const);
     const int asm_smem = (Q * D * D + Q) * 8;
     const int npairs = D * (D + 1) / 2;
@@ -911,6 +1021,33 @@ MEDGP_API int medgp_cuda_sync(medgp_ctx *ctx)
     return MEDGP_OK;
 }
 
+// host-driven jitter rounds for the call paths that run without the graph's WHILE node
+// (profiling, MEDGP_GRAPHS=0, MEDGP_DEVICE_RETRY=0): re-run the failed evaluations with one more
+// noise addition until they pass or kMaxJitter is reached (c_inference_exact.cpp:99-108)
+static int host_retry_rounds(medgp_ctx *ctx, std::vector<Request> reqs, int batch, const double *d_theta, int mode,
+                             double *d_nlml, double *d_grad, int *d_status, double *d_mean, double *d_var)
+{
+    cudaStream_t st = ctx->stream;
+    for (int round = 1; round <= kMaxJitter; round++) {
+        CU(cudaMemcpyAsync(ctx->h_status, d_status, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        resolve_marks(ctx);
+        std::vector<Request> again;
+        for (auto &rq : reqs)
+            if (ctx->h_status[rq.out_index] < 0 && rq.jitter < kMaxJitter) {
+                Request r2 = rq;
+                r2.jitter++;
+                again.push_back(r2);
+            }
+        if (again.empty()) break;
+        reqs.swap(again);
+        CU(cudaMemsetAsync(ctx->d_fail, 0, batch * sizeof(int), st));
+        const int rc = run_batch(ctx, reqs, d_theta, mode, d_nlml, d_grad, d_status, d_mean, d_var, 0);
+        if (rc) return rc;
+    }
+    return MEDGP_OK;
+}
+
 MEDGP_API int medgp_cuda_nlml_grad_device(medgp_ctx *ctx, int batch, const int *series_id,
                                           const double *d_theta, int want_grad, double *d_nlml,
                                           double *d_grad, int *d_status)
@@ -924,16 +1061,30 @@ MEDGP_API int medgp_cuda_nlml_grad_device(medgp_ctx *ctx, int batch, const int *
     cudaSetDevice(ctx->device);
     int rc = check_series_ids(ctx, batch, series_id);
     if (rc) return rc;
-    // the descriptor staging buffer is reused: the previous call must have drained
-    CU(cudaStreamSynchronize(ctx->stream));
-    resolve_marks(ctx);
+    if (want_grad)
+        for (int b = 0; b < batch; b++)
+            if (ctx->series[series_id[b]].time_order) {
+                ctx->err = "nlml_grad_device: gradients need a feature-ordered series (medgp_cuda_add_series)";
+                return MEDGP_ERR_ARG;
+            }
+    if (ctx->profile) {  // stage marks are resolved per call
+        CU(cudaStreamSynchronize(ctx->stream));
+        resolve_marks(ctx);
+    }
+    // no host synchronisation here: the call fills its own descriptor slot, and everything it
+    // enqueues is ordered behind the previous call on the context's stream
     rc = ensure_staging(ctx, batch, 0);
     if (rc) return rc;
     std::vector<Request> reqs(batch);
     for (int b = 0; b < batch; b++) reqs[b] = {series_id[b], b, 0, 0, 0};
     CU(cudaMemsetAsync(ctx->d_fail, 0, batch * sizeof(int), ctx->stream));
-    return run_batch(ctx, std::move(reqs), d_theta, want_grad ? 1 : 0, d_nlml, d_grad, d_status,
-                     nullptr, nullptr, 0);
+    rc = run_batch(ctx, reqs, d_theta, want_grad ? 1 : 0, d_nlml, d_grad, d_status, nullptr, nullptr, 0);
+    if (rc) return rc;
+    if (!ctx->retry_on_device) {
+        rc = host_retry_rounds(ctx, std::move(reqs), batch, d_theta, want_grad ? 1 : 0, d_nlml, d_grad, d_status, nullptr, nullptr);
+        if (rc) return rc;
+    }
+    return release_desc_slot(ctx);
 }
 
 static bool is_pinned_host(const void *p)
@@ -1005,28 +1156,23 @@ MEDGP_API int medgp_cuda_nlml_grad(medgp_ctx *ctx, int batch, const int *series_
     };
     std::vector<Request> reqs(batch);
     for (int b = 0; b < batch; b++) reqs[b] = {series_id[b], b, 0, 0, 0};
-    for (int round = 0; round <= kMaxJitter && !reqs.empty(); round++) {
-        CU(cudaMemsetAsync(ctx->d_fail, 0, batch * sizeof(int), st));
-        rc = run_batch(ctx, reqs, ctx->d_theta, want_grad ? 1 : 0, d_nlml, d_grad, ctx->d_status,
-                       nullptr, nullptr, 0);
+    CU(cudaMemsetAsync(ctx->d_fail, 0, batch * sizeof(int), st));
+    rc = run_batch(ctx, reqs, ctx->d_theta, want_grad ? 1 : 0, d_nlml, d_grad, ctx->d_status, nullptr, nullptr, 0);
+    if (rc) return rc;
+    // jitter retries happened inside the launch sequence (graph WHILE node); without it the
+    // host drives them
+    if (!ctx->retry_on_device) {
+        rc = host_retry_rounds(ctx, std::move(reqs), batch, ctx->d_theta, want_grad ? 1 : 0, d_nlml, d_grad,
+                               ctx->d_status, nullptr, nullptr);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
-        // the results ride on the same synchronisation as the status words: in the common case
-        // (nothing needs jitter) the call ends after this one wait
-        rc = fetch_outputs();
-        if (rc) return rc;
-        CU(cudaStreamSynchronize(st));
-        resolve_marks(ctx);
-        // jitter: add sigma^2 to the diagonal again and refactor (c_inference_exact.cpp:99-108)
-        std::vector<Request> again;
-        for (auto &rq : reqs)
-            if (ctx->h_status[rq.out_index] < 0 && rq.jitter < kMaxJitter) {
-                Request r2 = rq;
-                r2.jitter++;
-                again.push_back(r2);
-            }
-        reqs.swap(again);
     }
+    rc = release_desc_slot(ctx);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+    rc = fetch_outputs();
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st));  // the one wait of the call
+    resolve_marks(ctx);
     if (!pin_out) {
         memcpy(nlml, ctx->h_out, (size_t)batch * 8);
         if (want_grad) memcpy(grad, ctx->h_out + batch, (size_t)batch * P * 8);
@@ -1072,24 +1218,19 @@ MEDGP_API int medgp_cuda_predict(medgp_ctx *ctx, int batch, const int *series_id
     std::vector<Request> reqs(batch);
     for (int b = 0; b < batch; b++)
         reqs[b] = {series_id[b], b, 0, star_offset[b + 1] - star_offset[b], star_offset[b]};
-    for (int round = 0; round <= kMaxJitter && !reqs.empty(); round++) {
-        CU(cudaMemsetAsync(ctx->d_fail, 0, batch * sizeof(int), st));
-        rc = run_batch(ctx, reqs, ctx->d_theta, 2, d_nlml, nullptr, ctx->d_status, d_mean, d_var, 0);
+    CU(cudaMemsetAsync(ctx->d_fail, 0, batch * sizeof(int), st));
+    rc = run_batch(ctx, reqs, ctx->d_theta, 2, d_nlml, nullptr, ctx->d_status, d_mean, d_var, 0);
+    if (rc) return rc;
+    if (!ctx->retry_on_device) {
+        rc = host_retry_rounds(ctx, std::move(reqs), batch, ctx->d_theta, 2, d_nlml, nullptr, ctx->d_status, d_mean, d_var);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        resolve_marks(ctx);
-        std::vector<Request> again;
-        for (auto &rq : reqs)
-            if (ctx->h_status[rq.out_index] < 0 && rq.jitter < kMaxJitter) {
-                Request r2 = rq;
-                r2.jitter++;
-                again.push_back(r2);
-            }
-        reqs.swap(again);
     }
+    rc = release_desc_slot(ctx);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, ((size_t)batch + 2 * (size_t)nstar) * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    resolve_marks(ctx);
     memcpy(mean, ctx->h_out + batch, (size_t)nstar * 8);
     memcpy(var, ctx->h_out + batch + nstar, (size_t)nstar * 8);
     memcpy(status, ctx->h_status, (size_t)batch * sizeof(int));
@@ -1128,6 +1269,8 @@ MEDGP_API int medgp_cuda_predict_online(medgp_ctx *ctx, int batch, const int *se
     double *d_nlml = ctx->d_out, *d_mean = ctx->d_out + batch, *d_var = d_mean + ntot;
     CU(cudaMemsetAsync(ctx->d_fail, 0, batch * sizeof(int), st));
     rc = run_batch(ctx, reqs, ctx->d_theta, 3, d_nlml, nullptr, ctx->d_status, d_mean, d_var, 0);
+    if (rc) return rc;
+    rc = release_desc_slot(ctx);
     if (rc) return rc;
     CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, batch * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, ((size_t)batch + 2 * ntot) * 8, cudaMemcpyDeviceToHost, st));
@@ -1209,6 +1352,13 @@ MEDGP_API int medgp_cuda_debug_matrices(medgp_ctx *ctx, int series_id, const dou
             for (size_t i = 0; i < n; i++) alpha[s.perm[i]] = ha[i];
         }
     }
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_debug_force_fail(medgp_ctx *ctx, int attempts)
+{
+    if (!ctx || attempts < 0) return MEDGP_ERR_ARG;
+    ctx->force_fail = attempts;
     return MEDGP_OK;
 }
 

@@ -18,7 +18,11 @@ struct BackendSlot {
     medgp_ctx *ctx = nullptr;
     int Q = 0, D = 0, R = 0;
     // small LRU of uploaded series keyed by a content hash
-    struct Entry { uint64_t key; int n; int id; };
+    struct Entry {
+        uint64_t key; int id;
+        std::vector<int> meta;       // the uploaded arrays themselves: a hash hit is confirmed by content
+        std::vector<float> x, y;
+    };
     std::list<Entry> lru;
 };
 std::map<int, BackendSlot> g_slots;
@@ -84,7 +88,7 @@ int medgp_backend::series_for(medgp_ctx *ctx, const vector<int> &meta, const vec
     key = fnv(key, y.data(), y.size() * sizeof(float));
     if (s)
         for (auto it = s->lru.begin(); it != s->lru.end(); ++it)
-            if (it->key == key && it->n == (int)x.size()) {
+            if (it->key == key && it->meta == meta && it->x == x && it->y == y) {
                 s->lru.splice(s->lru.begin(), s->lru, it);
                 return s->lru.front().id;
             }
@@ -93,7 +97,7 @@ int medgp_backend::series_for(medgp_ctx *ctx, const vector<int> &meta, const vec
     int rc = medgp_cuda_add_series(ctx, (int)x.size(), (const int32_t *)meta.data(), x.data(), y.data(), &id);
     if (rc != MEDGP_OK) die("medgp_cuda_add_series", ctx, rc);
     if (s) {
-        s->lru.push_front({key, (int)x.size(), id});
+        s->lru.push_front({key, id, meta, x, y});
         if (s->lru.size() > kSeriesCache) {
             medgp_cuda_free_series(ctx, s->lru.back().id);
             s->lru.pop_back();
@@ -215,6 +219,9 @@ vector<vector<float> > GP_Regression::predict(const vector<int> &meta, const vec
     vector<double> mean(m), var(m);
     const int off[2] = {0, m};
     int status = 0;
+    // the series cache may have evicted (and reused) the id since train(): resolve it again from
+    // the arrays, which uploads them anew if they are gone
+    fit.series_id = medgp_backend::series_for(fit.ctx, meta, x, y);
     int rc = medgp_cuda_predict(fit.ctx, 1, &fit.series_id, fit.theta.data(), off,
                                 (const int32_t *)meta2.data(), x2.data(), mean.data(), var.data(), &status);
     if (rc != MEDGP_OK) die("medgp_cuda_predict", fit.ctx, rc);

@@ -29,6 +29,15 @@ scg_stepper::scg_stepper(int max_iteration, const vector<double> &init_parameter
       success(false), M(0), d0(0), f0_unused(0), x1(0), x2(0), x3(0), x4(0), d1(0), d2(0), d3(0), d4(0),
       f1(0), f2(0), f3(0), f4(0), F0(0), fX(0), X(init_parameter), probe(init_parameter)
 {
+    // The reference advances its counter by signbit(max_iteration) only (c_optimizer_scg.cpp:73,88,114),
+    // so a positive budget ("Linesearch" mode) never terminates there.  Nothing in MedGP passes one;
+    // it is refused here instead of being reproduced.
+    if (max_iteration > 0) {
+        std::cout << "ERROR: c_optimizer_scg needs a negative max_iteration (function-evaluation budget); got "
+                  << max_iteration << std::endl;
+        fX = NAN;
+        state = DONE;
+    }
 }
 
 void scg_stepper::make_probe()

@@ -163,6 +163,13 @@ typedef struct {
 
 static void fit_free(fit_t *f) { if (f) { free(f->L); free(f->alpha); free(f); } }
 
+/* Tests of the jitter path: the first `attempts` factorisations of every evaluation count as
+ * failed (what spotrf reporting info != 0 that many times would cause in
+ * c_inference_exact.cpp:97-108), so the additions and everything downstream of them are
+ * exercised on well-conditioned matrices where the results can be compared to 1e-9. */
+static int g_force_fail = 0;
+ORACLE_API void medgp_oracle_force_fail(int attempts) { g_force_fail = attempts < 0 ? 0 : attempts; }
+
 /* K + noise -> L, alpha, with the reference's jitter loop
  * (medgpc/src/inference/c_inference_exact.cpp:76-125) */
 static fit_t *fit_series(const hyp_t *h, int n, const int32_t *meta, const float *x, const float *y)
@@ -177,7 +184,7 @@ static fit_t *fit_series(const hyp_t *h, int n, const int32_t *meta, const float
     memcpy(f->L, K, sizeof(double) * (size_t)n * n);
     int info = chol_lower(n, f->L);
     int count = 0;
-    while (info != 0 && count < 10) {
+    while ((info != 0 || count < g_force_fail) && count < 10) {
         for (int i = 0; i < n; i++) K[(size_t)i * n + i] += h->sigma[meta[i]] * h->sigma[meta[i]];
         memcpy(f->L, K, sizeof(double) * (size_t)n * n);
         info = chol_lower(n, f->L);

@@ -45,6 +45,12 @@ def _prep(meta, x, y=None):
     return meta, x, y
 
 
+def force_fail(attempts):
+    """Tests of the jitter path: the first `attempts` factorisations of every later evaluation
+    count as failed (0 = off)."""
+    lib().medgp_oracle_force_fail(int(attempts))
+
+
 def nlml_grad(Q, D, R, meta, x, y, theta, want_grad=True, grad_mode=0, pi=PI_REF):
     """Returns (nlml, grad or None, status)."""
     meta, x, y = _prep(meta, x, y)

@@ -20,6 +20,7 @@ int medgp_oracle_nlml_grad(int Q, int D, int R, double pi, int n, const int32_t 
 int medgp_oracle_predict(int Q, int D, int R, double pi, int n, const int32_t *meta, const float *x,
                          const float *y, const double *theta, int m, const int32_t *meta_star,
                          const float *x_star, double *mean, double *var, int *status);
+void medgp_oracle_force_fail(int attempts);
 
 typedef struct { int n; int32_t *meta; float *x, *y; } series_t;
 struct medgp_ctx { int Q, D, R, P; double pi; series_t *s; int ns, cap; };
@@ -28,6 +29,8 @@ int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_bytes)
 {
     (void)device; (void)workspace_bytes;
     *out = (medgp_ctx *)calloc(1, sizeof(medgp_ctx));
+    /* same test hook as the CUDA library: the first attempts of every factorisation count as failed */
+    if (getenv("MEDGP_FORCE_FAIL")) medgp_oracle_force_fail(atoi(getenv("MEDGP_FORCE_FAIL")));
     return MEDGP_OK;
 }
 void medgp_cuda_destroy(medgp_ctx *c) { if (c) { medgp_cuda_clear_series(c); free(c->s); free(c); } }
