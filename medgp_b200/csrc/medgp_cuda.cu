@@ -1312,6 +1312,13 @@ MEDGP_API int medgp_cuda_debug_matrices(medgp_ctx *ctx, int series_id, const dou
         return MEDGP_OK;
     };
     std::vector<Request> one = {{series_id, 0, 0, 0, 0}};
+    // the taps read buffers between stages and re-run single kernels on the descriptors: no
+    // device-side jitter loop here (it would retire the descriptor), one pass only
+    struct RetryOff {
+        medgp_ctx *c; bool saved;
+        explicit RetryOff(medgp_ctx *cc) : c(cc), saved(cc->device_retry) { c->device_retry = false; }
+        ~RetryOff() { c->device_retry = saved; }
+    } retry_off(ctx);
     if (K) {
         // a full NLML pass sets up descriptors and parameters ...
         rc = run_batch(ctx, one, ctx->d_theta, 0, ctx->d_out, nullptr, ctx->d_status, nullptr, nullptr, 0);

@@ -10,6 +10,8 @@ Contents:
   varem   reference c_optimizer_varEM on the same objective (EM state, pruning flags)
   init    first random theta vectors of the reference's c_experiment::get_global_hyp
   train   reference main_one_train.o end to end on one tiny patient
+  test    reference main_one_test.o end to end (sliding-window imputation, with and without
+          online updates) on a patient with shared time stamps: every output file
 """
 import importlib.util
 import json
@@ -43,7 +45,7 @@ def parse_tagged(text):
     return out
 
 
-def write_experiment(tmp, Q, D, R, features, prior_index, n_init, n_iter, patients):
+def write_experiment(tmp, Q, D, R, features, prior_index, n_init, n_iter, patients, **opt_over):
     """exp_setup.json / hyp_bound.txt / data files as medgpc/util/config.py writes them."""
     spec = importlib.util.spec_from_file_location(
         "refconfig", os.path.join(REFERENCE_ROOT, "medgpc", "util", "config.py"))
@@ -51,6 +53,7 @@ def write_experiment(tmp, Q, D, R, features, prior_index, n_init, n_iter, patien
     spec.loader.exec_module(cfg)
     opt = json.load(open(os.path.join(REFERENCE_ROOT, "scripts", "opt_prior0.json")))
     opt["random_init_num"], opt["top_iteration_num"] = n_init, n_iter
+    opt.update(opt_over)
     for d in ("config", "train", "test", "kernel/fold0", "data"):
         os.makedirs(os.path.join(tmp, d), exist_ok=True)
     paths = dict(data_dir=os.path.join(tmp, "data"), exp_top_dir=tmp,
@@ -78,7 +81,8 @@ def main():
     gold = {"note": "outputs of the unmodified reference (g++ -O2, OpenBLAS shim); float arithmetic"}
     # ---- eval
     cases = []
-    for (Q, D, R, n, seed) in [(2, 2, 2, 80, 1), (1, 1, 1, 37, 3), (3, 4, 2, 130, 4), (5, 24, 8, 300, 5)]:
+    for (Q, D, R, n, seed) in [(2, 2, 2, 80, 1), (1, 1, 1, 37, 3), (3, 4, 2, 130, 4), (5, 24, 8, 300, 5),
+                               (5, 24, 8, 500, 6)]:  # the last one is the C2 shape at full size (T = 8 tiles deep)
         meta, x, y = synth.make_patient(D, n, seed)
         theta = synth.init_hyp_lmc_sm(Q, D, R, 2, seed=718 + seed)[1]
         r = oracle.ref_eval(Q, D, R, meta, x, y, theta, mode=1)
@@ -120,6 +124,33 @@ def main():
                              init_hyp=init_hyp.tolist(), hyp=hyp.tolist(), nlml_init_fp64=f_init, nlml_fit_fp64=f_fit,
                              train_num=int(open(os.path.join(tmp, "train", "train_num_p0.txt")).read()),
                              train_flag=int(open(os.path.join(tmp, "train", "train_flag_p0.txt")).read()))
+    # ---- end-to-end test executable: both imputation modes (main_one_test.cpp:447-472 outputs)
+    with tempfile.TemporaryDirectory() as tmp:
+        Q, D, R, n = 2, 2, 1, 26
+        meta, x, y = synth.make_patient(D, n, seed=77, T=100.0)
+        x[3] = x[14]   # two features observed at one time stamp
+        x[20] = x[7]   # and a second shared stamp
+        lr = 1e-3
+        cfg = write_experiment(tmp, Q, D, R, [18, 19], 0, 20, 30, {"p0": (meta, x, y)}, online_learn_rate=lr)
+        theta = synth.init_hyp_lmc_sm(Q, D, R, 1, seed=3)[0]
+        theta[D + 1] = 0.0   # an A entry at exactly 0 is clamped at test time (c_prior.cpp:118-140)
+        with open(os.path.join(tmp, "kernel", "fold0", "None_mode_mixture_num.txt"), "w") as fh:
+            fh.write(f"{Q}\n")
+        theta.tofile(os.path.join(tmp, "kernel", "fold0", "None_mode_param.bin"))
+        run([os.path.join(REF, "main_one_test.o"), "--cfg", cfg, "--pan", "p0", "--thread", "1", "--fold", "0",
+             "--kernclust-alg", "None"])
+        td = os.path.join(tmp, "test")
+        modes = {}
+        for mode in ("mean_wo_update", "mean_w_update"):
+            modes[mode] = dict(
+                flag=[int(v) for v in open(os.path.join(td, f"test_{mode}_flag_p0.txt")).read().split()],
+                feature=[int(v) for v in open(os.path.join(td, f"test_{mode}_feature_p0.txt")).read().split()],
+                ci=[int(v) for v in open(os.path.join(td, f"test_{mode}_ci_p0.txt")).read().split()],
+                etime=np.fromfile(os.path.join(td, f"test_{mode}_etime_p0.bin")).tolist(),
+                error=np.fromfile(os.path.join(td, f"test_{mode}_error_p0.bin")).tolist(),
+                pred=np.fromfile(os.path.join(td, f"test_{mode}_pred_p0.bin")).tolist())
+        gold["test"] = dict(Q=Q, D=D, R=R, n=n, patient_seed=77, T=100.0, shared=[[3, 14], [20, 7]], features=[18, 19],
+                            online_learn_rate=lr, theta_seed=3, theta=theta.tolist(), modes=modes)
     with open(os.path.join(ROOT, "tests", "golden", "golden.json"), "w") as f:
         json.dump(gold, f, indent=1)
     print("wrote tests/golden/golden.json:", {k: (len(v) if isinstance(v, list) else "ok") for k, v in gold.items()})

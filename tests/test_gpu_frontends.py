@@ -4,6 +4,7 @@ committed reference outputs (tests/golden/golden.json)."""
 import json
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -11,6 +12,8 @@ import pytest
 from medgp_b200 import expfiles, synth
 
 pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "medgp_b200", "host")
@@ -71,6 +74,58 @@ def test_train_front_ends_gpu_vs_oracle_build(tmp_path, oracle, prior_index, bud
             fa = oracle.nlml_grad(Q, D, R, m, x, y, a, want_grad=False)[0]
             fb = oracle.nlml_grad(Q, D, R, m, x, y, b, want_grad=False)[0]
             assert abs(fa - fb) <= 0.02 * abs(fb)
+
+
+def test_test_executable_gpu_vs_reference_golden(tmp_path):
+    """The shipped main_one_test (CUDA backend) against the committed outputs of the UNMODIFIED
+    reference main_one_test.o (tests/golden/make_golden.py), both imputation modes, through the
+    one-factorisation paths and through the reference's literal one-fit-per-observation procedure."""
+    from test_host_logic import run_test_executable_against_golden
+    run_test_executable_against_golden(os.path.join(HOST, "main_one_test"), str(tmp_path / "online"))
+    run_test_executable_against_golden(os.path.join(HOST, "main_one_test"), str(tmp_path / "refit"),
+                                       env=dict(os.environ, MEDGP_NO_ONLINE="1"))
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "main_one_train_cuda.o")),
+                    reason="oracle/_ref not built (needs /root/reference once)")
+def test_reference_executable_with_cuda_binding(tmp_path, oracle):
+    """oracle/_ref/main_one_train_cuda.o = unmodified reference sources + c_inference_cuda +
+    -lmedgp_cuda (oracle/ref/build_ref.sh): train_hyp / train_flag against the reference's own
+    main_one_train.o after a 12-evaluation budget, a variational-EM round with prior terms, and
+    single evaluations through the reference's compute_objective against the golden vectors."""
+    from test_host_logic import run_reference_binding_checks
+    run_reference_binding_checks("cuda", tmp_path, oracle)
+
+
+@pytest.mark.parametrize("attempts", [2])
+def test_jitter_success_through_main_one_train(tmp_path, attempts):
+    """The jitter-success branch through the training executable: with the first two
+    factorisation attempts of every evaluation declared failed (MEDGP_FORCE_FAIL, honoured by the
+    CUDA library and by the oracle backend alike) main_one_train must walk the same optimiser
+    path on the GPU as on the oracle -- i.e. NLML and gradients of K + 3 sigma^2 agree evaluation
+    after evaluation (c_inference_exact.cpp:99-108)."""
+    Q, D, R = 2, 3, 2
+    pats = {"p0": synth.make_patient(D, 90, seed=321)}
+    kw = dict(prior_index=0, random_init_num=6, top_iteration_num=12)
+    env = dict(os.environ, MEDGP_FORCE_FAIL=str(attempts))
+    hyp = {}
+    for tag, exe in (("gpu", os.path.join(HOST, "main_one_train")), ("orc", os.path.join(BUILD, "main_one_train"))):
+        top = str(tmp_path / tag)
+        cfg = expfiles.write_experiment(top, Q, D, R, [1, 3, 4], pats, **kw)
+        out = subprocess.run([exe, "--cfg", cfg, "--pan", "p0", "--thread", "1"], check=True, capture_output=True,
+                             text=True, timeout=900, env=env).stdout
+        assert f"jittered {attempts} time(s)" in out or tag == "orc"
+        assert expfiles.read_int_txt(os.path.join(top, "train", "train_flag_p0.txt")) == [1]
+        hyp[tag] = (expfiles.read_double_bin(os.path.join(top, "train", "train_init_hyp_p0.bin")),
+                    expfiles.read_double_bin(os.path.join(top, "train", "train_hyp_p0.bin")))
+    assert np.array_equal(hyp["gpu"][0], hyp["orc"][0])
+    assert np.abs(hyp["gpu"][1] - hyp["orc"][1]).max() <= 1e-7 * max(1.0, np.abs(hyp["orc"][1]).max())
+    # and the forced jitter changed the problem: without it the fitted theta is different
+    top = str(tmp_path / "plain")
+    cfg = expfiles.write_experiment(top, Q, D, R, [1, 3, 4], pats, **kw)
+    run([os.path.join(BUILD, "main_one_train"), "--cfg", cfg, "--pan", "p0", "--thread", "1"])
+    plain = expfiles.read_double_bin(os.path.join(top, "train", "train_hyp_p0.bin"))
+    assert np.abs(plain - hyp["orc"][1]).max() > 1e-4
 
 
 def test_test_front_end_gpu_vs_oracle_build(tmp_path):

@@ -203,6 +203,111 @@ def test_main_one_test_matches_python_replay(tmp_path, oracle):
         assert expfiles.read_int_txt(os.path.join(td, f"test_{name}_ci_p0.txt")) == cis
 
 
+def run_test_executable_against_golden(exe, top, env=None):
+    """Runs a main_one_test executable on the committed case of GOLD["test"] and compares every
+    output file with what the UNMODIFIED reference main_one_test.o wrote (main_one_test.cpp:447-472),
+    both modes.  Tolerance: the reference's float arithmetic (2e-4 on predictions and errors);
+    a confidence-interval flag may only differ where the error sits on the interval's edge."""
+    g = GOLD["test"]
+    Q, D, R = g["Q"], g["D"], g["R"]
+    meta, x, y = synth.make_patient(D, g["n"], seed=g["patient_seed"], T=g["T"])
+    for a, b in g["shared"]:
+        x[a] = x[b]
+    cfg = expfiles.write_experiment(top, Q, D, R, g["features"], {"p0": (meta, x, y)},
+                                    online_learn_rate=g["online_learn_rate"])
+    expfiles.write_mode_kernel(top, Q, np.array(g["theta"]))
+    subprocess.run([exe, "--cfg", cfg, "--pan", "p0", "--thread", "1", "--fold", "0", "--kernclust-alg", "None"],
+                   check=True, capture_output=True, text=True, timeout=600, env=env)
+    td = os.path.join(top, "test")
+    for mode, ref in g["modes"].items():
+        assert expfiles.read_int_txt(os.path.join(td, f"test_{mode}_flag_p0.txt")) == ref["flag"]
+        assert expfiles.read_int_txt(os.path.join(td, f"test_{mode}_feature_p0.txt")) == ref["feature"]
+        pred = expfiles.read_double_bin(os.path.join(td, f"test_{mode}_pred_p0.bin"))
+        err = expfiles.read_double_bin(os.path.join(td, f"test_{mode}_error_p0.bin"))
+        etime = expfiles.read_double_bin(os.path.join(td, f"test_{mode}_etime_p0.bin"))
+        assert len(pred) == g["n"] == len(ref["pred"])
+        assert np.abs(pred - np.array(ref["pred"])).max() <= 2e-4
+        assert np.abs(err - np.array(ref["error"])).max() <= 2e-4
+        assert np.array_equal(etime, np.array(ref["etime"]))
+        ci = expfiles.read_int_txt(os.path.join(td, f"test_{mode}_ci_p0.txt"))
+        assert sum(int(a != b) for a, b in zip(ci, ref["ci"])) <= 1 and len(ci) == len(ref["ci"])
+
+
+def test_main_one_test_vs_reference_golden(tmp_path):
+    """the host front-end (on the oracle backend) against the reference's own test executable"""
+    run_test_executable_against_golden(os.path.join(BUILD, "main_one_test"), str(tmp_path))
+    # ... and with the reference's literal one-fit-per-observation procedure
+    run_test_executable_against_golden(os.path.join(BUILD, "main_one_test"), str(tmp_path / "refit"),
+                                       env=dict(os.environ, MEDGP_NO_ONLINE="1"))
+
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+needs_ref = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "main_one_train_orb.o")),
+                               reason="oracle/_ref not built (needs /root/reference once)")
+
+
+def run_reference_binding_checks(suffix, tmp_path, oracle):
+    """The drop-in boundary proven by compilation: the UNMODIFIED reference sources with
+    c_inference_cuda (oracle/ref/c_inference_cuda.{h,cpp}) in place of c_inference_prior, linked
+    against the C ABI (`suffix` = "cuda": libmedgp_cuda.so, "orb": the oracle backend), against
+    the reference's own executables on the same experiment directory."""
+    Q, D, R = 2, 3, 2
+    pats = {"p0": synth.make_patient(D, 90, seed=321)}
+    # "host": this repo's own front-end on the SAME backend as the binding
+    host_dir = os.path.join(ROOT, "medgp_b200", "host") if suffix == "cuda" else BUILD
+    exes = {"ref": os.path.join(REF, "main_one_train.o"), "bind": os.path.join(REF, f"main_one_train_{suffix}.o"),
+            "host": os.path.join(host_dir, "main_one_train")}
+    env = oracle.ref_env()
+    for prior_index, budget in ((0, 12), (2, 1)):
+        kw = dict(prior_index=prior_index, random_init_num=6, top_iteration_num=budget, iteration_num_per_update=10)
+        res = {}
+        for tag, exe in exes.items():
+            top = str(tmp_path / f"{tag}{prior_index}")
+            cfg = expfiles.write_experiment(top, Q, D, R, [1, 3, 4], pats, **kw)
+            subprocess.run([exe, "--cfg", cfg, "--pan", "p0", "--thread", "1"], check=True, capture_output=True,
+                           text=True, timeout=900, env=env)
+            tr = os.path.join(top, "train")
+            res[tag] = dict(init=expfiles.read_double_bin(os.path.join(tr, "train_init_hyp_p0.bin")),
+                            hyp=expfiles.read_double_bin(os.path.join(tr, "train_hyp_p0.bin")),
+                            flag=expfiles.read_int_txt(os.path.join(tr, "train_flag_p0.txt")),
+                            num=expfiles.read_int_txt(os.path.join(tr, "train_num_p0.txt")))
+            if prior_index == 2:
+                res[tag]["var"] = expfiles.read_double_bin(os.path.join(tr, "train_var_hyp_p0.bin"))
+        assert res["bind"]["flag"] == res["ref"]["flag"] == [1] and res["bind"]["num"] == res["ref"]["num"]
+        assert np.array_equal(res["bind"]["init"], res["ref"]["init"])   # same best random initialisation
+        if prior_index == 0:
+            # a 12-evaluation budget: the float reference and the FP64 backend have not diverged yet
+            assert np.abs(res["bind"]["hyp"] - res["ref"]["hyp"]).max() <= 1e-3
+        else:
+            # one variational-EM round = 100 chained evaluations WITH the prior terms: the binding
+            # inside the reference's optimiser walks the path of this repo's host layer on the
+            # same backend (both FP64) ...
+            assert np.abs(res["bind"]["hyp"] - res["host"]["hyp"]).max() <= 1e-5
+            assert np.abs(res["bind"]["var"] - res["host"]["var"]).max() <= 1e-5
+            # ... and reaches the float reference's objective (theta itself is chaotic, SURVEY section 6)
+            m, x, y = expfiles.reload_patient(str(tmp_path / "ref2"), "p0", [1, 3, 4])
+            fb = oracle.nlml_grad(Q, D, R, m, x, y, res["bind"]["hyp"], want_grad=False)[0]
+            fr = oracle.nlml_grad(Q, D, R, m, x, y, res["ref"]["hyp"], want_grad=False)[0]
+            assert abs(fb - fr) <= 0.03 * abs(fr)
+    # single evaluations through the reference's c_objective_one::compute_objective -> binding
+    for c in GOLD["eval"][:4]:
+        meta, x, y = synth.make_patient(c["D"], c["n"], c["seed"])
+        theta = synth.init_hyp_lmc_sm(c["Q"], c["D"], c["R"], 2, seed=c["theta_seed"])[1]
+        path = str(tmp_path / "case.txt")
+        oracle.write_case(path, c["Q"], c["D"], c["R"], meta, x, y, theta)
+        out = subprocess.run([os.path.join(REF, f"ref_eval_{suffix}"), path, "1", "1", "1"], check=True,
+                             capture_output=True, text=True, timeout=600, env=env).stdout
+        r = oracle.parse_ref_output(out)
+        assert r["ok"] and abs(r["nlml"] - c["nlml"]) <= 2e-6 * abs(c["nlml"])
+        gref = np.array(c["grad"])
+        assert np.abs(r["values"] - gref).max() <= 5e-5 * np.abs(gref).max()
+
+
+@needs_ref
+def test_reference_binding_on_oracle_backend(tmp_path, oracle):
+    run_reference_binding_checks("orb", tmp_path, oracle)
+
+
 def test_cohort_test_front_end_writes_what_main_one_test_writes(tmp_path):
     """main_cohort_test (one batched online-imputation call per shard) against main_one_test run
     patient by patient: identical test_mean_wo_update_* files, shards cover every patient."""
