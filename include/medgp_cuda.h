@@ -140,6 +140,39 @@ int medgp_cuda_predict_online(medgp_ctx *ctx, int batch, const int *series_id, c
 int medgp_cuda_debug_matrices(medgp_ctx *ctx, int series_id, const double *theta,
                               double *K, double *L, double *alpha, double *Kinv);
 
+/* ---- Device-resident lock-step optimiser.  Replaces the loop of c_optimizer_scg::optimize
+ * (util/c_optimizer_scg.cpp:25-284: Rasmussen's minimize, Polak-Ribiere CG with cubic /
+ * quadratic line search) for `count` instances at once -- one per (patient, initialisation) --
+ * together with the prior terms of c_inference_prior::compute_nlml
+ * (inference/c_inference_prior.cpp:59-150).  The line-search state of every instance lives in
+ * HBM; one super-step = one batched NLML+gradient evaluation at every live instance's probe
+ * point + one kernel that advances all state machines; theta and gradients never cross PCIe,
+ * the host only polls how many instances still want evaluations.  Control flow is the
+ * reference's, evaluation for evaluation (summation order of the dot products differs). */
+typedef struct medgp_scg medgp_scg;
+int medgp_cuda_scg_create(medgp_ctx *ctx, int count, medgp_scg **out);
+void medgp_cuda_scg_destroy(medgp_scg *scg);
+/* (Re)start every instance: instance b optimises series_id[b] from theta0[b*P..] with budget
+ * max_iteration[b] < 0 = -(function evaluations), the only form MedGP uses (main_one_train.cpp:270-291,
+ * c_optimizer_varEM.cpp:64-69); a budget >= 0 leaves the instance finished at theta0.
+ * Priors, per instance and hyper-parameter in theta order (all three arrays or none):
+ *   prior_type  count*P: -1 none, 0 clamp (gradient forced to 0), 1 normal(p0, VARIANCE p1),
+ *               2 laplace(p0, scale p1)                          (prior/c_prior.cpp:383-421)
+ *   prior_exp   count*P: 1 = the hyper-parameter is stored as a log, d log p gets the factor h
+ *   prior_param count*P*2: (p0, p1) */
+int medgp_cuda_scg_start(medgp_scg *scg, const int *series_id, const double *theta0, const int *max_iteration,
+                         const signed char *prior_type, const signed char *prior_exp, const float *prior_param);
+/* Enqueue `super_steps` super-steps (finished instances are passed over on the device), wait,
+ * and report how many instances still want evaluations. */
+int medgp_cuda_scg_run(medgp_scg *scg, int super_steps, int *active_left);
+/* Best point, its objective (NLML + prior terms) and the evaluations spent, per instance
+ * (opt_parameter / opt_loss of c_optimizer_scg::optimize).  Any pointer may be NULL. */
+int medgp_cuda_scg_result(medgp_scg *scg, double *theta_best, double *loss, int *evals);
+/* Test taps: drive the SAME device state machine with an external objective -- fetch every
+ * instance's probe point (wants[b] = 0 once finished), then feed (f, gradient, ok) for all. */
+int medgp_cuda_scg_points(medgp_scg *scg, double *theta, int *wants);
+int medgp_cuda_scg_feed(medgp_scg *scg, const double *f, const double *grad, const int *ok);
+
 /* Tests of the jitter path: declare the first `attempts` factorisation attempts of every
  * evaluation failed, whatever their pivots (0 = off).  An evaluation then comes back with
  * status == attempts and the values of K + (1 + attempts) sigma^2 -- what the reference computes

@@ -27,6 +27,8 @@ SYMBOLS = [
     "medgp_cuda_sync", "medgp_cuda_predict", "medgp_cuda_predict_online", "medgp_cuda_debug_matrices", "medgp_cuda_debug_force_fail", "medgp_cuda_profile",
     "medgp_cuda_stage_times", "medgp_cuda_malloc", "medgp_cuda_free", "medgp_cuda_memcpy_h2d",
     "medgp_cuda_memcpy_d2h", "medgp_cuda_host_alloc", "medgp_cuda_host_free", "medgp_cuda_stream",
+    "medgp_cuda_scg_create", "medgp_cuda_scg_destroy", "medgp_cuda_scg_start", "medgp_cuda_scg_run",
+    "medgp_cuda_scg_result", "medgp_cuda_scg_points", "medgp_cuda_scg_feed",
 ]
 
 
@@ -86,6 +88,15 @@ def load_library():
     lib.medgp_cuda_host_free.argtypes = [vp, vp]
     lib.medgp_cuda_stream.argtypes = [vp]
     lib.medgp_cuda_stream.restype = vp
+    bp = ctypes.POINTER(ctypes.c_byte)
+    lib.medgp_cuda_scg_create.argtypes = [vp, i, ctypes.POINTER(vp)]
+    lib.medgp_cuda_scg_destroy.argtypes = [vp]
+    lib.medgp_cuda_scg_destroy.restype = None
+    lib.medgp_cuda_scg_start.argtypes = [vp, ip, dp, ip, bp, bp, fp]
+    lib.medgp_cuda_scg_run.argtypes = [vp, i, ip]
+    lib.medgp_cuda_scg_result.argtypes = [vp, dp, dp, ip]
+    lib.medgp_cuda_scg_points.argtypes = [vp, dp, ip]
+    lib.medgp_cuda_scg_feed.argtypes = [vp, dp, dp, ip]
     _lib = lib
     return lib
 
@@ -255,6 +266,10 @@ class Context:
                 out[k] = v
         return out
 
+    def scg_session(self, count):
+        """Device-resident lock-step SCG over `count` instances (medgp_cuda_scg_*)."""
+        return ScgSession(self, count)
+
     def force_fail(self, attempts):
         """Tests of the jitter path: the first `attempts` factorisation attempts count as failed."""
         self._check(self.lib.medgp_cuda_debug_force_fail(self.h, int(attempts)))
@@ -267,3 +282,53 @@ class Context:
         self._check(self.lib.medgp_cuda_stage_times(self.h, ctypes.byref(st), int(reset)))
         return {name: dict(ms=st.ms[i], launches=st.launches[i], flops=st.flops[i], bytes=st.bytes[i])
                 for i, name in enumerate(STAGES)} | {"evals": st.evals}
+
+
+class ScgSession:
+    """Python face of the device-resident optimiser session (include/medgp_cuda.h: medgp_cuda_scg_*)."""
+
+    def __init__(self, ctx, count):
+        self.ctx, self.lib, self.count, self.P = ctx, ctx.lib, int(count), ctx.P
+        self.h = ctypes.c_void_p()
+        ctx._check(self.lib.medgp_cuda_scg_create(ctx.h, self.count, ctypes.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.lib.medgp_cuda_scg_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def start(self, series_ids, theta0, max_iteration, prior_type=None, prior_exp=None, prior_param=None):
+        sids = np.ascontiguousarray(series_ids, dtype=np.int32)
+        theta0 = np.ascontiguousarray(theta0, dtype=np.float64).reshape(self.count, self.P)
+        budget = np.ascontiguousarray(np.broadcast_to(max_iteration, (self.count,)), dtype=np.int32)
+        bp = ctypes.POINTER(ctypes.c_byte)
+        if prior_type is None:
+            pt = pe = pp = None
+        else:
+            prior_type = np.ascontiguousarray(prior_type, dtype=np.int8).reshape(self.count, self.P)
+            prior_exp = np.ascontiguousarray(prior_exp, dtype=np.int8).reshape(self.count, self.P)
+            prior_param = np.ascontiguousarray(prior_param, dtype=np.float32).reshape(self.count, self.P, 2)
+            pt, pe, pp = prior_type.ctypes.data_as(bp), prior_exp.ctypes.data_as(bp), _fp(prior_param)
+        self.ctx._check(self.lib.medgp_cuda_scg_start(self.h, _ip(sids), _dp(theta0), _ip(budget), pt, pe, pp))
+
+    def run(self, super_steps):
+        left = ctypes.c_int(0)
+        self.ctx._check(self.lib.medgp_cuda_scg_run(self.h, int(super_steps), ctypes.byref(left)))
+        return left.value
+
+    def result(self):
+        theta, loss = np.empty((self.count, self.P)), np.empty(self.count)
+        evals = np.empty(self.count, dtype=np.int32)
+        self.ctx._check(self.lib.medgp_cuda_scg_result(self.h, _dp(theta), _dp(loss), _ip(evals)))
+        return theta, loss, evals
+
+    def points(self):
+        theta, wants = np.empty((self.count, self.P)), np.empty(self.count, dtype=np.int32)
+        self.ctx._check(self.lib.medgp_cuda_scg_points(self.h, _dp(theta), _ip(wants)))
+        return theta, wants
+
+    def feed(self, f, grad, ok):
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        grad = np.ascontiguousarray(grad, dtype=np.float64).reshape(self.count, self.P)
+        ok = np.ascontiguousarray(ok, dtype=np.int32)
+        self.ctx._check(self.lib.medgp_cuda_scg_feed(self.h, _dp(f), _dp(grad), _ip(ok)))

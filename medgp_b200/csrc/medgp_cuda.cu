@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "cov.cuh"
 #include "linalg.cuh"
+#include "scg.cuh"
 
 #define MEDGP_API extern "C" __attribute__((visibility("default")))
 
@@ -87,6 +88,7 @@ struct medgp_ctx {
     size_t desc_cap = 0;
     int *d_tickets = nullptr;  // 8 sub-chunk streams x kTicketsPerSub
     bool device_retry = true;  // MEDGP_DEVICE_RETRY=0: jitter retries are driven by the host instead of the graph's WHILE node
+    const int *ext_skip = nullptr;  // device flags by out_index (optimiser sessions): 1 = pass over this evaluation
     bool retry_on_device = false;  // set by run_batch: the last chunk sequence carried its own jitter loop
     int force_fail = 0;        // medgp_cuda_debug_force_fail: the first attempts of every evaluation are declared failed
     uint64_t graph_clock = 0;
@@ -592,6 +594,8 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         // ---- issue: a CUDA graph per chunk structure (captured once, replayed afterwards) keeps
         //      the CPU out of the way -- a step is hundreds of launches over several streams
         auto issue_all = [&]() -> int {
+            if (ctx->ext_skip)  // optimiser session: retire the descriptors of finished instances first
+                k_apply_skip<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(ctx->d_descs + dpos, (int)cnt, ctx->ext_skip);
             std::vector<LaunchList> prog(S);
             for (int sidx = 0; sidx < S; sidx++)
                 build_sub(ctx, subs[sidx], rl, fold, S == 1 ? st : ctx->sub_streams[sidx], d_theta, mode, d_nlml,
@@ -629,7 +633,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
             mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)ctx->stagger_us); mix(ctx->chain_diag); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
             mix((uint64_t)(uintptr_t)d_theta); mix((uint64_t)(uintptr_t)d_nlml); mix((uint64_t)(uintptr_t)d_grad);
             mix((uint64_t)(uintptr_t)d_status); mix((uint64_t)(uintptr_t)d_mean); mix((uint64_t)(uintptr_t)d_var);
-            mix((uint64_t)(uintptr_t)ctx->d_fail);
+            mix((uint64_t)(uintptr_t)ctx->d_fail); mix((uint64_t)(uintptr_t)ctx->ext_skip);
             // the launches bake in the model (ModelDims by value, Q-templated kernels, smem sizes)
             mix((uint64_t)md.Q); mix((uint64_t)md.D); mix((uint64_t)md.R); mix((uint64_t)md.P); mix((uint64_t)md.parLen);
             { uint64_t pib; memcpy(&pib, &md.pi, 8); mix(pib); }
@@ -1360,6 +1364,215 @@ MEDGP_API int medgp_cuda_debug_matrices(medgp_ctx *ctx, int series_id, const dou
         }
     }
     return MEDGP_OK;
+}
+
+
+// ======================================================================= optimiser sessions
+struct medgp_scg {
+    medgp_ctx *ctx = nullptr;
+    ScgSession S{};
+    std::vector<int> series;
+    signed char *d_ptype = nullptr, *d_pexp = nullptr;
+    float *d_ppar = nullptr;
+    int *h_active = nullptr;  // pinned
+    bool started = false;
+};
+
+MEDGP_API int medgp_cuda_scg_create(medgp_ctx *ctx, int count, medgp_scg **out)
+{
+    if (!ctx || !ctx->model_set || count < 1 || !out) {
+        if (ctx) ctx->err = "scg_create: bad argument or model not set";
+        return MEDGP_ERR_ARG;
+    }
+    cudaSetDevice(ctx->device);
+    medgp_scg *g = new medgp_scg();
+    g->ctx = ctx;
+    const size_t P = ctx->md.P, n = (size_t)count;
+    g->S.count = count;
+    g->S.P = (int)P;
+    bool ok = cudaMalloc(&g->S.sc, n * sizeof(ScgScalars)) == cudaSuccess &&
+              cudaMalloc(&g->S.vec, n * SCG_NVEC * P * 8) == cudaSuccess &&
+              cudaMalloc(&g->S.theta, n * P * 8) == cudaSuccess && cudaMalloc(&g->S.nlml, n * 8) == cudaSuccess &&
+              cudaMalloc(&g->S.grad, n * P * 8) == cudaSuccess && cudaMalloc(&g->S.status, n * sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&g->S.skip, n * sizeof(int)) == cudaSuccess && cudaMalloc(&g->S.active, sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&g->d_ptype, n * P) == cudaSuccess && cudaMalloc(&g->d_pexp, n * P) == cudaSuccess &&
+              cudaMalloc(&g->d_ppar, n * P * 2 * sizeof(float)) == cudaSuccess &&
+              cudaMallocHost(&g->h_active, sizeof(int)) == cudaSuccess;
+    if (!ok) {
+        ctx->err = "scg_create: out of memory";
+        medgp_cuda_scg_destroy(g);
+        return MEDGP_ERR_NOMEM;
+    }
+    *out = g;
+    return MEDGP_OK;
+}
+
+MEDGP_API void medgp_cuda_scg_destroy(medgp_scg *g)
+{
+    if (!g) return;
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
+    cudaFree(g->S.sc); cudaFree(g->S.vec); cudaFree(g->S.theta); cudaFree(g->S.nlml); cudaFree(g->S.grad);
+    cudaFree(g->S.status); cudaFree(g->S.skip); cudaFree(g->S.active);
+    cudaFree(g->d_ptype); cudaFree(g->d_pexp); cudaFree(g->d_ppar);
+    if (g->h_active) cudaFreeHost(g->h_active);
+    delete g;
+}
+
+MEDGP_API int medgp_cuda_scg_start(medgp_scg *g, const int *series_id, const double *theta0, const int *max_iteration,
+                                   const signed char *prior_type, const signed char *prior_exp, const float *prior_param)
+{
+    if (!g || !series_id || !theta0 || !max_iteration || ((prior_type != nullptr) != (prior_param != nullptr)) ||
+        ((prior_type != nullptr) != (prior_exp != nullptr))) {
+        if (g) g->ctx->err = "scg_start: bad argument";
+        return MEDGP_ERR_ARG;
+    }
+    medgp_ctx *ctx = g->ctx;
+    cudaSetDevice(ctx->device);
+    const int count = g->S.count;
+    const size_t P = ctx->md.P;
+    int rc = check_series_ids(ctx, count, series_id);
+    if (rc) return rc;
+    for (int b = 0; b < count; b++) {
+        if (ctx->series[series_id[b]].time_order) {
+            ctx->err = "scg_start: gradients need a feature-ordered series (medgp_cuda_add_series)";
+            return MEDGP_ERR_ARG;
+        }
+        if (prior_type)
+            for (size_t k = 0; k < P; k++) {
+                const int t = prior_type[(size_t)b * P + k];
+                if (t < -1 || t > 2) {
+                    ctx->err = "scg_start: prior types -1 (none), 0 (clamp), 1 (normal), 2 (laplace) run on the device";
+                    return MEDGP_ERR_ARG;
+                }
+            }
+    }
+    cudaStream_t st = ctx->stream;
+    CU(cudaStreamSynchronize(st));  // the staging buffers below are plain temporaries
+    g->series.assign(series_id, series_id + count);
+    double *d_theta0 = nullptr;
+    int *d_len = nullptr;
+    CU(cudaMalloc(&d_theta0, (size_t)count * P * 8));
+    CU(cudaMalloc(&d_len, (size_t)count * sizeof(int)));
+    CU(cudaMemcpyAsync(d_theta0, theta0, (size_t)count * P * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_len, max_iteration, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (prior_type) {
+        CU(cudaMemcpyAsync(g->d_ptype, prior_type, (size_t)count * P, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(g->d_pexp, prior_exp, (size_t)count * P, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(g->d_ppar, prior_param, (size_t)count * P * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+        g->S.ptype = g->d_ptype; g->S.pexp = g->d_pexp; g->S.ppar = g->d_ppar;
+    } else {
+        g->S.ptype = nullptr; g->S.pexp = nullptr; g->S.ppar = nullptr;
+    }
+    k_scg_start<<<count, MEDGP_SCG_THREADS, 0, st>>>(g->S, d_theta0, d_len);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    cudaFree(d_theta0);
+    cudaFree(d_len);
+    g->started = true;
+    return MEDGP_OK;
+}
+
+// the tail of a super-step (and of the test tap): advance every live instance
+static int scg_advance(medgp_scg *g)
+{
+    medgp_ctx *ctx = g->ctx;
+    k_scg_advance<<<g->S.count, MEDGP_SCG_THREADS, 0, ctx->stream>>>(g->S, ctx->md);
+    CU(cudaGetLastError());
+    return MEDGP_OK;
+}
+
+static int scg_count_active(medgp_scg *g, int *active_left)
+{
+    medgp_ctx *ctx = g->ctx;
+    k_scg_count<<<1, 256, 0, ctx->stream>>>(g->S);
+    CU(cudaMemcpyAsync(g->h_active, g->S.active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    resolve_marks(ctx);
+    if (active_left) *active_left = *g->h_active;
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_scg_run(medgp_scg *g, int super_steps, int *active_left)
+{
+    if (!g || !g->started || super_steps < 0) {
+        if (g) g->ctx->err = "scg_run: session not started";
+        return MEDGP_ERR_ARG;
+    }
+    medgp_ctx *ctx = g->ctx;
+    cudaSetDevice(ctx->device);
+    const int count = g->S.count;
+    std::vector<Request> reqs(count);
+    for (int b = 0; b < count; b++) reqs[b] = {g->series[b], b, 0, 0, 0};
+    for (int step = 0; step < super_steps; step++) {
+        int rc = ensure_staging(ctx, count, 0);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(ctx->d_fail, 0, count * sizeof(int), ctx->stream));
+        ctx->ext_skip = g->S.skip;
+        rc = run_batch(ctx, reqs, g->S.theta, 1, g->S.nlml, g->S.grad, g->S.status, nullptr, nullptr, 0);
+        if (rc == MEDGP_OK && !ctx->retry_on_device)
+            rc = host_retry_rounds(ctx, reqs, count, g->S.theta, 1, g->S.nlml, g->S.grad, g->S.status, nullptr, nullptr);
+        ctx->ext_skip = nullptr;
+        if (rc) return rc;
+        rc = release_desc_slot(ctx);
+        if (rc) return rc;
+        rc = scg_advance(g);
+        if (rc) return rc;
+    }
+    return scg_count_active(g, active_left);
+}
+
+MEDGP_API int medgp_cuda_scg_result(medgp_scg *g, double *theta_best, double *loss, int *evals)
+{
+    if (!g || !g->started) return MEDGP_ERR_ARG;
+    medgp_ctx *ctx = g->ctx;
+    cudaSetDevice(ctx->device);
+    const int count = g->S.count;
+    const size_t P = ctx->md.P;
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<ScgScalars> sc(count);
+    CU(cudaMemcpy(sc.data(), g->S.sc, (size_t)count * sizeof(ScgScalars), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < count; b++) {
+        if (loss) loss[b] = sc[b].fX;
+        if (evals) evals[b] = sc[b].n_eval;
+    }
+    if (theta_best)
+        CU(cudaMemcpy2D(theta_best, P * 8, g->S.vec + SCG_X * P, SCG_NVEC * P * 8, P * 8, count, cudaMemcpyDeviceToHost));
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_scg_points(medgp_scg *g, double *theta, int *wants)
+{
+    if (!g || !g->started) return MEDGP_ERR_ARG;
+    medgp_ctx *ctx = g->ctx;
+    cudaSetDevice(ctx->device);
+    const int count = g->S.count;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (theta) CU(cudaMemcpy(theta, g->S.theta, (size_t)count * ctx->md.P * 8, cudaMemcpyDeviceToHost));
+    if (wants) {
+        std::vector<int> skip(count);
+        CU(cudaMemcpy(skip.data(), g->S.skip, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int b = 0; b < count; b++) wants[b] = skip[b] ? 0 : 1;
+    }
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_scg_feed(medgp_scg *g, const double *f, const double *grad, const int *ok)
+{
+    if (!g || !g->started || !f || !grad || !ok) return MEDGP_ERR_ARG;
+    medgp_ctx *ctx = g->ctx;
+    cudaSetDevice(ctx->device);
+    const int count = g->S.count;
+    const size_t P = ctx->md.P;
+    std::vector<int> status(count);
+    for (int b = 0; b < count; b++) status[b] = ok[b] ? 0 : -1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(g->S.nlml, f, (size_t)count * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g->S.grad, grad, (size_t)count * P * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g->S.status, status.data(), (size_t)count * sizeof(int), cudaMemcpyHostToDevice));
+    int rc = scg_advance(g);
+    if (rc) return rc;
+    return scg_count_active(g, nullptr);
 }
 
 MEDGP_API int medgp_cuda_debug_force_fail(medgp_ctx *ctx, int attempts)

@@ -1,10 +1,13 @@
 // main_cohort_train -- train a whole cohort (or one shard of it) on one GPU in lock-step.
 //   main_cohort_train --cfg exp_setup.json --pans <file with one PAN per line>
-//                     [--device d] [--shard i/N] [--max-evals E]
+//                     [--device d] [--shard i/N] [--host-optimizer] [--max-evals E]
 // Per patient this produces exactly the files main_one_train writes and
 // follows the same procedure (score random_init_num random initialisations, optimise the best
-// with SCG or variational EM), but every optimiser super-step evaluates ALL active patients
-// with one batched library call.  The reference deploys one job per patient
+// with SCG or variational EM), but every optimiser super-step evaluates ALL active patients at
+// once, and the line searches themselves run ON THE DEVICE (medgp_cuda_scg_*: one state machine
+// per patient in HBM, theta never crosses PCIe; the host keeps the variational-EM rounds).
+// --host-optimizer selects the older path: host steppers, one batched library call (theta up,
+// gradients down) per super-step.  The reference deploys one job per patient
 // (medgpc/util/run_exp_generator.py:213-260); sharding here is the same idea per GPU:
 // patients are dealt to shards by descending n^3 (LPT), and shards never communicate.
 #include <algorithm>
@@ -53,18 +56,20 @@ int main(int argc, const char *argv[])
     string exp_cfg, pan_file;
     int device = 0, shard = 0, nshard = 1;
     long max_evals = -1;
+    bool host_optimizer = false;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--cfg") && i + 1 < argc) exp_cfg = argv[++i];
         else if (!strcmp(argv[i], "--pans") && i + 1 < argc) pan_file = argv[++i];
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--max-evals") && i + 1 < argc) max_evals = atol(argv[++i]);
+        else if (!strcmp(argv[i], "--host-optimizer")) host_optimizer = true;
         else if (!strcmp(argv[i], "--shard") && i + 1 < argc) {
             if (sscanf(argv[++i], "%d/%d", &shard, &nshard) != 2 || nshard < 1 || shard < 0 || shard >= nshard) {
                 cout << "Error: --shard expects i/N" << endl;
                 return 1;
             }
         } else {
-            cout << "usage: main_cohort_train --cfg exp_setup.json --pans list.txt [--device d] [--shard i/N] [--max-evals E]" << endl;
+            cout << "usage: main_cohort_train --cfg exp_setup.json --pans list.txt [--device d] [--shard i/N] [--host-optimizer] [--max-evals E]" << endl;
             return 1;
         }
     }
@@ -168,7 +173,29 @@ int main(int argc, const char *argv[])
         p->active = true;
     }
     long grad_evals = 0, super_steps = 0;
-    while (true) {
+    std::vector<medgp_opt_instance> inst;
+    std::vector<Patient *> inst_owner;
+    for (Patient *p : mine)
+        if (p->active) {
+            medgp_opt_instance it;
+            it.series_id = p->series_id;
+            it.init_parameter = p->best_init;
+            it.prior = p->prior.get();
+            it.use_varem = p->use_vem;
+            it.max_iteration = -curr_exp.get_scg_max_iter_num();
+            it.sub_opt_iter = curr_exp.get_prior_sub_opt_iter();
+            inst.push_back(it);
+            inst_owner.push_back(p);
+        }
+    const bool on_device = !host_optimizer && max_evals < 0 && medgp_device_optimizer_supports(inst);
+    if (on_device) {
+        super_steps = medgp_optimize_on_device(ctx, kp, n_lik, inst);
+        for (size_t k = 0; k < inst.size(); k++) {
+            inst_owner[k]->opt_parameter = inst[k].opt_parameter;
+            grad_evals += inst[k].evals;
+        }
+    } else {
+      while (true) {
         vector<medgp_eval_request> reqs;
         vector<Patient *> owner;
         for (Patient *p : mine)
@@ -184,15 +211,16 @@ int main(int argc, const char *argv[])
         for (long q = 0; q < (long)reqs.size(); q++) owner[q]->feed(res[q].ok, res[q].value, res[q].grad);
         grad_evals += (long)reqs.size();
         super_steps++;
+      }
     }
     const double dtB = now_s() - tB;
-    cout << "phase B (optimisation): " << grad_evals << " NLML+gradient evaluations in " << super_steps
+    cout << "phase B (optimisation, " << (on_device ? "device-resident" : "host") << " line searches): " << grad_evals << " NLML+gradient evaluations in " << super_steps
          << " super-steps, " << dtB << " s (" << (dtB > 0 ? grad_evals / dtB : 0.0) << " evals/s)" << endl;
     // ---- outputs
     for (Patient *p : mine) {
         bool flag = false;
         if (p->enough && p->success) {
-            p->opt_parameter = p->use_vem ? p->vem.best_parameter() : p->scg.best_parameter();
+            if (!on_device) p->opt_parameter = p->use_vem ? p->vem.best_parameter() : p->scg.best_parameter();
             curr_exp.output_double_bin(curr_exp.get_exp_train_dir() + "train_hyp_" + p->pan, p->opt_parameter);
             if (p->use_vem)
                 curr_exp.output_double_bin(curr_exp.get_exp_train_dir() + "train_var_hyp_" + p->pan, p->prior->get_cov_varEM_all());

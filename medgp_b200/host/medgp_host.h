@@ -451,32 +451,80 @@ class c_optimizer_scg : public c_optimizer {
 
 #define DEFAULT_SCG_MAX_ITER 80
 
-// Re-entrant variational EM for the hierarchical-gamma sparse prior on A
-// (util/c_optimizer_varEM.cpp:60-162): SCG with 100 evaluations for the first 5 rounds, then
-// sub_opt_iter; closed-form tau, phi, delta, psi updates; 0.5 % early stop.  It owns nothing:
-// it mutates the c_prior it is given, exactly as the reference does.
-class varem_stepper {
+// Outer loop of the variational EM for the hierarchical-gamma sparse prior on A
+// (util/c_optimizer_varEM.cpp:60-162), without the inner optimiser: budget() is the SCG budget
+// of the coming round (100 evaluations for the first 5 rounds, then sub_opt_iter, as a negative
+// max_iteration), start() the point it starts from, finish_round() takes the inner optimiser's
+// result, applies the 0.5 % early stop and the closed-form tau, phi, delta, psi updates, prunes
+// the A entries whose psi hits 0, and reports whether another round follows.  It owns nothing:
+// it mutates the c_prior it is given, exactly as the reference does.  Whoever runs the inner
+// SCG -- the host stepper below or the device-resident session (medgp_cuda_scg_*) -- shares it.
+class varem_rounds {
   public:
-    varem_stepper() : prior(nullptr), done_(true) {}
-    varem_stepper(int max_iteration, const std::vector<double> &init_parameter, int sub_opt_iter,
-                  const std::vector<int> &kernel_param, int lik_num, c_prior *prior);
-    bool wants_eval() const { return !done_; }
-    const std::vector<double> &point() const { return scg.point(); }
-    void feed(bool ok, double f, const std::vector<double> &g);
+    varem_rounds() : prior(nullptr), done_(true) {}
+    varem_rounds(int max_iteration, const std::vector<double> &init_parameter, int sub_opt_iter,
+                 const std::vector<int> &kernel_param, int lik_num, c_prior *prior);
+    bool done() const { return done_; }
+    int budget() const { return -(iter < 5 ? 100 : sub_opt_iter); }
+    const std::vector<double> &start() const { return opt_parameter; }
+    void finish_round(double loss, const std::vector<double> &parameter);
     const std::vector<double> &best_parameter() const { return opt_parameter; }
     double best_loss() const { return opt_loss; }
     int rounds() const { return iter; }
 
   private:
-    void start_round();
-    void end_round();
-    scg_stepper scg;
     c_prior *prior;
     bool done_;
     int max_iter, iter, sub_opt_iter, Q, D, R, lik_num;
     double opt_loss, best_loss_;
     std::vector<double> opt_parameter;
 };
+
+// Re-entrant variational EM: varem_rounds around the host SCG stepper.
+class varem_stepper {
+  public:
+    varem_stepper() {}
+    varem_stepper(int max_iteration, const std::vector<double> &init_parameter, int sub_opt_iter,
+                  const std::vector<int> &kernel_param, int lik_num, c_prior *prior);
+    bool wants_eval() const { return !outer.done(); }
+    const std::vector<double> &point() const { return scg.point(); }
+    void feed(bool ok, double f, const std::vector<double> &g);
+    const std::vector<double> &best_parameter() const { return outer.best_parameter(); }
+    double best_loss() const { return outer.best_loss(); }
+    int rounds() const { return outer.rounds(); }
+
+  private:
+    scg_stepper scg;
+    varem_rounds outer;
+};
+
+// ------------------------------------------------------------------------------------------
+// Device-resident lock-step optimisation of many instances (one per patient): the SCG line
+// searches run inside libmedgp_cuda.so (medgp_cuda_scg_*: state in HBM, theta never crosses
+// PCIe); this driver owns what the reference keeps on the host between SCG runs -- the
+// variational-EM rounds and their prior-table updates (c_optimizer_varEM.cpp:60-162).
+struct medgp_opt_instance {
+    int series_id = -1;
+    std::vector<double> init_parameter;
+    c_prior *prior = nullptr;     // may be null (no prior terms)
+    bool use_varem = false;       // prior mode 2: variational EM around SCG; else plain SCG
+    int max_iteration = 0;        // as passed to c_optimizer_*::optimize (negative: evaluation budget / EM rounds)
+    int sub_opt_iter = DEFAULT_SCG_MAX_ITER;
+    // results
+    std::vector<double> opt_parameter;
+    double opt_loss = 0.0;
+    long evals = 0;
+};
+// External objective for tests (drives the device state machine through the session's taps
+// instead of the GPU evaluation): returns ok, fills f and g for instance `index` at point x.
+typedef bool (*medgp_external_objective)(int index, const std::vector<double> &x, double &f, std::vector<double> &g, void *user);
+// true when every instance's prior table can run on the device (no kde prior)
+bool medgp_device_optimizer_supports(const std::vector<medgp_opt_instance> &inst);
+// Runs all instances to completion; returns the number of super-steps.  poll_every: super-steps
+// enqueued between two "anyone left?" polls.
+long medgp_optimize_on_device(medgp_ctx *ctx, const std::vector<int> &kernel_param, int lik_num,
+                              std::vector<medgp_opt_instance> &inst, int poll_every = 16,
+                              medgp_external_objective external = nullptr, void *user = nullptr);
 
 class c_optimizer_varEM : public c_optimizer {
   public:

@@ -261,8 +261,8 @@ double c_optimizer_varEM::update_psi(const float &alpha, const double &a, const 
     return (sub + sqrt(sub * sub + 8.0 * delta * a * a)) / (4.0 * delta);
 }
 
-varem_stepper::varem_stepper(int max_iteration, const vector<double> &init_parameter, int sub_iter,
-                             const vector<int> &kernel_param, int lik_num_, c_prior *prior_)
+varem_rounds::varem_rounds(int max_iteration, const vector<double> &init_parameter, int sub_iter,
+                           const vector<int> &kernel_param, int lik_num_, c_prior *prior_)
     : prior(prior_), done_(false), max_iter(std::abs(max_iteration)), iter(0), sub_opt_iter(sub_iter),
       lik_num(lik_num_), opt_loss(0.0), best_loss_(0.0), opt_parameter(init_parameter)
 {
@@ -272,25 +272,12 @@ varem_stepper::varem_stepper(int max_iteration, const vector<double> &init_param
     }
     Q = kernel_param[0]; D = kernel_param[1]; R = kernel_param[2];
     if (max_iter == 0) done_ = true;
-    else start_round();
 }
 
-void varem_stepper::start_round()
+void varem_rounds::finish_round(double loss, const vector<double> &parameter)
 {
-    const int evals = iter < 5 ? 100 : sub_opt_iter;  // c_optimizer_varEM.cpp:64-69
-    scg = scg_stepper(-evals, opt_parameter);
-}
-
-void varem_stepper::feed(bool ok, double f, const vector<double> &g)
-{
-    scg.feed(ok, f, g);
-    if (!scg.wants_eval()) end_round();
-}
-
-void varem_stepper::end_round()
-{
-    opt_loss = scg.best_loss();
-    opt_parameter = scg.best_parameter();
+    opt_loss = loss;
+    opt_parameter = parameter;
     if (iter > 0) {
         const double change_ratio = (opt_loss - best_loss_) / best_loss_;
         if (fabs(change_ratio) < 0.005) {  // early stop (c_optimizer_varEM.cpp:89-95)
@@ -340,8 +327,182 @@ void varem_stepper::end_round()
                 prior->fix_param_cov[index][1] = prior->get_cov_varEM_one(index);
             }
     iter++;
-    if (iter < max_iter) start_round();
-    else done_ = true;
+    if (iter >= max_iter) done_ = true;
+}
+
+varem_stepper::varem_stepper(int max_iteration, const vector<double> &init_parameter, int sub_iter,
+                             const vector<int> &kernel_param, int lik_num, c_prior *prior)
+    : outer(max_iteration, init_parameter, sub_iter, kernel_param, lik_num, prior)
+{
+    if (!outer.done()) scg = scg_stepper(outer.budget(), outer.start());
+}
+
+void varem_stepper::feed(bool ok, double f, const vector<double> &g)
+{
+    scg.feed(ok, f, g);
+    if (scg.wants_eval()) return;
+    outer.finish_round(scg.best_loss(), scg.best_parameter());
+    if (!outer.done()) scg = scg_stepper(outer.budget(), outer.start());
+}
+
+// ------------------------------------------------------------------ device-resident lock-step optimisation
+namespace {
+// prior table of one instance in theta order [lik | cov] as the session wants it
+bool prior_table(const c_prior *prior, int n_lik, int P, signed char *type, signed char *is_exp, float *param)
+{
+    for (int k = 0; k < P; k++) {
+        type[k] = -1; is_exp[k] = 0; param[2 * k] = 0.f; param[2 * k + 1] = 1.f;
+    }
+    if (!prior) return true;
+    for (int k = 0; k < P; k++) {
+        const bool lik = k < n_lik;
+        const int i = lik ? k : k - n_lik;
+        const bool flag = lik ? prior->flag_lik[i] : prior->flag_cov[i];
+        if (!flag) continue;
+        const int t = lik ? prior->type_lik[i] : prior->type_cov[i];
+        if (t > 2) return false;  // kde: not on the device
+        // an active entry of type -1 changes nothing (c_inference_prior.cpp:106-108; one_lik returns zeros)
+        type[k] = (signed char)(t < 0 ? -1 : t);
+        is_exp[k] = (lik ? prior->exp_lik[i] : prior->exp_cov[i]) ? 1 : 0;
+        const std::vector<float> &fp = lik ? prior->fix_param_lik[i] : prior->fix_param_cov[i];
+        if (t >= 1 && fp.size() < 2) return false;
+        if (fp.size() >= 2) { param[2 * k] = fp[0]; param[2 * k + 1] = fp[1]; }
+    }
+    return true;
+}
+
+void die_opt(const char *what, medgp_ctx *ctx, int rc)
+{
+    std::cerr << "ERROR: " << what << " failed with status " << rc << " (" << medgp_cuda_last_error(ctx)
+              << "); libmedgp_cuda.so has no CPU fallback" << std::endl;
+    exit(1);
+}
+}  // namespace
+
+bool medgp_device_optimizer_supports(const std::vector<medgp_opt_instance> &inst)
+{
+    for (const auto &it : inst) {
+        if (!it.prior) continue;
+        for (size_t i = 0; i < it.prior->type_lik.size(); i++)
+            if (it.prior->flag_lik[i] && it.prior->type_lik[i] > 2) return false;
+        for (size_t i = 0; i < it.prior->type_cov.size(); i++)
+            if (it.prior->flag_cov[i] && it.prior->type_cov[i] > 2) return false;
+    }
+    return true;
+}
+
+long medgp_optimize_on_device(medgp_ctx *ctx, const vector<int> &kernel_param, int lik_num,
+                              std::vector<medgp_opt_instance> &inst, int poll_every,
+                              medgp_external_objective external, void *user)
+{
+    const int P = medgp_cuda_num_hyp(ctx);
+    long super_steps = 0;
+    // outer state: plain SCG = one "round" with the whole budget
+    std::vector<varem_rounds> outer(inst.size());
+    std::vector<char> live(inst.size(), 0);
+    for (size_t k = 0; k < inst.size(); k++) {
+        medgp_opt_instance &it = inst[k];
+        it.opt_parameter = it.init_parameter;
+        it.opt_loss = NAN;
+        it.evals = 0;
+        if (it.use_varem) {
+            outer[k] = varem_rounds(it.max_iteration, it.init_parameter, it.sub_opt_iter, kernel_param, lik_num, it.prior);
+            live[k] = outer[k].done() ? 0 : 1;
+        } else {
+            live[k] = it.max_iteration < 0 ? 1 : 0;
+            if (it.max_iteration > 0)
+                std::cout << "ERROR: c_optimizer_scg needs a negative max_iteration (function-evaluation budget); got "
+                          << it.max_iteration << std::endl;
+        }
+    }
+    while (true) {
+        // ---- the instances of this round
+        std::vector<int> who;
+        for (size_t k = 0; k < inst.size(); k++)
+            if (live[k]) who.push_back((int)k);
+        if (who.empty()) break;
+        const int count = (int)who.size();
+        std::vector<int> sids(count), budget(count);
+        std::vector<double> theta0((size_t)count * P);
+        std::vector<signed char> ptype((size_t)count * P), pexp((size_t)count * P);
+        std::vector<float> ppar((size_t)count * P * 2);
+        bool any_prior = false;
+        for (int b = 0; b < count; b++) {
+            medgp_opt_instance &it = inst[who[b]];
+            sids[b] = it.series_id;
+            budget[b] = it.use_varem ? outer[who[b]].budget() : it.max_iteration;
+            const vector<double> &x0 = it.use_varem ? outer[who[b]].start() : it.init_parameter;
+            std::copy(x0.begin(), x0.end(), theta0.begin() + (size_t)b * P);
+            if (!prior_table(it.prior, lik_num, P, &ptype[(size_t)b * P], &pexp[(size_t)b * P], &ppar[(size_t)b * P * 2])) {
+                std::cerr << "ERROR: this prior table cannot run on the device (kde prior); use the host optimisers" << std::endl;
+                exit(1);
+            }
+            // an external objective (tests) owns its prior terms, as a c_objective does in the reference
+            any_prior = any_prior || (it.prior != nullptr && !external);
+        }
+        medgp_scg *scg = nullptr;
+        int rc = medgp_cuda_scg_create(ctx, count, &scg);
+        if (rc != MEDGP_OK) die_opt("medgp_cuda_scg_create", ctx, rc);
+        rc = medgp_cuda_scg_start(scg, sids.data(), theta0.data(), budget.data(), any_prior ? ptype.data() : nullptr,
+                                  any_prior ? pexp.data() : nullptr, any_prior ? ppar.data() : nullptr);
+        if (rc != MEDGP_OK) die_opt("medgp_cuda_scg_start", ctx, rc);
+        // ---- run the round to completion
+        if (!external) {
+            int left = count;
+            while (left > 0) {
+                rc = medgp_cuda_scg_run(scg, poll_every, &left);
+                if (rc != MEDGP_OK) die_opt("medgp_cuda_scg_run", ctx, rc);
+                super_steps += poll_every;
+            }
+        } else {  // tests: the same device state machine on an external objective
+            std::vector<double> pts((size_t)count * P), f(count), g((size_t)count * P);
+            std::vector<int> wants(count), ok(count);
+            while (true) {
+                rc = medgp_cuda_scg_points(scg, pts.data(), wants.data());
+                if (rc != MEDGP_OK) die_opt("medgp_cuda_scg_points", ctx, rc);
+                bool any = false;
+                for (int b = 0; b < count; b++) {
+                    ok[b] = 0;
+                    if (!wants[b]) continue;
+                    any = true;
+                    vector<double> x(pts.begin() + (size_t)b * P, pts.begin() + (size_t)(b + 1) * P), gg;
+                    double ff = 0.0;
+                    ok[b] = external(who[b], x, ff, gg, user) ? 1 : 0;
+                    if (ok[b]) {
+                        f[b] = ff;
+                        std::copy(gg.begin(), gg.end(), g.begin() + (size_t)b * P);
+                    }
+                }
+                if (!any) break;
+                rc = medgp_cuda_scg_feed(scg, f.data(), g.data(), ok.data());
+                if (rc != MEDGP_OK) die_opt("medgp_cuda_scg_feed", ctx, rc);
+                super_steps++;
+            }
+        }
+        // ---- results, EM updates
+        std::vector<double> best((size_t)count * P), loss(count);
+        std::vector<int> evals(count);
+        rc = medgp_cuda_scg_result(scg, best.data(), loss.data(), evals.data());
+        if (rc != MEDGP_OK) die_opt("medgp_cuda_scg_result", ctx, rc);
+        medgp_cuda_scg_destroy(scg);
+        for (int b = 0; b < count; b++) {
+            medgp_opt_instance &it = inst[who[b]];
+            const vector<double> x(best.begin() + (size_t)b * P, best.begin() + (size_t)(b + 1) * P);
+            it.evals += evals[b];
+            if (it.use_varem) {
+                varem_rounds &o = outer[who[b]];
+                o.finish_round(loss[b], x);
+                it.opt_parameter = o.best_parameter();
+                it.opt_loss = o.best_loss();
+                live[who[b]] = o.done() ? 0 : 1;
+            } else {
+                it.opt_parameter = x;
+                it.opt_loss = loss[b];
+                live[who[b]] = 0;
+            }
+        }
+    }
+    return super_steps;
 }
 
 void c_optimizer_varEM::optimize(const int &max_iteration, const vector<double> &init_parameter,

@@ -2,6 +2,7 @@
 // format as oracle/ref/ref_scg.cpp so tests can diff the two.
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 #include "../../medgp_b200/host/c_experiment.h"
@@ -52,6 +53,67 @@ int main(int argc, char **argv)
         vector<double> ve = prior.get_cov_varEM_all();
         for (size_t i = 0; i < ve.size(); i++) printf("v %.17g\n", ve[i]);
         for (int i = 0; i < ncov; i++) printf("t %d\n", prior.type_cov[i]);
+    } else if (!strcmp(argv[1], "dscg") || !strcmp(argv[1], "dvarem")) {
+        // the DEVICE-resident optimiser (medgp_cuda_scg_*: state machine in HBM) on the analytic
+        // objective, driven through the session's taps by medgp_optimize_on_device; same output
+        // format as "scg" / "varem".  The model only fixes P: unused trailing coordinates get a
+        // zero gradient, which leaves every dot product -- and so the trajectory -- unchanged.
+        const bool vem = !strcmp(argv[1], "dvarem");
+        const int iters = atoi(argv[2]);
+        int sub = 0, a0 = 3;
+        vector<int> kp = {1, 2, 1};
+        vector<float> ph = {0.01f, 0.01f};
+        if (vem) {
+            sub = atoi(argv[3]);
+            kp = {atoi(argv[4]), atoi(argv[5]), atoi(argv[6])};
+            ph = {(float)atof(argv[7]), (float)atof(argv[8])};
+            a0 = 9;
+        }
+        vector<double> x0;
+        for (int i = a0; i < argc; i++) x0.push_back(atof(argv[i]));
+        const int Q = kp[0], D = kp[1], R = kp[2], ncov = Q * (D * R + 2 + D);
+        medgp_ctx *ctx = medgp_backend::context(Q, D, R);
+        const int P = medgp_cuda_num_hyp(ctx);
+        if ((int)x0.size() > P) { printf("error: x0 longer than P\n"); return 2; }
+        struct user_t { size_t n; int calls; } user = {x0.size(), 0};
+        c_prior prior(ncov, 0, D);
+        if (vem) prior.setup_param(7, kp, 2, ph);
+        // two identical instances: the batch must advance them independently and identically
+        std::vector<medgp_opt_instance> inst(2);
+        for (auto &it : inst) {
+            it.series_id = 0;
+            it.init_parameter = x0;
+            it.init_parameter.resize(P, 0.0);
+            it.prior = vem ? &prior : nullptr;
+            it.use_varem = vem;
+            it.max_iteration = iters;
+            it.sub_opt_iter = sub;
+        }
+        c_prior prior2 = prior;
+        if (vem) inst[1].prior = &prior2;
+        // a dummy series so that series_id 0 exists
+        { int sid; int32_t m3[3] = {0, 0, 1 % D}; float x3[3] = {1, 2, 3}, y3[3] = {0.1f, 0.2f, 0.3f};
+          medgp_cuda_add_series(ctx, 3, m3, x3, y3, &sid); for (auto &it : inst) it.series_id = sid; }
+        medgp_optimize_on_device(ctx, kp, D, inst, 16,
+            [](int index, const vector<double> &x, double &f, vector<double> &g, void *u) -> bool {
+                user_t *us = (user_t *)u;
+                if (index == 0) us->calls++;
+                vector<double> xs(x.begin(), x.begin() + us->n), gs;
+                if (!analytic_objective(xs, f, gs)) return false;
+                g.assign(x.size(), 0.0);
+                std::copy(gs.begin(), gs.end(), g.begin());
+                return true;
+            }, &user);
+        for (int k = 0; k < P; k++)
+            if (inst[0].opt_parameter[k] != inst[1].opt_parameter[k]) { printf("error: instances differ\n"); return 3; }
+        printf("calls %d\nloss %.17g\n", user.calls, inst[0].opt_loss);
+        for (size_t i = 0; i < x0.size(); i++) printf("x %.17g\n", inst[0].opt_parameter[i]);
+        if (vem) {
+            vector<double> ve = prior.get_cov_varEM_all();
+            for (size_t i = 0; i < ve.size(); i++) printf("v %.17g\n", ve[i]);
+            for (int i = 0; i < ncov; i++) printf("t %d\n", prior.type_cov[i]);
+        }
+        medgp_backend::shutdown();
     } else if (!strcmp(argv[1], "init")) {
         c_experiment e(argv[2]);
         vector<vector<double> > hyp;

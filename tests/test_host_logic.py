@@ -59,6 +59,27 @@ def test_varem_stepper_follows_reference(idx):
     assert [int(v) for v in out["t"]] == c["t"]      # same pruning / prior-type flags
 
 
+@pytest.mark.parametrize("idx", range(len(GOLD["scg"]) + len(GOLD["varem"])))
+def test_device_optimiser_driver_follows_reference(idx):
+    """medgp_optimize_on_device (variational-EM rounds, result handling; the session itself is
+    the oracle backend's here) on the analytic objective against the reference's optimisers.
+    The device state machine proper is tests/test_gpu_optimizer.py."""
+    if idx < len(GOLD["scg"]):
+        c = GOLD["scg"][idx]
+        out = tagged(run([os.path.join(BUILD, "host_check"), "dscg", str(c["max_iteration"])] + [repr(v) for v in c["x0"]]))
+        assert int(out["calls"][0]) == c["calls"]
+        assert abs(out["loss"][0] - c["loss"]) <= 1e-10 * abs(c["loss"])
+        assert np.abs(np.array(out["x"]) - np.array(c["x"])).max() <= 1e-7
+    else:
+        c = GOLD["varem"][idx - len(GOLD["scg"])]
+        out = tagged(run([os.path.join(BUILD, "host_check"), "dvarem", str(c["max_iteration"]), str(c["sub_iter"]),
+                          str(c["Q"]), str(c["D"]), str(c["R"]), "0.01", "0.01"] + [repr(v) for v in c["x0"]]))
+        assert abs(int(out["calls"][0]) - c["calls"]) <= 2
+        assert abs(out["loss"][0] - c["loss"]) <= 1e-9 * abs(c["loss"])
+        assert np.abs(np.array(out["x"]) - np.array(c["x"])).max() <= 1e-5
+        assert [int(v) for v in out["t"]] == c["t"]
+
+
 def test_random_initialisation_is_bit_identical(tmp_path):
     g = GOLD["init"]
     Q, D, R = g["Q"], g["D"], g["R"]
