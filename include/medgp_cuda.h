@@ -88,7 +88,13 @@ int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, const floa
 enum { MEDGP_ORDER_FEATURE = 0, MEDGP_ORDER_TIME = 1 };
 int medgp_cuda_add_series_ordered(medgp_ctx *ctx, int n, const int32_t *meta, const float *x,
                                   const float *y, int order, int *out_series_id);
+/* `count` series in one call -- one device allocation, one host-to-device copy: n[b] points each,
+ * meta / x / y concatenated in batch order.  For callers that upload a training window per patient
+ * and time stamp (the with-update branch of run_test_one, main_one_test.cpp:286-348). */
+int medgp_cuda_add_series_batch(medgp_ctx *ctx, int count, const int *n, const int32_t *meta, const float *x,
+                                const float *y, int order, int *out_series_ids);
 int medgp_cuda_free_series(medgp_ctx *ctx, int series_id);
+int medgp_cuda_free_series_batch(medgp_ctx *ctx, int count, const int *series_ids);
 int medgp_cuda_clear_series(medgp_ctx *ctx);
 
 /* batch NLML (+ gradient) evaluations: evaluation b uses series_id[b] and theta[b*P..].

@@ -27,7 +27,7 @@ SYMBOLS = [
     "medgp_cuda_sync", "medgp_cuda_predict", "medgp_cuda_predict_online", "medgp_cuda_debug_matrices", "medgp_cuda_debug_force_fail", "medgp_cuda_profile",
     "medgp_cuda_stage_times", "medgp_cuda_malloc", "medgp_cuda_free", "medgp_cuda_memcpy_h2d",
     "medgp_cuda_memcpy_d2h", "medgp_cuda_host_alloc", "medgp_cuda_host_free", "medgp_cuda_stream",
-    "medgp_cuda_scg_create", "medgp_cuda_scg_destroy", "medgp_cuda_scg_start", "medgp_cuda_scg_run",
+    "medgp_cuda_add_series_batch", "medgp_cuda_free_series_batch", "medgp_cuda_scg_create", "medgp_cuda_scg_destroy", "medgp_cuda_scg_start", "medgp_cuda_scg_run",
     "medgp_cuda_scg_result", "medgp_cuda_scg_points", "medgp_cuda_scg_feed",
 ]
 
@@ -71,6 +71,8 @@ def load_library():
     lib.medgp_cuda_add_series_ordered.argtypes = [vp, i, ip, fp, fp, i, ip]
     lib.medgp_cuda_predict_online.argtypes = [vp, i, ip, dp, dp, dp, ip]
     lib.medgp_cuda_free_series.argtypes = [vp, i]
+    lib.medgp_cuda_add_series_batch.argtypes = [vp, i, ip, ip, fp, fp, i, ip]
+    lib.medgp_cuda_free_series_batch.argtypes = [vp, i, ip]
     lib.medgp_cuda_clear_series.argtypes = [vp]
     lib.medgp_cuda_nlml_grad.argtypes = [vp, i, ip, dp, i, dp, dp, ip]
     lib.medgp_cuda_nlml_grad_device.argtypes = [vp, i, ip, vp, i, vp, vp, vp]

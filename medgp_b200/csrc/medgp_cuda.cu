@@ -15,6 +15,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <memory>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -33,8 +34,18 @@ constexpr int kGradRows = 32;   // rows per gradient work item (= one warp, lane
 constexpr int kGradCols = 64;   // target columns per gradient work item
 constexpr int kMaxJitter = 10;  // inference/c_inference_exact.cpp:99
 
+// device memory shared by the series of one upload; freed when the last of them goes
+struct DeviceBlob {
+    char *d = nullptr;
+    explicit DeviceBlob(char *p) : d(p) {}
+    ~DeviceBlob() { if (d) cudaFree(d); }
+    DeviceBlob(const DeviceBlob &) = delete;
+    DeviceBlob &operator=(const DeviceBlob &) = delete;
+};
+
 struct Series {
     bool alive = false;
+    std::shared_ptr<DeviceBlob> blob;
     int n = 0, npad = 0, T = 0, nitems = 0, nseg = 0;
     double trange2 = 0.0;   // (max t - min t)^2
     bool time_order = false; // points sorted by time (online imputation) instead of by feature
@@ -76,6 +87,7 @@ struct medgp_ctx {
     char *arena = nullptr;
     size_t arena_bytes = 0;
     std::vector<Series> series;
+    std::vector<int> free_slots;  // dead entries of `series`
     std::string err;
     // staging owned by the context (grown on demand)
     // h_descs is the current slot of a ring: a call fills its own slot, so the next call need
@@ -724,8 +736,7 @@ int check_series_ids(medgp_ctx *ctx, int batch, const int *series_id)
 
 void free_series_mem(Series &s)
 {
-    cudaFree(s.d_t);  // d_t is the base of the series' single allocation
-    s = Series();
+    s = Series();  // drops its share of the upload's device blob
 }
 
 }  // namespace
@@ -865,22 +876,26 @@ MEDGP_API int medgp_cuda_num_hyp(const medgp_ctx *ctx)
     return (ctx && ctx->model_set) ? ctx->md.P : (int)MEDGP_ERR_ARG;
 }
 
-MEDGP_API int medgp_cuda_add_series_ordered(medgp_ctx *ctx, int n, const int32_t *meta, const float *x,
-                                            const float *y, int order, int *out_series_id)
+namespace {
+
+struct SeriesLayout {  // byte offsets of a series' arrays inside its device blob
+    size_t o_t, o_y, o_meta, o_off, o_items, o_pair, o_gs, o_perm, total;
+};
+
+// Host side of an upload: validate, sort, build the gradient work items / timestamp groups,
+// and lay everything out in one blob.
+int prepare_series(int D, int n, const int32_t *meta, const float *x, const float *y, int order,
+                   Series &s, std::vector<char> &blob, SeriesLayout &lay, std::string &err)
 {
-    if (!ctx || !ctx->model_set || n < 1 || !meta || !x || !y || !out_series_id ||
-        (order != MEDGP_ORDER_FEATURE && order != MEDGP_ORDER_TIME)) {
-        if (ctx) ctx->err = "add_series: bad argument or model not set";
+    if (n < 1 || (order != MEDGP_ORDER_FEATURE && order != MEDGP_ORDER_TIME)) {
+        err = "add_series: bad argument";
         return MEDGP_ERR_ARG;
     }
-    const int D = ctx->md.D;
     for (int i = 0; i < n; i++)
         if (meta[i] < 0 || meta[i] >= D) {
-            ctx->err = "add_series: meta out of range";
+            err = "add_series: meta out of range";
             return MEDGP_ERR_ARG;
         }
-    cudaSetDevice(ctx->device);
-    Series s;
     s.alive = true;
     s.n = n;
     s.npad = (n + MEDGP_NB - 1) / MEDGP_NB * MEDGP_NB;
@@ -944,49 +959,123 @@ MEDGP_API int medgp_cuda_add_series_ordered(medgp_ctx *ctx, int n, const int32_t
         s.ngroups = (int)gstart.size() - 1;
         for (int g = 0; g < s.ngroups; g++)
             if (gstart[g + 1] - gstart[g] > MEDGP_GMAX) {
-                ctx->err = "add_series: more than 32 points share one timestamp (online imputation groups)";
+                err = "add_series: more than 32 points share one timestamp (online imputation groups)";
                 return MEDGP_ERR_ARG;
             }
     }
-    // one allocation + one copy per series (test-time workloads upload thousands of short ones)
-    const size_t o_t = 0, o_y = o_t + (size_t)s.npad * 8, o_meta = o_y + (size_t)s.npad * 8;
-    const size_t o_off = align_up(o_meta + (size_t)s.npad * 4, 16), o_items = align_up(o_off + (size_t)(D + 1) * 4, 16);
-    const size_t o_pair = o_items + std::max<size_t>(1, items.size()) * sizeof(int4);
-    const size_t o_gs = align_up(o_pair + seg_start.size() * sizeof(int), 16);
-    const size_t o_perm = o_gs + gstart.size() * sizeof(int);
-    const size_t total = o_perm + (s.time_order ? (size_t)n * sizeof(int) : 0);
-    std::vector<char> blob(total, 0);
-    memcpy(blob.data() + o_t, ht.data(), (size_t)s.npad * 8);
-    memcpy(blob.data() + o_y, hy.data(), (size_t)s.npad * 8);
-    memcpy(blob.data() + o_meta, hm.data(), (size_t)s.npad * 4);
-    memcpy(blob.data() + o_off, off.data(), (size_t)(D + 1) * 4);
-    if (!items.empty()) memcpy(blob.data() + o_items, items.data(), items.size() * sizeof(int4));
-    memcpy(blob.data() + o_pair, seg_start.data(), seg_start.size() * sizeof(int));
+    lay.o_t = 0;
+    lay.o_y = lay.o_t + (size_t)s.npad * 8;
+    lay.o_meta = lay.o_y + (size_t)s.npad * 8;
+    lay.o_off = align_up(lay.o_meta + (size_t)s.npad * 4, 16);
+    lay.o_items = align_up(lay.o_off + (size_t)(D + 1) * 4, 16);
+    lay.o_pair = lay.o_items + std::max<size_t>(1, items.size()) * sizeof(int4);
+    lay.o_gs = align_up(lay.o_pair + seg_start.size() * sizeof(int), 16);
+    lay.o_perm = lay.o_gs + gstart.size() * sizeof(int);
+    lay.total = lay.o_perm + (s.time_order ? (size_t)n * sizeof(int) : 0);
+    const size_t base = blob.size();  // 256-aligned by the callers
+    blob.resize(base + align_up(lay.total, 256), 0);
+    char *bp = blob.data() + base;
+    memcpy(bp + lay.o_t, ht.data(), (size_t)s.npad * 8);
+    memcpy(bp + lay.o_y, hy.data(), (size_t)s.npad * 8);
+    memcpy(bp + lay.o_meta, hm.data(), (size_t)s.npad * 4);
+    memcpy(bp + lay.o_off, off.data(), (size_t)(D + 1) * 4);
+    if (!items.empty()) memcpy(bp + lay.o_items, items.data(), items.size() * sizeof(int4));
+    memcpy(bp + lay.o_pair, seg_start.data(), seg_start.size() * sizeof(int));
     if (s.time_order) {
-        memcpy(blob.data() + o_gs, gstart.data(), gstart.size() * sizeof(int));
-        memcpy(blob.data() + o_perm, s.perm.data(), (size_t)n * sizeof(int));
+        memcpy(bp + lay.o_gs, gstart.data(), gstart.size() * sizeof(int));
+        memcpy(bp + lay.o_perm, s.perm.data(), (size_t)n * sizeof(int));
     }
-    char *d_blob = nullptr;
-    CU(cudaMalloc(&d_blob, total));
-    CU(cudaMemcpy(d_blob, blob.data(), total, cudaMemcpyHostToDevice));
-    s.d_t = (double *)(d_blob + o_t);
-    s.d_y = (double *)(d_blob + o_y);
-    s.d_meta = (int *)(d_blob + o_meta);
-    s.d_off = (int *)(d_blob + o_off);
-    s.d_items = (int4 *)(d_blob + o_items);
-    s.d_seg_start = (int *)(d_blob + o_pair);
-    if (s.time_order) {
-        s.d_gstart = (int *)(d_blob + o_gs);
-        s.d_perm = (int *)(d_blob + o_perm);
-    }
-    // reuse a dead slot if there is one
-    int id = -1;
-    for (size_t i = 0; i < ctx->series.size(); i++)
-        if (!ctx->series[i].alive) { id = (int)i; break; }
-    if (id < 0) { id = (int)ctx->series.size(); ctx->series.emplace_back(); }
-    ctx->series[id] = std::move(s);
-    *out_series_id = id;
     return MEDGP_OK;
+}
+
+void bind_series(Series &s, const SeriesLayout &lay, char *d_base, const std::shared_ptr<DeviceBlob> &blob)
+{
+    s.blob = blob;
+    s.d_t = (double *)(d_base + lay.o_t);
+    s.d_y = (double *)(d_base + lay.o_y);
+    s.d_meta = (int *)(d_base + lay.o_meta);
+    s.d_off = (int *)(d_base + lay.o_off);
+    s.d_items = (int4 *)(d_base + lay.o_items);
+    s.d_seg_start = (int *)(d_base + lay.o_pair);
+    if (s.time_order) {
+        s.d_gstart = (int *)(d_base + lay.o_gs);
+        s.d_perm = (int *)(d_base + lay.o_perm);
+    }
+}
+
+int place_series(medgp_ctx *ctx, Series &&s)
+{
+    int id;
+    if (!ctx->free_slots.empty()) {  // reuse a dead slot
+        id = ctx->free_slots.back();
+        ctx->free_slots.pop_back();
+    } else {
+        id = (int)ctx->series.size();
+        ctx->series.emplace_back();
+    }
+    ctx->series[id] = std::move(s);
+    return id;
+}
+
+}  // namespace
+
+// One device allocation and ONE host-to-device copy for `count` series (test-time workloads
+// upload a training window per patient and time stamp: thousands of short series).
+MEDGP_API int medgp_cuda_add_series_batch(medgp_ctx *ctx, int count, const int *n, const int32_t *meta, const float *x,
+                                          const float *y, int order, int *out_series_ids)
+{
+    if (!ctx || !ctx->model_set || count < 0 || !n || !meta || !x || !y || !out_series_ids) {
+        if (ctx) ctx->err = "add_series_batch: bad argument or model not set";
+        return MEDGP_ERR_ARG;
+    }
+    if (count == 0) return MEDGP_OK;
+    cudaSetDevice(ctx->device);
+    std::vector<Series> ser(count);
+    std::vector<SeriesLayout> lay(count);
+    std::vector<size_t> base(count), first(count);
+    std::vector<std::vector<char> > part(count);
+    size_t pos = 0;
+    for (int b = 0; b < count; b++) {
+        if (n[b] < 1) { ctx->err = "add_series_batch: empty series"; return MEDGP_ERR_ARG; }
+        first[b] = pos;
+        pos += (size_t)n[b];
+    }
+    // sorting and the work-item lists of the series are independent: spread them over the host cores
+    int bad = MEDGP_OK;
+#pragma omp parallel for schedule(dynamic, 16) if (count >= 64)
+    for (int b = 0; b < count; b++) {
+        std::string err;
+        const int rc = prepare_series(ctx->md.D, n[b], meta + first[b], x + first[b], y + first[b], order, ser[b], part[b], lay[b], err);
+        if (rc) {
+#pragma omp critical
+            { bad = rc; ctx->err = err; }
+        }
+    }
+    if (bad) return bad;
+    size_t total = 0;
+    for (int b = 0; b < count; b++) { base[b] = total; total += part[b].size(); }
+    std::vector<char> blob(total);
+#pragma omp parallel for schedule(static) if (count >= 64)
+    for (int b = 0; b < count; b++) memcpy(blob.data() + base[b], part[b].data(), part[b].size());
+    char *d_blob = nullptr;
+    CU(cudaMalloc(&d_blob, blob.size()));
+    std::shared_ptr<DeviceBlob> owner = std::make_shared<DeviceBlob>(d_blob);
+    CU(cudaMemcpy(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    for (int b = 0; b < count; b++) {
+        bind_series(ser[b], lay[b], d_blob + base[b], owner);
+        out_series_ids[b] = place_series(ctx, std::move(ser[b]));
+    }
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_add_series_ordered(medgp_ctx *ctx, int n, const int32_t *meta, const float *x,
+                                            const float *y, int order, int *out_series_id)
+{
+    if (!ctx || !ctx->model_set || n < 1 || !meta || !x || !y || !out_series_id) {
+        if (ctx) ctx->err = "add_series: bad argument or model not set";
+        return MEDGP_ERR_ARG;
+    }
+    return medgp_cuda_add_series_batch(ctx, 1, &n, meta, x, y, order, out_series_id);
 }
 
 MEDGP_API int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, const float *x,
@@ -1002,6 +1091,22 @@ MEDGP_API int medgp_cuda_free_series(medgp_ctx *ctx, int series_id)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_series_mem(ctx->series[series_id]);
+    ctx->free_slots.push_back(series_id);
+    return MEDGP_OK;
+}
+
+MEDGP_API int medgp_cuda_free_series_batch(medgp_ctx *ctx, int count, const int *series_ids)
+{
+    if (!ctx || count < 0 || (count > 0 && !series_ids)) return MEDGP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    int rc = check_series_ids(ctx, count, series_ids);
+    if (rc) return rc;
+    cudaStreamSynchronize(ctx->stream);
+    for (int b = 0; b < count; b++) {
+        if (!ctx->series[series_ids[b]].alive) continue;  // listed twice
+        free_series_mem(ctx->series[series_ids[b]]);
+        ctx->free_slots.push_back(series_ids[b]);
+    }
     return MEDGP_OK;
 }
 
@@ -1013,6 +1118,7 @@ MEDGP_API int medgp_cuda_clear_series(medgp_ctx *ctx)
     for (auto &s : ctx->series)
         if (s.alive) free_series_mem(s);
     ctx->series.clear();
+    ctx->free_slots.clear();
     return MEDGP_OK;
 }
 

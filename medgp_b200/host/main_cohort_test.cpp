@@ -1,14 +1,21 @@
-// main_cohort_test -- online imputation (mode mean_wo_update) of a whole cohort, or one shard
-// of it, on one GPU.
+// main_cohort_test -- online imputation of a whole cohort, or one shard of it, on one GPU, without
+// and with online hyper-parameter updates (main_one_test.cpp:140-141 runs both for one patient).
 //   main_cohort_test --cfg exp_setup.json --pans <file with one PAN per line> --fold F
-//                    --kernclust-alg A [--device d] [--shard i/N]
-// Per patient this writes exactly the test_mean_wo_update_* files main_one_test writes (SURVEY.md
-// appendix B).  All patients of a fold share the mode hyper-parameters
+//                    --kernclust-alg A [--device d] [--shard i/N] [--update no|yes|both]
+// Per patient this writes exactly the test_mean_wo_update_* / test_mean_w_update_* files
+// main_one_test writes.  All patients of a fold share the mode hyper-parameters
 // (kernel/fold<F>/<A>_mode_param.bin, c_experiment.cpp:198), and without updates one factorisation
 // of the time-ordered patient yields every held-out prediction (medgp_cuda_predict_online), so the
 // shard is ONE batched library call; patients for which that path does not apply are refitted
-// per observation as main_one_test does.  The with-update mode is sequential in time per patient
-// and stays with main_one_test.
+// per observation as main_one_test does.
+// With updates theta moves along each patient's time axis (momentum SGD on the 72 h window,
+// main_one_test.cpp:309-348), so time stays sequential PER PATIENT -- but patients are independent:
+// the shard advances in lock-step over the patients' time-stamp index, and every super-step is two
+// batched library calls for all patients at once: NLML+gradient on the update windows
+// (medgp_cuda_nlml_grad), then one factorisation of "72 h history + this stamp" per patient whose
+// leave-one-out identities give the predictions of the stamp's observations
+// (medgp_cuda_predict_online).  The windows of a super-step are uploaded in one call
+// (medgp_cuda_add_series_batch).
 #include <algorithm>
 #include <chrono>
 #include <cstring>
@@ -42,25 +49,242 @@ struct TestPatient {
 };
 }  // namespace
 
+namespace {
+// One patient of the with-update mode: its position on its own time axis and its own theta.
+struct UpdPatient {
+    TestPatient *p = nullptr;
+    vector<float> stamps;              // unique sorted time stamps
+    vector<double> best, delta;        // current hyper-parameters, momentum buffer
+    float last_update = 0.f;
+    vector<HeldOut> tasks;             // in the reference's output order (tt major, jj minor)
+    vector<double> mean, var;
+    vector<int> status;
+};
+
+// With online updates (main_one_test.cpp:269-444 with flag_update): lock-step over the time-stamp
+// index of all patients of the shard.
+void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPatient *> &mine, const vector<int> &kp,
+                     const vector<double> &mode_parameter, int fold, const string &alg)
+{
+    const double t0 = now_s();
+    const string output_prefix = "mean_w_update";
+    const double learn_rate = curr_exp.get_online_learn_rate(), momentum = curr_exp.get_online_momentum();
+    // the test-time prior table only clamps the A entries the mode kernel has at exactly 0
+    // (c_prior.cpp:118-140); it depends on the mode parameters alone, so all patients share it
+    c_prior prior(curr_exp.get_test_cov_num(fold, alg), curr_exp.get_mean_num(), curr_exp.get_lik_num());
+    prior.init_test_prior(curr_exp.get_kernel_index(), kp, mode_parameter);
+    c_objective_batch batch(ctx, kp[0], kp[1], kp[2]);
+    vector<UpdPatient> pats;
+    size_t max_stamps = 0;
+    for (TestPatient *p : mine) {
+        if (p->time.empty()) continue;
+        UpdPatient u;
+        u.p = p;
+        u.stamps = p->time;
+        std::sort(u.stamps.begin(), u.stamps.end());
+        u.stamps.erase(std::unique(u.stamps.begin(), u.stamps.end()), u.stamps.end());
+        u.best = mode_parameter;
+        u.delta.assign(mode_parameter.size(), 0.0);
+        u.last_update = u.stamps[0];
+        max_stamps = std::max(max_stamps, u.stamps.size());
+        pats.push_back(std::move(u));
+    }
+    long n_updates = 0, n_failed_updates = 0, n_predictions = 0, n_refits = 0;
+    struct Window { vector<int> past_m, curr_m, curr_i; vector<float> past_t, past_v, curr_t, curr_v; };
+    vector<Window> win(pats.size());
+    for (size_t tt = 0; tt < max_stamps; tt++) {
+        // ---- the windows of this super-step (main_one_test.cpp:286-306)
+        vector<size_t> act;
+        for (size_t k = 0; k < pats.size(); k++) {
+            UpdPatient &u = pats[k];
+            if (tt >= u.stamps.size()) continue;
+            act.push_back(k);
+            Window &w = win[k];
+            w = Window();
+            const float stamp = u.stamps[tt];
+            const TestPatient &p = *u.p;
+            for (size_t ii = 0; ii < p.time.size(); ii++) {
+                if (p.time[ii] < stamp) {
+                    if (fabs(p.time[ii] - stamp) <= 72.0) {  // 72 h history
+                        w.past_m.push_back(p.meta[ii]); w.past_t.push_back(p.time[ii]); w.past_v.push_back(p.value[ii]);
+                    }
+                } else if (p.time[ii] == stamp) {
+                    w.curr_m.push_back(p.meta[ii]); w.curr_i.push_back((int)ii);
+                    w.curr_t.push_back(p.time[ii]); w.curr_v.push_back(p.value[ii]);
+                }
+            }
+        }
+        if (act.empty()) break;
+        // ---- (a) one momentum-SGD step on the past window where one is due (main_one_test.cpp:309-348)
+        {
+            vector<size_t> upd;        // patients with an update due
+            vector<int> ns;
+            vector<int32_t> cm;
+            vector<float> cx, cy;
+            vector<size_t> evaluated;  // ... whose window can be evaluated (more than 2 points, c_objective_one.cpp:51)
+            for (size_t k : act) {
+                UpdPatient &u = pats[k];
+                const float stamp = u.stamps[tt];
+                if (!((tt > 3) && (stamp - u.last_update) > 5.0 / 60.0)) continue;
+                u.last_update = stamp;
+                upd.push_back(k);
+                const Window &w = win[k];
+                if (w.past_t.size() <= 2) continue;
+                evaluated.push_back(k);
+                ns.push_back((int)w.past_t.size());
+                cm.insert(cm.end(), w.past_m.begin(), w.past_m.end());
+                cx.insert(cx.end(), w.past_t.begin(), w.past_t.end());
+                cy.insert(cy.end(), w.past_v.begin(), w.past_v.end());
+            }
+            vector<medgp_eval_result> res;
+            if (!evaluated.empty()) {
+                vector<int> sids(evaluated.size());
+                if (medgp_cuda_add_series_batch(ctx, (int)evaluated.size(), ns.data(), cm.data(), cx.data(), cy.data(),
+                                                MEDGP_ORDER_FEATURE, sids.data()) != MEDGP_OK) {
+                    std::cerr << "ERROR: medgp_cuda_add_series_batch: " << medgp_cuda_last_error(ctx) << endl;
+                    exit(1);
+                }
+                vector<medgp_eval_request> reqs;
+                for (size_t q = 0; q < evaluated.size(); q++) reqs.push_back({sids[q], &pats[evaluated[q]].best, &prior});
+                batch.compute(true, reqs, res);
+                medgp_cuda_free_series_batch(ctx, (int)sids.size(), sids.data());
+            }
+            size_t q = 0;
+            for (size_t k : upd) {
+                UpdPatient &u = pats[k];
+                const bool have = q < evaluated.size() && evaluated[q] == k;
+                const bool ok = have && res[q].ok;
+                if (ok) {
+                    const vector<double> &g = res[q].grad;
+                    for (size_t h = 0; h < mode_parameter.size(); h++) {
+                        const bool prior_flag = prior.get_one_prior_flag((int)h);
+                        const int prior_type = prior.get_one_prior_type((int)h);
+                        if ((!prior_flag) | (prior_type != 0)) {
+                            u.delta[h] = momentum * u.delta[h] + learn_rate * g[h];
+                            u.best[h] -= u.delta[h];
+                        }
+                    }
+                    n_updates++;
+                } else {
+                    cout << "Warning: PAN " << u.p->pan << ": failed to update at t[" << tt << "] = " << u.stamps[tt]
+                         << "; reset to mode parameters" << endl;
+                    u.best = mode_parameter;
+                    std::fill(u.delta.begin(), u.delta.end(), 0.0);
+                    n_failed_updates++;
+                }
+                if (have) q++;
+            }
+        }
+        // ---- (b) the observations of the stamp, each from "72 h history + the rest of the stamp"
+        //      (main_one_test.cpp:352-399): one factorisation of history + stamp per patient
+        vector<size_t> first_task(pats.size(), 0);
+        vector<size_t> fit;  // patients with training data at this stamp
+        vector<int> ns;
+        vector<int32_t> cm;
+        vector<float> cx, cy;
+        for (size_t k : act) {
+            UpdPatient &u = pats[k];
+            const Window &w = win[k];
+            first_task[k] = u.tasks.size();
+            for (size_t jj = 0; jj < w.curr_t.size(); jj++) {
+                HeldOut h;
+                h.has_training = w.past_t.size() + w.curr_t.size() > 1;
+                h.index = w.curr_i[jj];
+                h.test_meta = w.curr_m[jj]; h.test_time = w.curr_t[jj]; h.test_value = w.curr_v[jj]; h.stamp = u.stamps[tt];
+                u.tasks.push_back(h);
+            }
+            u.mean.resize(u.tasks.size(), 0.0);
+            u.var.resize(u.tasks.size(), 0.0);
+            u.status.resize(u.tasks.size(), -1);
+            if (w.past_t.size() + w.curr_t.size() <= 1) continue;  // no training data: zero-mean fallback at output
+            fit.push_back(k);
+            ns.push_back((int)(w.past_t.size() + w.curr_t.size()));
+            cm.insert(cm.end(), w.past_m.begin(), w.past_m.end()); cm.insert(cm.end(), w.curr_m.begin(), w.curr_m.end());
+            cx.insert(cx.end(), w.past_t.begin(), w.past_t.end()); cx.insert(cx.end(), w.curr_t.begin(), w.curr_t.end());
+            cy.insert(cy.end(), w.past_v.begin(), w.past_v.end()); cy.insert(cy.end(), w.curr_v.begin(), w.curr_v.end());
+        }
+        vector<char> done(pats.size(), 0);
+        if (!fit.empty() && online_paths_enabled()) {
+            vector<int> sids(fit.size());
+            if (medgp_cuda_add_series_batch(ctx, (int)fit.size(), ns.data(), cm.data(), cx.data(), cy.data(), MEDGP_ORDER_TIME,
+                                            sids.data()) == MEDGP_OK) {
+                size_t ntot = 0;
+                vector<double> thetas;
+                for (size_t q = 0; q < fit.size(); q++) {
+                    ntot += (size_t)ns[q];
+                    thetas.insert(thetas.end(), pats[fit[q]].best.begin(), pats[fit[q]].best.end());
+                }
+                vector<double> m(ntot), v(ntot);
+                vector<int> st(fit.size(), -1);
+                if (medgp_cuda_predict_online(ctx, (int)fit.size(), sids.data(), thetas.data(), m.data(), v.data(), st.data()) != MEDGP_OK) {
+                    std::cerr << "ERROR: medgp_cuda_predict_online: " << medgp_cuda_last_error(ctx) << endl;
+                    exit(1);
+                }
+                size_t off = 0;
+                for (size_t q = 0; q < fit.size(); q++) {
+                    UpdPatient &u = pats[fit[q]];
+                    const Window &w = win[fit[q]];
+                    const size_t np = w.past_t.size(), g = w.curr_t.size();
+                    if (st[q] == 0) {
+                        for (size_t jj = 0; jj < g; jj++) {
+                            u.mean[first_task[fit[q]] + jj] = (double)(float)m[off + np + jj];  // the reference returns float moments
+                            u.var[first_task[fit[q]] + jj] = (double)(float)v[off + np + jj];
+                            u.status[first_task[fit[q]] + jj] = 0;
+                        }
+                        done[fit[q]] = 1;
+                        n_predictions += (long)g;
+                    }
+                    off += (size_t)ns[q];
+                }
+                medgp_cuda_free_series_batch(ctx, (int)sids.size(), sids.data());
+            }
+        }
+        for (size_t k : fit) {  // whatever the batched path could not serve: the single-patient routine (refits, jitter)
+            if (done[k]) continue;
+            UpdPatient &u = pats[k];
+            const Window &w = win[k];
+            impute_time_stamp(ctx, u.best, w.past_m, w.past_t, w.past_v, w.curr_m, w.curr_t, w.curr_v, u.tasks, first_task[k],
+                              u.mean, u.var, u.status);
+            n_refits += (long)w.curr_t.size();
+        }
+    }
+    batch.release();
+    for (UpdPatient &u : pats)
+        write_imputation_outputs(curr_exp, output_prefix, u.p->pan, u.tasks, u.mean, u.var, u.status, mode_parameter);
+    for (TestPatient *p : mine)
+        curr_exp.output_int_txt(curr_exp.get_exp_test_dir() + "test_" + output_prefix + "_flag_" + p->pan,
+                                vector<int>(1, (int)!p->time.empty()));
+    cout << "with updates: " << n_predictions << " predictions and " << n_updates << " hyper-parameter updates ("
+         << n_failed_updates << " reset) in " << max_stamps << " lock-step super-steps, " << n_refits
+         << " predictions by the single-patient routine; elapsed time = " << now_s() - t0 << " seconds" << endl;
+}
+}  // namespace
+
 int main(int argc, const char *argv[])
 {
     string exp_cfg, pan_file, kernel_clust_alg;
     int device = 0, shard = 0, nshard = 1, fold = 0;
+    string update_arg = "both";
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--cfg") && i + 1 < argc) exp_cfg = argv[++i];
         else if (!strcmp(argv[i], "--pans") && i + 1 < argc) pan_file = argv[++i];
         else if (!strcmp(argv[i], "--fold") && i + 1 < argc) fold = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--kernclust-alg") && i + 1 < argc) kernel_clust_alg = argv[++i];
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--update") && i + 1 < argc) update_arg = argv[++i];
         else if (!strcmp(argv[i], "--shard") && i + 1 < argc) {
             if (sscanf(argv[++i], "%d/%d", &shard, &nshard) != 2 || nshard < 1 || shard < 0 || shard >= nshard) {
                 cout << "Error: --shard expects i/N" << endl;
                 return 1;
             }
         } else {
-            cout << "usage: main_cohort_test --cfg exp_setup.json --pans list.txt --fold F --kernclust-alg A [--device d] [--shard i/N]" << endl;
+            cout << "usage: main_cohort_test --cfg exp_setup.json --pans list.txt --fold F --kernclust-alg A [--device d] [--shard i/N] [--update no|yes|both]" << endl;
             return 1;
         }
+    }
+    if (update_arg != "no" && update_arg != "yes" && update_arg != "both") {
+        cout << "Error: --update expects no, yes or both" << endl;
+        return 1;
     }
     if (exp_cfg.empty() || pan_file.empty() || kernel_clust_alg.empty()) {
         cout << "Error: --cfg, --pans and --kernclust-alg are required" << endl;
@@ -102,6 +326,7 @@ int main(int argc, const char *argv[])
 
     medgp_ctx *ctx = medgp_backend::context(kp[0], kp[1], kp[2], device);
     const double t0 = now_s();
+    if (update_arg != "yes") {
     // ---- upload time-ordered, one batched call for the shard
     vector<int> sids;
     vector<TestPatient *> owner;
@@ -158,8 +383,11 @@ int main(int argc, const char *argv[])
         curr_exp.output_int_txt(curr_exp.get_exp_test_dir() + "test_" + output_prefix + "_flag_" + p->pan,
                                 vector<int>(1, (int)test_flag));
     }
-    cout << "Finish all jobs. " << predictions << " predictions from one factorisation per patient in " << t_online
-         << " s, " << refits << " by per-observation refits; total elapsed time = " << now_s() - t0 << " seconds" << endl;
+    cout << "without updates: " << predictions << " predictions from one factorisation per patient in " << t_online
+         << " s, " << refits << " by per-observation refits; elapsed time = " << now_s() - t0 << " seconds" << endl;
+    }
+    if (update_arg != "no") run_with_update(ctx, curr_exp, mine, kp, mode_parameter, fold, kernel_clust_alg);
+    cout << "Finish all jobs. Total elapsed time = " << now_s() - t0 << " seconds" << endl;
     medgp_backend::shutdown();
     return 0;
 }

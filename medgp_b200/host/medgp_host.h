@@ -523,7 +523,7 @@ bool medgp_device_optimizer_supports(const std::vector<medgp_opt_instance> &inst
 // Runs all instances to completion; returns the number of super-steps.  poll_every: super-steps
 // enqueued between two "anyone left?" polls.
 long medgp_optimize_on_device(medgp_ctx *ctx, const std::vector<int> &kernel_param, int lik_num,
-                              std::vector<medgp_opt_instance> &inst, int poll_every = 16,
+                              std::vector<medgp_opt_instance> &inst, int poll_every = 8,
                               medgp_external_objective external = nullptr, void *user = nullptr);
 
 class c_optimizer_varEM : public c_optimizer {

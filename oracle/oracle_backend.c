@@ -57,11 +57,28 @@ int medgp_cuda_add_series(medgp_ctx *c, int n, const int32_t *meta, const float 
     *id = slot;
     return MEDGP_OK;
 }
+int medgp_cuda_add_series_batch(medgp_ctx *c, int count, const int *n, const int32_t *meta, const float *x,
+                                const float *y, int order, int *ids)
+{
+    size_t pos = 0;
+    (void)order;
+    for (int b = 0; b < count; b++) {
+        int rc = medgp_cuda_add_series(c, n[b], meta + pos, x + pos, y + pos, &ids[b]);
+        if (rc) return rc;
+        pos += (size_t)n[b];
+    }
+    return MEDGP_OK;
+}
 int medgp_cuda_free_series(medgp_ctx *c, int id)
 {
     if (id < 0 || id >= c->ns || c->s[id].n == 0) return MEDGP_ERR_ARG;
     free(c->s[id].meta); free(c->s[id].x); free(c->s[id].y);
     memset(&c->s[id], 0, sizeof(series_t));
+    return MEDGP_OK;
+}
+int medgp_cuda_free_series_batch(medgp_ctx *c, int count, const int *ids)
+{
+    for (int b = 0; b < count; b++) medgp_cuda_free_series(c, ids[b]);
     return MEDGP_OK;
 }
 int medgp_cuda_clear_series(medgp_ctx *c)

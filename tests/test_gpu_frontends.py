@@ -84,6 +84,8 @@ def test_test_executable_gpu_vs_reference_golden(tmp_path):
     run_test_executable_against_golden(os.path.join(HOST, "main_one_test"), str(tmp_path / "online"))
     run_test_executable_against_golden(os.path.join(HOST, "main_one_test"), str(tmp_path / "refit"),
                                        env=dict(os.environ, MEDGP_NO_ONLINE="1"))
+    # the cohort front-end: both modes batched over patients (here a cohort of one)
+    run_test_executable_against_golden(os.path.join(HOST, "main_cohort_test"), str(tmp_path / "cohort"))
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "main_one_train_cuda.o")),
