@@ -1,4 +1,5 @@
 // c_experiment.cpp -- see c_experiment.h.  File formats: SURVEY.md appendix B.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -253,6 +254,92 @@ void c_experiment::get_one_patient_data(string PAN, vector<int> &meta_vec, vecto
             value_vec.push_back((float)norm_temp);
         }
     }
+}
+
+namespace {
+// [mean, std] of one feature over the cohort: two raw doubles (c_experiment.cpp:276-284)
+vector<double> read_feature_stat(const string &data_dir, const string &fid)
+{
+    vector<double> stat;
+    std::ifstream databin(data_dir + "feature" + fid + "_stat.bin", std::ios::binary);
+    double f;
+    while (databin.read(reinterpret_cast<char *>(&f), sizeof(double))) stat.push_back(f);
+    if (stat.size() < 2) {
+        std::cerr << "File " << data_dir << "feature" << fid << "_stat.bin is missing or short." << std::endl;
+        exit(1);
+    }
+    return stat;
+}
+}  // namespace
+
+vector<int> c_experiment::get_cohort_sizes(const vector<string> &pans) const
+{
+    vector<int> sizes(pans.size(), 0);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long k = 0; k < (long)pans.size(); k++) {
+        int n = 0;
+        for (int j = 0; j < (int)feature_index.size(); j++) {
+            const string filename = exp_data_dir + pans[k] + "/feature" + std::to_string((long long)feature_index[j]) + ".txt";
+            std::ifstream data(filename.c_str());
+            if (!data) {
+#pragma omp critical
+                std::cerr << "File " << filename << " could not be opened." << std::endl;
+                exit(1);
+            }
+            float vec_len = 0;
+            data >> vec_len;  // the count line
+            n += (int)vec_len;
+        }
+        sizes[k] = n;
+    }
+    return sizes;
+}
+
+void c_experiment::get_cohort_data(const vector<string> &pans, vector<patient_data> &out) const
+{
+    vector<vector<double> > stat(feature_index.size());
+    for (size_t j = 0; j < feature_index.size(); j++)
+        stat[j] = read_feature_stat(exp_data_dir, std::to_string((long long)feature_index[j]));
+    out.assign(pans.size(), patient_data());
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long k = 0; k < (long)pans.size(); k++) {
+        patient_data &p = out[k];
+        for (int j = 0; j < (int)feature_index.size(); j++) {
+            const string filename = exp_data_dir + pans[k] + "/feature" + std::to_string((long long)feature_index[j]) + ".txt";
+            std::ifstream data(filename.c_str());
+            if (!data) {
+#pragma omp critical
+                std::cerr << "File " << filename << " could not be opened." << std::endl;
+                exit(1);
+            }
+            float vec_len = 0, temp = 0;
+            data >> vec_len;
+            for (int i = 0; i < (int)vec_len; i++) {  // same arithmetic as get_one_patient_data
+                p.meta.push_back(j);
+                data >> temp;
+                p.time.push_back(temp);
+                data >> temp;
+                const double norm_temp = ((double)temp - stat[j][0]) / stat[j][1];
+                p.value.push_back((float)norm_temp);
+            }
+        }
+    }
+}
+
+vector<int> medgp_lpt_assign(const vector<int> &sizes, int nshard)
+{
+    vector<size_t> order(sizes.size());
+    for (size_t k = 0; k < order.size(); k++) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return sizes[a] > sizes[b]; });
+    vector<double> load(std::max(1, nshard), 0.0);
+    vector<int> out(sizes.size(), 0);
+    for (size_t k : order) {
+        const int tgt = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        const double n = (double)sizes[k];
+        load[tgt] += n * n * n;
+        out[k] = tgt;
+    }
+    return out;
 }
 
 void c_experiment::get_hyp_bounds()

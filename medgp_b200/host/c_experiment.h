@@ -34,6 +34,17 @@ class c_experiment {
     void get_one_patient_data(std::string PAN, std::vector<int> &meta_vec, std::vector<float> &time_vec,
                               std::vector<float> &value_vec, bool verbose = true) const;
 
+    // ---- cohort-level input: a cohort is thousands of patients x one small
+    // text file per feature.  A shard first reads the SIZES of all patients (the count line of
+    // every feature file) to deal patients to shards, then loads only its own patients; both
+    // passes run over the host cores, and the per-feature statistics are read once.
+    std::vector<int> get_cohort_sizes(const std::vector<std::string> &pans) const;
+    struct patient_data {
+        std::vector<int> meta;
+        std::vector<float> time, value;
+    };
+    void get_cohort_data(const std::vector<std::string> &pans, std::vector<patient_data> &out) const;
+
     int get_hyp_num() const { return get_lik_num() + get_cov_num() + get_mean_num(); }
     int get_cov_num() const;
     int get_lik_num() const;
@@ -62,5 +73,10 @@ class c_experiment {
     std::vector<float> prior_hyp;
     std::vector<double> hyp_array_ub, hyp_array_lb;
 };
+
+// Longest-processing-time-first deal of patients to shards, load ~ n^3:
+// returns the shard of every patient.  Same rule as medgp_b200/shard.py: lpt_assign (ties by
+// original order, first least-loaded shard).
+std::vector<int> medgp_lpt_assign(const std::vector<int> &sizes, int nshard);
 
 #endif

@@ -90,15 +90,19 @@ void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPa
         pats.push_back(std::move(u));
     }
     long n_updates = 0, n_failed_updates = 0, n_predictions = 0, n_refits = 0;
+    double t_win = 0, t_up_a = 0, t_eval = 0, t_sgd = 0, t_up_b = 0, t_pred = 0;  // where a super-step goes (printed at the end)
     struct Window { vector<int> past_m, curr_m, curr_i; vector<float> past_t, past_v, curr_t, curr_v; };
     vector<Window> win(pats.size());
     for (size_t tt = 0; tt < max_stamps; tt++) {
         // ---- the windows of this super-step (main_one_test.cpp:286-306)
+        double tp = now_s();
         vector<size_t> act;
-        for (size_t k = 0; k < pats.size(); k++) {
+        for (size_t k = 0; k < pats.size(); k++)
+            if (tt < pats[k].stamps.size()) act.push_back(k);
+#pragma omp parallel for schedule(dynamic, 16)
+        for (long a = 0; a < (long)act.size(); a++) {
+            const size_t k = act[a];
             UpdPatient &u = pats[k];
-            if (tt >= u.stamps.size()) continue;
-            act.push_back(k);
             Window &w = win[k];
             w = Window();
             const float stamp = u.stamps[tt];
@@ -115,6 +119,7 @@ void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPa
             }
         }
         if (act.empty()) break;
+        t_win += now_s() - tp;
         // ---- (a) one momentum-SGD step on the past window where one is due (main_one_test.cpp:309-348)
         {
             vector<size_t> upd;        // patients with an update due
@@ -138,17 +143,24 @@ void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPa
             }
             vector<medgp_eval_result> res;
             if (!evaluated.empty()) {
+                tp = now_s();
                 vector<int> sids(evaluated.size());
                 if (medgp_cuda_add_series_batch(ctx, (int)evaluated.size(), ns.data(), cm.data(), cx.data(), cy.data(),
                                                 MEDGP_ORDER_FEATURE, sids.data()) != MEDGP_OK) {
                     std::cerr << "ERROR: medgp_cuda_add_series_batch: " << medgp_cuda_last_error(ctx) << endl;
                     exit(1);
                 }
+                t_up_a += now_s() - tp;
+                tp = now_s();
                 vector<medgp_eval_request> reqs;
                 for (size_t q = 0; q < evaluated.size(); q++) reqs.push_back({sids[q], &pats[evaluated[q]].best, &prior});
                 batch.compute(true, reqs, res);
+                t_eval += now_s() - tp;
+                tp = now_s();
                 medgp_cuda_free_series_batch(ctx, (int)sids.size(), sids.data());
+                t_up_a += now_s() - tp;
             }
+            tp = now_s();
             size_t q = 0;
             for (size_t k : upd) {
                 UpdPatient &u = pats[k];
@@ -174,6 +186,7 @@ void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPa
                 }
                 if (have) q++;
             }
+            t_sgd += now_s() - tp;
         }
         // ---- (b) the observations of the stamp, each from "72 h history + the rest of the stamp"
         //      (main_one_test.cpp:352-399): one factorisation of history + stamp per patient
@@ -206,8 +219,12 @@ void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPa
         vector<char> done(pats.size(), 0);
         if (!fit.empty() && online_paths_enabled()) {
             vector<int> sids(fit.size());
-            if (medgp_cuda_add_series_batch(ctx, (int)fit.size(), ns.data(), cm.data(), cx.data(), cy.data(), MEDGP_ORDER_TIME,
-                                            sids.data()) == MEDGP_OK) {
+            tp = now_s();
+            const int rc_up = medgp_cuda_add_series_batch(ctx, (int)fit.size(), ns.data(), cm.data(), cx.data(), cy.data(),
+                                                          MEDGP_ORDER_TIME, sids.data());
+            t_up_b += now_s() - tp;
+            if (rc_up == MEDGP_OK) {
+                tp = now_s();
                 size_t ntot = 0;
                 vector<double> thetas;
                 for (size_t q = 0; q < fit.size(); q++) {
@@ -236,7 +253,10 @@ void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPa
                     }
                     off += (size_t)ns[q];
                 }
+                t_pred += now_s() - tp;
+                tp = now_s();
                 medgp_cuda_free_series_batch(ctx, (int)sids.size(), sids.data());
+                t_up_b += now_s() - tp;
             }
         }
         for (size_t k : fit) {  // whatever the batched path could not serve: the single-patient routine (refits, jitter)
@@ -257,6 +277,8 @@ void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPa
     cout << "with updates: " << n_predictions << " predictions and " << n_updates << " hyper-parameter updates ("
          << n_failed_updates << " reset) in " << max_stamps << " lock-step super-steps, " << n_refits
          << " predictions by the single-patient routine; elapsed time = " << now_s() - t0 << " seconds" << endl;
+    cout << "  of which: windows " << t_win << " s, window uploads " << t_up_a + t_up_b << " s, NLML+gradient calls " << t_eval
+         << " s, SGD steps " << t_sgd << " s, imputation calls " << t_pred << " s" << endl;
 }
 }  // namespace
 
@@ -306,23 +328,24 @@ int main(int argc, const char *argv[])
         string line;
         while (f >> line) pans.push_back(line);
     }
-    vector<TestPatient> all(pans.size());
-    for (size_t k = 0; k < pans.size(); k++) {
-        all[k].pan = pans[k];
-        curr_exp.get_one_patient_data(pans[k], all[k].meta, all[k].time, all[k].value);
-    }
-    vector<size_t> order(all.size());
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return all[a].time.size() > all[b].time.size(); });
-    vector<double> load(nshard, 0.0);
+    // sizes-only pass over the whole cohort, LPT deal, then only this shard's patients are parsed
+    const vector<int> sizes = curr_exp.get_cohort_sizes(pans);
+    const vector<int> shard_of = medgp_lpt_assign(sizes, nshard);
+    vector<string> my_pans;
+    for (size_t k = 0; k < pans.size(); k++)
+        if (shard_of[k] == shard) my_pans.push_back(pans[k]);
+    vector<c_experiment::patient_data> loaded;
+    curr_exp.get_cohort_data(my_pans, loaded);
+    vector<TestPatient> all(my_pans.size());
     vector<TestPatient *> mine;
-    for (size_t k : order) {
-        const int tgt = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-        const double n = (double)all[k].time.size();
-        load[tgt] += n * n * n;
-        if (tgt == shard) mine.push_back(&all[k]);
+    for (size_t k = 0; k < my_pans.size(); k++) {
+        all[k].pan = my_pans[k];
+        all[k].meta.swap(loaded[k].meta);
+        all[k].time.swap(loaded[k].time);
+        all[k].value.swap(loaded[k].value);
+        mine.push_back(&all[k]);
     }
-    cout << "shard " << shard << "/" << nshard << ": " << mine.size() << " of " << all.size() << " patients on device " << device << endl;
+    cout << "shard " << shard << "/" << nshard << ": " << mine.size() << " of " << pans.size() << " patients on device " << device << endl;
 
     medgp_ctx *ctx = medgp_backend::context(kp[0], kp[1], kp[2], device);
     const double t0 = now_s();

@@ -88,23 +88,29 @@ int main(int argc, const char *argv[])
         string line;
         while (f >> line) pans.push_back(line);
     }
-    vector<Patient> all(pans.size());
-    for (size_t k = 0; k < pans.size(); k++) {
-        all[k].pan = pans[k];
-        curr_exp.get_one_patient_data(pans[k], all[k].meta, all[k].time, all[k].value, false);
-    }
-    vector<size_t> order(all.size());
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return all[a].time.size() > all[b].time.size(); });
-    vector<double> load(nshard, 0.0);
+    // sizes-only pass over the whole cohort (one count line per feature file, over the host
+    // cores), LPT deal, then only this shard's patients are parsed
+    const double t_io = now_s();
+    const vector<int> sizes = curr_exp.get_cohort_sizes(pans);
+    const vector<int> shard_of = medgp_lpt_assign(sizes, nshard);
+    vector<string> my_pans;
+    for (size_t k = 0; k < pans.size(); k++)
+        if (shard_of[k] == shard) my_pans.push_back(pans[k]);
+    vector<c_experiment::patient_data> loaded;
+    curr_exp.get_cohort_data(my_pans, loaded);
+    vector<Patient> all(my_pans.size());
     vector<Patient *> mine;
-    for (size_t k : order) {
-        const int tgt = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-        const double n = (double)all[k].time.size();
-        load[tgt] += n * n * n;
-        if (tgt == shard) mine.push_back(&all[k]);
+    for (size_t k = 0; k < my_pans.size(); k++) {
+        all[k].pan = my_pans[k];
+        all[k].meta.swap(loaded[k].meta);
+        all[k].time.swap(loaded[k].time);
+        all[k].value.swap(loaded[k].value);
+        mine.push_back(&all[k]);
     }
-    cout << "shard " << shard << "/" << nshard << ": " << mine.size() << " of " << all.size() << " patients on device " << device << endl;
+    // largest first: the library sorts evaluations by size anyway, and output order does not matter
+    std::stable_sort(mine.begin(), mine.end(), [](const Patient *a, const Patient *b) { return a->time.size() > b->time.size(); });
+    cout << "loaded " << mine.size() << " of " << pans.size() << " patients in " << now_s() - t_io << " s" << endl;
+    cout << "shard " << shard << "/" << nshard << ": " << mine.size() << " of " << pans.size() << " patients on device " << device << endl;
 
     medgp_ctx *ctx = medgp_backend::context(kp[0], kp[1], kp[2], device);
     c_objective_batch batch(ctx, kp[0], kp[1], kp[2]);
@@ -216,8 +222,10 @@ int main(int argc, const char *argv[])
     const double dtB = now_s() - tB;
     cout << "phase B (optimisation, " << (on_device ? "device-resident" : "host") << " line searches): " << grad_evals << " NLML+gradient evaluations in " << super_steps
          << " super-steps, " << dtB << " s (" << (dtB > 0 ? grad_evals / dtB : 0.0) << " evals/s)" << endl;
-    // ---- outputs
-    for (Patient *p : mine) {
+    // ---- outputs (independent files per patient: written over the host cores)
+#pragma omp parallel for schedule(dynamic, 8)
+    for (long k = 0; k < (long)mine.size(); k++) {
+        Patient *p = mine[k];
         bool flag = false;
         if (p->enough && p->success) {
             if (!on_device) p->opt_parameter = p->use_vem ? p->vem.best_parameter() : p->scg.best_parameter();

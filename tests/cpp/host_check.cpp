@@ -114,6 +114,26 @@ int main(int argc, char **argv)
             for (int i = 0; i < ncov; i++) printf("t %d\n", prior.type_cov[i]);
         }
         medgp_backend::shutdown();
+    } else if (!strcmp(argv[1], "lpt")) {
+        // lpt <nshard> <size>...: the C++ deal of patients to shards (front-ends)
+        vector<int> sizes;
+        for (int i = 3; i < argc; i++) sizes.push_back(atoi(argv[i]));
+        const vector<int> sh = medgp_lpt_assign(sizes, atoi(argv[2]));
+        for (size_t i = 0; i < sh.size(); i++) printf("s %d\n", sh[i]);
+    } else if (!strcmp(argv[1], "sizes")) {
+        // sizes <cfg> <pan>...: sizes-only pass and full cohort load of c_experiment
+        c_experiment e(argv[2]);
+        vector<std::string> pans;
+        for (int i = 3; i < argc; i++) pans.push_back(argv[i]);
+        const vector<int> sz = e.get_cohort_sizes(pans);
+        vector<c_experiment::patient_data> data;
+        e.get_cohort_data(pans, data);
+        for (size_t k = 0; k < pans.size(); k++) {
+            vector<int> m; vector<float> t, v;
+            e.get_one_patient_data(pans[k], m, t, v, false);
+            const bool same = m == data[k].meta && t == data[k].time && v == data[k].value && (int)t.size() == sz[k];
+            printf("n %d\nsame %d\n", sz[k], (int)same);
+        }
     } else if (!strcmp(argv[1], "init")) {
         c_experiment e(argv[2]);
         vector<vector<double> > hyp;

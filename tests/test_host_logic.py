@@ -150,6 +150,20 @@ def test_cohort_driver_equals_one_patient_runs(tmp_path, prior_index):
             assert np.array_equal(a, b), name       # lock-step batching changes nothing
 
 
+def test_cohort_loader_equals_patient_loader(tmp_path):
+    """sizes-only pass + parallel cohort load (c_experiment::get_cohort_sizes / get_cohort_data)
+    give what get_one_patient_data gives patient by patient, including empty features"""
+    Q, D, R = 2, 3, 2
+    pats = _patients(D, [40, 55, 33, 71], 90)
+    pats["gap"] = (np.array([0, 0, 2, 2, 2], dtype=np.int32), np.array([1, 2, 3, 4, 5], dtype=np.float32),
+                   np.array([0.1, 0.2, 0.3, -0.4, 0.5], dtype=np.float32))   # feature 1 has no observation
+    cfg = expfiles.write_experiment(str(tmp_path), Q, D, R, [1, 3, 4], pats)
+    out = run([os.path.join(BUILD, "host_check"), "sizes", cfg] + list(pats))
+    ns = [int(line.split()[1]) for line in out.split("\n") if line.startswith("n ")]
+    same = [int(line.split()[1]) for line in out.split("\n") if line.startswith("same ")]
+    assert ns == [len(p[1]) for p in pats.values()] and same == [1] * len(pats)
+
+
 def test_cohort_sharding_covers_every_patient(tmp_path):
     Q, D, R = 1, 2, 1
     pats = _patients(D, [30, 45, 38, 52, 41], 80)

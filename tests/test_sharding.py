@@ -22,6 +22,24 @@ def test_lpt_balances_cubic_load():
     assert (shard.lpt_assign([10, 20, 30], 1) == 0).all()
 
 
+def test_cpp_lpt_equals_python_lpt(tmp_path):
+    """the front-ends' C++ deal (medgp_lpt_assign) is the Python one (shard.lpt_assign), patient for
+    patient, and balances the cubic load of a C3-like cohort"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "oracle"), "host_on_oracle"], check=True, capture_output=True)
+    exe = os.path.join(root, "oracle", "_build", "host_check")
+    sizes = np.random.default_rng(3).integers(300, 1501, 600)
+    for world in (1, 2, 8):
+        out = subprocess.run([exe, "lpt", str(world)] + [str(int(v)) for v in sizes], check=True, capture_output=True, text=True).stdout
+        got = np.array([int(line.split()[1]) for line in out.split("\n") if line.startswith("s ")])
+        want = shard.lpt_assign(sizes, world)
+        assert np.array_equal(got, want)
+        load = np.array([(sizes[got == r].astype(float) ** 3).sum() for r in range(world)])
+        assert load.max() / load.mean() < 1.01
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
