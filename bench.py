@@ -14,6 +14,7 @@ its own GPU, and there is no collective on the data path.
   e2e    evaluations/s through medgp_cuda_nlml_grad with HOST buffers (theta H2D and
          nlml/grad/status D2H inside the timed region)
   c2     the same two numbers on configs[1] (256 patients x n=500, one theta each), rank 0
+  c5     configs[4]: online imputation over 1024 patients, both modes, predictions/s (N=1)
   --impl reference   the reference's own CPU implementation (oracle/_ref/ref_eval, the
          unmodified reference compiled against OpenBLAS) on the box's host cores, one
          single-thread process per core as the reference is deployed, on a size-stratified
@@ -269,6 +270,17 @@ def cpu_baseline_sample():
                       f"evaluation time ({float(np.mean(secs)):.1f} s); {REF_NOTE}"}
 
 
+def c5_metric(with_reference=True):
+    """BASELINE.json configs[4]: online test-time imputation over 1024 synthetic patients, both modes,
+    through the shipped front-end main_cohort_test (tools/bench_c5.py), with the reference's
+    main_one_test.o on a bounded sample beside it."""
+    from tools import bench_c5
+    res = bench_c5.run_ours(1024, 200, 500)
+    res["both_modes_predictions_per_s"] = 2 * res["observations"] / (res["wo_update"]["seconds"] + res["w_update"]["seconds"])
+    res["reference_sample"] = bench_c5.run_reference(None, 150) if with_reference else None
+    return res
+
+
 # ------------------------------------------------------------------------------------ our arm
 def time_device_steps(torch, ctx, stream, step, steps, barrier):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -510,6 +522,8 @@ def run_ours(args):
                 out["cholesky_fp64"] = cholesky_metric(api, fp64_burst)
             if not args.no_cpu_baseline:
                 out["cpu_baseline"] = cpu_baseline_sample()
+            if not args.no_c5:
+                out["c5"] = c5_metric(with_reference=not args.no_cpu_baseline)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -526,6 +540,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cholesky", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -74,6 +74,13 @@ void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPa
     c_prior prior(curr_exp.get_test_cov_num(fold, alg), curr_exp.get_mean_num(), curr_exp.get_lik_num());
     prior.init_test_prior(curr_exp.get_kernel_index(), kp, mode_parameter);
     c_objective_batch batch(ctx, kp[0], kp[1], kp[2]);
+    // entries the SGD step moves: everything but the clamped ones (main_one_test.cpp:328-334)
+    vector<char> movable(mode_parameter.size());
+    for (size_t h = 0; h < mode_parameter.size(); h++) {
+        const bool prior_flag = prior.get_one_prior_flag((int)h);
+        const int prior_type = prior.get_one_prior_type((int)h);
+        movable[h] = ((!prior_flag) | (prior_type != 0)) ? 1 : 0;
+    }
     vector<UpdPatient> pats;
     size_t max_stamps = 0;
     for (TestPatient *p : mine) {
@@ -161,30 +168,33 @@ void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPa
                 t_up_a += now_s() - tp;
             }
             tp = now_s();
-            size_t q = 0;
-            for (size_t k : upd) {
-                UpdPatient &u = pats[k];
-                const bool have = q < evaluated.size() && evaluated[q] == k;
-                const bool ok = have && res[q].ok;
-                if (ok) {
+            vector<long> slot(pats.size(), -1);  // patient -> its result, or -1: window too small
+            for (size_t q = 0; q < evaluated.size(); q++) slot[evaluated[q]] = (long)q;
+#pragma omp parallel for schedule(static)
+            for (long a = 0; a < (long)upd.size(); a++) {
+                UpdPatient &u = pats[upd[a]];
+                const long q = slot[upd[a]];
+                if (q >= 0 && res[q].ok) {
                     const vector<double> &g = res[q].grad;
-                    for (size_t h = 0; h < mode_parameter.size(); h++) {
-                        const bool prior_flag = prior.get_one_prior_flag((int)h);
-                        const int prior_type = prior.get_one_prior_type((int)h);
-                        if ((!prior_flag) | (prior_type != 0)) {
+                    for (size_t h = 0; h < mode_parameter.size(); h++)
+                        if (movable[h]) {
                             u.delta[h] = momentum * u.delta[h] + learn_rate * g[h];
                             u.best[h] -= u.delta[h];
                         }
-                    }
-                    n_updates++;
                 } else {
-                    cout << "Warning: PAN " << u.p->pan << ": failed to update at t[" << tt << "] = " << u.stamps[tt]
-                         << "; reset to mode parameters" << endl;
                     u.best = mode_parameter;
                     std::fill(u.delta.begin(), u.delta.end(), 0.0);
+                }
+            }
+            for (size_t k : upd) {
+                const long q = slot[k];
+                if (q >= 0 && res[q].ok) {
+                    n_updates++;
+                } else {
+                    cout << "Warning: PAN " << pats[k].p->pan << ": failed to update at t[" << tt << "] = " << pats[k].stamps[tt]
+                         << "; reset to mode parameters" << endl;
                     n_failed_updates++;
                 }
-                if (have) q++;
             }
             t_sgd += now_s() - tp;
         }
@@ -226,11 +236,12 @@ void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPa
             if (rc_up == MEDGP_OK) {
                 tp = now_s();
                 size_t ntot = 0;
-                vector<double> thetas;
-                for (size_t q = 0; q < fit.size(); q++) {
-                    ntot += (size_t)ns[q];
-                    thetas.insert(thetas.end(), pats[fit[q]].best.begin(), pats[fit[q]].best.end());
-                }
+                const size_t P = mode_parameter.size();
+                vector<double> thetas(fit.size() * P);
+                for (size_t q = 0; q < fit.size(); q++) ntot += (size_t)ns[q];
+#pragma omp parallel for schedule(static)
+                for (long q = 0; q < (long)fit.size(); q++)
+                    std::copy(pats[fit[q]].best.begin(), pats[fit[q]].best.end(), thetas.begin() + (size_t)q * P);
                 vector<double> m(ntot), v(ntot);
                 vector<int> st(fit.size(), -1);
                 if (medgp_cuda_predict_online(ctx, (int)fit.size(), sids.data(), thetas.data(), m.data(), v.data(), st.data()) != MEDGP_OK) {

@@ -45,6 +45,7 @@ def run_ours(patients=1024, n_min=200, n_max=500):
         wall = time.perf_counter() - t0
         wo = re.search(r"without updates: (\d+) predictions from one factorisation per patient in ([\d.e+-]+) s, (\d+) by per-observation refits; elapsed time = ([\d.e+-]+)", out)
         w = re.search(r"with updates: (\d+) predictions and (\d+) hyper-parameter updates \((\d+) reset\) in (\d+) lock-step super-steps, (\d+) predictions by the single-patient routine; elapsed time = ([\d.e+-]+)", out)
+        bd = re.search(r"of which: windows ([\d.e+-]+) s, window uploads ([\d.e+-]+) s, NLML\+gradient calls ([\d.e+-]+) s, SGD steps ([\d.e+-]+) s, imputation calls ([\d.e+-]+) s", out)
         n_obs = int(sizes.sum())
         # every observation is imputed once per mode
         done = all(len(expfiles.read_double_bin(os.path.join(top, "test", f"test_{m}_pred_p{k}.bin"))) == sizes[k]
@@ -58,7 +59,9 @@ def run_ours(patients=1024, n_min=200, n_max=500):
                           "gpu_call_seconds": float(wo.group(2))},
             "w_update": {"predictions": int(w.group(1)) + int(w.group(5)), "updates": int(w.group(2)), "resets": int(w.group(3)),
                          "super_steps": int(w.group(4)), "single_patient_routine": int(w.group(5)), "seconds": float(w.group(6)),
-                         "predictions_per_s": n_obs / float(w.group(6))},
+                         "predictions_per_s": n_obs / float(w.group(6)),
+                         "seconds_breakdown": dict(zip(("windows", "window_uploads", "nlml_grad_calls", "sgd_steps", "imputation_calls"),
+                                                       (float(v) for v in bd.groups()))) if bd else None},
             "front_end_wall_seconds": wall, "input_files_write_seconds": t_write, "unit": "predictions/s",
         }
     finally:
