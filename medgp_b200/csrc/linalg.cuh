@@ -644,13 +644,21 @@ k_trtri_row(const EvalDesc *__restrict__ descs, int i, int right_looking)
 //   trtri:  Acc_ji (+)= U_jk L_ik^T        for j <= k < i      (k_trtri_update), then
 //           U_j,k+1 = -Acc_j,k+1 X_k+1^T                       (k_trtri_row, right_looking = 1)
 __global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
-k_syrk_update(const EvalDesc *__restrict__ descs, int k)
+k_syrk_update(const EvalDesc *__restrict__ descs, int k, int part)
 {
+    // part 0: every lower tile of the trailing matrix; 1: its first block column only (the tiles
+    // the next step's diagonal and panel kernels need: the critical path of the look-ahead
+    // schedule); 2: everything but the first block column (runs beside the next step)
     extern __shared__ __align__(128) double smem[];
     __shared__ GemmBars bars;
     const EvalDesc &e = descs[blockIdx.y];
     int a, b;
-    tri_index(blockIdx.x, a, b);
+    if (part == 1) {
+        a = blockIdx.x; b = 0;
+    } else {
+        tri_index(blockIdx.x, a, b);
+        if (part == 2) { a += 1; b += 1; }
+    }
     const int i = k + 1 + a, j = k + 1 + b, T = e.T;
     if (i >= T || e.skip) return;
     gemm_bars_init(&bars);

@@ -123,6 +123,11 @@ struct medgp_ctx {
     int force_rl = -1;  // MEDGP_RL=0/1 forces the left-/right-looking factorisation (experiments)
     cudaStream_t sub_streams[8] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
+    // look-ahead of the right-looking factorisation: a second stream per sub-chunk for the bulk of
+    // the trailing update, which runs beside the next step's diagonal block and panel
+    cudaStream_t aux_streams[8] = {};
+    cudaEvent_t ev_panel[8] = {}, ev_bulk[8] = {};
+    bool lookahead = true;  // MEDGP_LOOKAHEAD=0 disables it
     cudaEvent_t ev_t0 = nullptr;      // MEDGP_TIMELINE: origin of the dumped stage intervals
     const char *timeline = nullptr;   // MEDGP_TIMELINE=<file>: with profiling on, keep the sub-streams and dump every stage interval
     // profiling
@@ -425,6 +430,10 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     // its flag).  Large batches keep separate diagonal / panel kernels: their sub-chunk streams
     // already overlap, and CTAs spinning on a flag would hold slots the other streams can use.
     const bool step_kernel = !rl && fold && ctx->fuse_diag && Tmax <= kTicketsPerSub;  // fold <=> few matrices in the chunk
+    const bool look = rl && ctx->lookahead;
+    cudaStream_t st2 = ctx->aux_streams[stagger_slot];
+    cudaEvent_t ev_panel = ctx->ev_panel[stagger_slot], ev_bulk = ctx->ev_bulk[stagger_slot];
+    bool bulk_pending = false;
     for (int k = 0; k < Tmax; k++) {
         const unsigned a0 = sc.act(k), a1 = k + 1 < Tmax ? sc.act(k + 1) : 0;
         const int rem = Tmax - k - 1;
@@ -448,11 +457,35 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
         if (rem > 0) {
             begin(MEDGP_STAGE_POTRF);
             out.push_back([=]() { k_potrf_panel<<<dim3(rem, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, pdepth, pfold, d_fail); L[MEDGP_STAGE_POTRF]++; });
-            if (rl)
-                out.push_back([=]() { k_syrk_update<<<dim3(rem * (rem + 1) / 2, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k); L[MEDGP_STAGE_POTRF]++; });
+            if (rl && !look)
+                out.push_back([=]() { k_syrk_update<<<dim3(rem * (rem + 1) / 2, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, 0); L[MEDGP_STAGE_POTRF]++; });
+            if (rl && look) {
+                // look-ahead: the first block column of the trailing update stays on this stream
+                // (the next diagonal block and panel need it); the rest goes to the auxiliary
+                // stream and overlaps the next step.  Orderings that matter: the bulk of step k
+                // follows the panel of step k; the column part of step k follows the bulk of step
+                // k-1 (both update the tiles of column k+1).
+                if (rem > 1) {
+                    out.push_back([=]() {
+                        cudaEventRecord(ev_panel, st);
+                        cudaStreamWaitEvent(st2, ev_panel, 0);
+                        k_syrk_update<<<dim3((rem - 1) * rem / 2, a1), MEDGP_GEMM_THREADS, gemm_smem, st2>>>(dd, k, 2);
+                        L[MEDGP_STAGE_POTRF]++;
+                    });
+                }
+                if (bulk_pending) out.push_back([=]() { cudaStreamWaitEvent(st, ev_bulk, 0); });
+                out.push_back([=]() { k_syrk_update<<<dim3(rem, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, 1); L[MEDGP_STAGE_POTRF]++; });
+                if (rem > 1) {
+                    out.push_back([=]() { cudaEventRecord(ev_bulk, st2); });
+                    bulk_pending = true;
+                } else {
+                    bulk_pending = false;  // the wait above joined the last bulk update
+                }
+            }
             end(MEDGP_STAGE_POTRF);
         }
     }
+    if (bulk_pending) out.push_back([=]() { cudaStreamWaitEvent(st, ev_bulk, 0); });  // join the auxiliary stream
     begin(MEDGP_STAGE_SOLVE);
     out.push_back([=]() { k_solve<<<ncta, 256, 0, st>>>(dd, md, d_nlml, d_status, d_fail, force_fail); L[MEDGP_STAGE_SOLVE]++; });
     end(MEDGP_STAGE_SOLVE);
@@ -642,7 +675,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         } else {
             uint64_t key = 1469598103934665603ULL;
             auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ULL; };
-            mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)ctx->stagger_us); mix(ctx->chain_diag); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
+            mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)ctx->stagger_us); mix(ctx->chain_diag); mix(ctx->lookahead); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
             mix((uint64_t)(uintptr_t)d_theta); mix((uint64_t)(uintptr_t)d_nlml); mix((uint64_t)(uintptr_t)d_grad);
             mix((uint64_t)(uintptr_t)d_status); mix((uint64_t)(uintptr_t)d_mean); mix((uint64_t)(uintptr_t)d_var);
             mix((uint64_t)(uintptr_t)ctx->d_fail); mix((uint64_t)(uintptr_t)ctx->ext_skip);
@@ -780,11 +813,15 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     if (const char *ev = getenv("MEDGP_FUSE_DIAG")) ctx->fuse_diag = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_GRAPHS")) ctx->use_graphs = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_DEVICE_RETRY")) ctx->device_retry = atoi(ev) != 0;
+    if (const char *ev = getenv("MEDGP_LOOKAHEAD")) ctx->lookahead = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_FORCE_FAIL")) ctx->force_fail = std::max(0, atoi(ev));  // tests of the jitter path through the executables
     if (const char *ev = getenv("MEDGP_STREAMS")) ctx->max_streams = std::max(1, std::min(8, atoi(ev)));
     for (int i = 0; i < 8; i++) {
         cudaStreamCreateWithFlags(&ctx->sub_streams[i], cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&ctx->aux_streams[i], cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_panel[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_bulk[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     for (int i = 0; i < kDescSlots; i++) cudaEventCreateWithFlags(&ctx->desc_ev[i], cudaEventDisableTiming);
@@ -816,7 +853,10 @@ MEDGP_API void medgp_cuda_destroy(medgp_ctx *ctx)
     for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second.exec);
     for (int i = 0; i < 8; i++) {
         if (ctx->sub_streams[i]) cudaStreamDestroy(ctx->sub_streams[i]);
+        if (ctx->aux_streams[i]) cudaStreamDestroy(ctx->aux_streams[i]);
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+        if (ctx->ev_panel[i]) cudaEventDestroy(ctx->ev_panel[i]);
+        if (ctx->ev_bulk[i]) cudaEventDestroy(ctx->ev_bulk[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     cudaFree(ctx->arena);
@@ -1480,7 +1520,8 @@ struct medgp_scg {
     std::vector<int> series;
     signed char *d_ptype = nullptr, *d_pexp = nullptr;
     float *d_ppar = nullptr;
-    int *h_active = nullptr;  // pinned
+    int *h_active = nullptr;  // pinned: [0] = live count, [1 + b] = skip flag of instance b
+    std::vector<int> live;    // instances that wanted an evaluation at the last poll
     bool started = false;
 };
 
@@ -1503,7 +1544,7 @@ MEDGP_API int medgp_cuda_scg_create(medgp_ctx *ctx, int count, medgp_scg **out)
               cudaMalloc(&g->S.skip, n * sizeof(int)) == cudaSuccess && cudaMalloc(&g->S.active, sizeof(int)) == cudaSuccess &&
               cudaMalloc(&g->d_ptype, n * P) == cudaSuccess && cudaMalloc(&g->d_pexp, n * P) == cudaSuccess &&
               cudaMalloc(&g->d_ppar, n * P * 2 * sizeof(float)) == cudaSuccess &&
-              cudaMallocHost(&g->h_active, sizeof(int)) == cudaSuccess;
+              cudaMallocHost(&g->h_active, (n + 1) * sizeof(int)) == cudaSuccess;
     if (!ok) {
         ctx->err = "scg_create: out of memory";
         medgp_cuda_scg_destroy(g);
@@ -1524,6 +1565,8 @@ MEDGP_API void medgp_cuda_scg_destroy(medgp_scg *g)
     if (g->h_active) cudaFreeHost(g->h_active);
     delete g;
 }
+
+static int scg_count_active(medgp_scg *g, int *active_left);
 
 MEDGP_API int medgp_cuda_scg_start(medgp_scg *g, const int *series_id, const double *theta0, const int *max_iteration,
                                    const signed char *prior_type, const signed char *prior_exp, const float *prior_param)
@@ -1576,7 +1619,7 @@ MEDGP_API int medgp_cuda_scg_start(medgp_scg *g, const int *series_id, const dou
     cudaFree(d_theta0);
     cudaFree(d_len);
     g->started = true;
-    return MEDGP_OK;
+    return scg_count_active(g, nullptr);
 }
 
 // the tail of a super-step (and of the test tap): advance every live instance
@@ -1593,8 +1636,14 @@ static int scg_count_active(medgp_scg *g, int *active_left)
     medgp_ctx *ctx = g->ctx;
     k_scg_count<<<1, 256, 0, ctx->stream>>>(g->S);
     CU(cudaMemcpyAsync(g->h_active, g->S.active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(g->h_active + 1, g->S.skip, (size_t)g->S.count * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     resolve_marks(ctx);
+    // the instances still running: the next super-steps are launched for these only (finished
+    // ones are still passed over on the device if they finish between two polls)
+    g->live.clear();
+    for (int b = 0; b < g->S.count; b++)
+        if (!g->h_active[1 + b]) g->live.push_back(b);
     if (active_left) *active_left = *g->h_active;
     return MEDGP_OK;
 }
@@ -1608,9 +1657,9 @@ MEDGP_API int medgp_cuda_scg_run(medgp_scg *g, int super_steps, int *active_left
     medgp_ctx *ctx = g->ctx;
     cudaSetDevice(ctx->device);
     const int count = g->S.count;
-    std::vector<Request> reqs(count);
-    for (int b = 0; b < count; b++) reqs[b] = {g->series[b], b, 0, 0, 0};
-    for (int step = 0; step < super_steps; step++) {
+    std::vector<Request> reqs;
+    for (int b : g->live) reqs.push_back({g->series[b], b, 0, 0, 0});
+    for (int step = 0; step < super_steps && !reqs.empty(); step++) {
         int rc = ensure_staging(ctx, count, 0);
         if (rc) return rc;
         CU(cudaMemsetAsync(ctx->d_fail, 0, count * sizeof(int), ctx->stream));
