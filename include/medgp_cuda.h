@@ -179,6 +179,15 @@ int medgp_cuda_scg_result(medgp_scg *scg, double *theta_best, double *loss, int 
 int medgp_cuda_scg_points(medgp_scg *scg, double *theta, int *wants);
 int medgp_cuda_scg_feed(medgp_scg *scg, const double *f, const double *grad, const int *ok);
 
+/* ---- Population "mode kernel" (between training and testing): batched Gaussian-KDE mode
+ * estimation.  Replaces compute_kde + compute_mode(weighted=True) of
+ * medgpc/clustering/mode_estimate.py:438-450 (statsmodels KDEUnivariate, kernel "gau", evaluated at
+ * the data points) for n_sets independent sets at once: set s holds data[offsets[s] .. offsets[s+1])
+ * (offsets[0] = 0) with bandwidth[s] > 0 (the caller's Silverman rule); mode[s] = density-weighted
+ * mean of the set; density (optional, like data) receives the per-point densities. */
+int medgp_cuda_kde_mode(medgp_ctx *ctx, int n_sets, const int *offsets, const double *data,
+                        const double *bandwidth, double *mode, double *density);
+
 /* Tests of the jitter path: declare the first `attempts` factorisation attempts of every
  * evaluation failed, whatever their pivots (0 = off).  An evaluation then comes back with
  * status == attempts and the values of K + (1 + attempts) sigma^2 -- what the reference computes

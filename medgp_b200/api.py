@@ -27,7 +27,7 @@ SYMBOLS = [
     "medgp_cuda_sync", "medgp_cuda_predict", "medgp_cuda_predict_online", "medgp_cuda_debug_matrices", "medgp_cuda_debug_force_fail", "medgp_cuda_profile",
     "medgp_cuda_stage_times", "medgp_cuda_malloc", "medgp_cuda_free", "medgp_cuda_memcpy_h2d",
     "medgp_cuda_memcpy_d2h", "medgp_cuda_host_alloc", "medgp_cuda_host_free", "medgp_cuda_stream",
-    "medgp_cuda_add_series_batch", "medgp_cuda_free_series_batch", "medgp_cuda_scg_create", "medgp_cuda_scg_destroy", "medgp_cuda_scg_start", "medgp_cuda_scg_run",
+    "medgp_cuda_kde_mode", "medgp_cuda_add_series_batch", "medgp_cuda_free_series_batch", "medgp_cuda_scg_create", "medgp_cuda_scg_destroy", "medgp_cuda_scg_start", "medgp_cuda_scg_run",
     "medgp_cuda_scg_result", "medgp_cuda_scg_points", "medgp_cuda_scg_feed",
 ]
 
@@ -91,6 +91,7 @@ def load_library():
     lib.medgp_cuda_stream.argtypes = [vp]
     lib.medgp_cuda_stream.restype = vp
     bp = ctypes.POINTER(ctypes.c_byte)
+    lib.medgp_cuda_kde_mode.argtypes = [vp, i, ip, dp, dp, dp, dp]
     lib.medgp_cuda_scg_create.argtypes = [vp, i, ctypes.POINTER(vp)]
     lib.medgp_cuda_scg_destroy.argtypes = [vp]
     lib.medgp_cuda_scg_destroy.restype = None
@@ -267,6 +268,19 @@ class Context:
             if v is not None:
                 out[k] = v
         return out
+
+    def kde_mode(self, sets, bandwidth, want_density=False):
+        """Gaussian-KDE mode (density-weighted mean) of every 1-D array in `sets` (medgp_cuda_kde_mode)."""
+        sets = [np.ascontiguousarray(v, dtype=np.float64).ravel() for v in sets]
+        off = np.zeros(len(sets) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(v) for v in sets])
+        data = np.concatenate(sets) if sets else np.zeros(0)
+        bw = np.ascontiguousarray(bandwidth, dtype=np.float64)
+        mode = np.empty(len(sets))
+        dens = np.empty(len(data)) if want_density else None
+        self._check(self.lib.medgp_cuda_kde_mode(self.h, len(sets), _ip(off), _dp(data), _dp(bw), _dp(mode),
+                                                 _dp(dens) if want_density else None))
+        return (mode, np.split(dens, off[1:-1])) if want_density else mode
 
     def scg_session(self, count):
         """Device-resident lock-step SCG over `count` instances (medgp_cuda_scg_*)."""

@@ -25,6 +25,7 @@
 #include "cov.cuh"
 #include "linalg.cuh"
 #include "scg.cuh"
+#include "kde.cuh"
 
 #define MEDGP_API extern "C" __attribute__((visibility("default")))
 
@@ -34,11 +35,57 @@ constexpr int kGradRows = 32;   // rows per gradient work item (= one warp, lane
 constexpr int kGradCols = 64;   // target columns per gradient work item
 constexpr int kMaxJitter = 10;  // inference/c_inference_exact.cpp:99
 
-// device memory shared by the series of one upload; freed when the last of them goes
+// device memory shared by the series of one upload; when the last of them goes it returns to
+// the context's small pool (test-time workloads upload and drop a batch of windows per super-step:
+// cudaMalloc / cudaFree, which synchronise the device, stay out of that loop)
+struct BlobPool {
+    std::vector<std::pair<char *, size_t> > free_list;
+    static constexpr size_t kMaxPooled = 8;
+    char *take(size_t bytes, size_t &cap)
+    {
+        size_t best = free_list.size();
+        for (size_t i = 0; i < free_list.size(); i++)
+            if (free_list[i].second >= bytes && (best == free_list.size() || free_list[i].second < free_list[best].second)) best = i;
+        if (best < free_list.size() && free_list[best].second <= 4 * bytes + (1 << 20)) {
+            char *p = free_list[best].first;
+            cap = free_list[best].second;
+            free_list.erase(free_list.begin() + best);
+            return p;
+        }
+        char *p = nullptr;
+        cap = bytes + bytes / 4;
+        if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr;
+        return p;
+    }
+    void give(char *p, size_t cap)
+    {
+        if (free_list.size() >= kMaxPooled) {  // drop the smallest
+            size_t small = 0;
+            for (size_t i = 1; i < free_list.size(); i++)
+                if (free_list[i].second < free_list[small].second) small = i;
+            if (free_list[small].second < cap) {
+                cudaFree(free_list[small].first);
+                free_list[small] = std::make_pair(p, cap);
+            } else {
+                cudaFree(p);
+            }
+            return;
+        }
+        free_list.push_back(std::make_pair(p, cap));
+    }
+    void clear()
+    {
+        for (auto &e : free_list) cudaFree(e.first);
+        free_list.clear();
+    }
+};
+
 struct DeviceBlob {
     char *d = nullptr;
-    explicit DeviceBlob(char *p) : d(p) {}
-    ~DeviceBlob() { if (d) cudaFree(d); }
+    size_t cap = 0;
+    BlobPool *pool = nullptr;
+    DeviceBlob(char *p, size_t c, BlobPool *pl) : d(p), cap(c), pool(pl) {}
+    ~DeviceBlob() { if (d) { if (pool) pool->give(d, cap); else cudaFree(d); } }
     DeviceBlob(const DeviceBlob &) = delete;
     DeviceBlob &operator=(const DeviceBlob &) = delete;
 };
@@ -88,6 +135,9 @@ struct medgp_ctx {
     size_t arena_bytes = 0;
     std::vector<Series> series;
     std::vector<int> free_slots;  // dead entries of `series`
+    BlobPool blob_pool;           // device memory of dropped uploads, reused by the next ones
+    char *h_upload = nullptr;     // page-locked staging of an upload
+    size_t upload_cap = 0;
     std::string err;
     // staging owned by the context (grown on demand)
     // h_descs is the current slot of a ring: a call fills its own slot, so the next call need
@@ -859,6 +909,8 @@ MEDGP_API void medgp_cuda_destroy(medgp_ctx *ctx)
         if (ctx->ev_bulk[i]) cudaEventDestroy(ctx->ev_bulk[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    ctx->blob_pool.clear();
+    if (ctx->h_upload) cudaFreeHost(ctx->h_upload);
     cudaFree(ctx->arena);
     cudaFree(ctx->d_tickets);
     for (int i = 0; i < kDescSlots; i++) {
@@ -1094,13 +1146,23 @@ MEDGP_API int medgp_cuda_add_series_batch(medgp_ctx *ctx, int count, const int *
     if (bad) return bad;
     size_t total = 0;
     for (int b = 0; b < count; b++) { base[b] = total; total += part[b].size(); }
-    std::vector<char> blob(total);
+    if (total > ctx->upload_cap) {
+        if (ctx->h_upload) cudaFreeHost(ctx->h_upload);
+        ctx->h_upload = nullptr;
+        ctx->upload_cap = 0;
+        CU(cudaMallocHost(&ctx->h_upload, total + total / 2));
+        ctx->upload_cap = total + total / 2;
+    }
+    char *blob = ctx->h_upload;
 #pragma omp parallel for schedule(static) if (count >= 64)
-    for (int b = 0; b < count; b++) memcpy(blob.data() + base[b], part[b].data(), part[b].size());
-    char *d_blob = nullptr;
-    CU(cudaMalloc(&d_blob, blob.size()));
-    std::shared_ptr<DeviceBlob> owner = std::make_shared<DeviceBlob>(d_blob);
-    CU(cudaMemcpy(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    for (int b = 0; b < count; b++) memcpy(blob + base[b], part[b].data(), part[b].size());
+    size_t cap = 0;
+    char *d_blob = ctx->blob_pool.take(total, cap);
+    if (!d_blob) { ctx->err = "add_series: out of device memory"; return MEDGP_ERR_NOMEM; }
+    std::shared_ptr<DeviceBlob> owner = std::make_shared<DeviceBlob>(d_blob, cap, &ctx->blob_pool);
+    // on the context's stream: ordered behind whatever still reads a recycled blob
+    CU(cudaMemcpyAsync(d_blob, blob, total, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     for (int b = 0; b < count; b++) {
         bind_series(ser[b], lay[b], d_blob + base[b], owner);
         out_series_ids[b] = place_series(ctx, std::move(ser[b]));
@@ -1728,6 +1790,59 @@ MEDGP_API int medgp_cuda_scg_feed(medgp_scg *g, const double *f, const double *g
     int rc = scg_advance(g);
     if (rc) return rc;
     return scg_count_active(g, nullptr);
+}
+
+// ======================================================================= mode-kernel KDE
+MEDGP_API int medgp_cuda_kde_mode(medgp_ctx *ctx, int n_sets, const int *offsets, const double *data,
+                                  const double *bandwidth, double *mode, double *density)
+{
+    if (!ctx || n_sets < 0 || !offsets || !data || !bandwidth || !mode) {
+        if (ctx) ctx->err = "kde_mode: bad argument";
+        return MEDGP_ERR_ARG;
+    }
+    if (n_sets == 0) return MEDGP_OK;
+    int n_max = 0;
+    for (int s = 0; s < n_sets; s++) {
+        const int n = offsets[s + 1] - offsets[s];
+        if (n < 1 || !(bandwidth[s] > 0.0)) {
+            ctx->err = "kde_mode: every set needs at least one value and a positive bandwidth";
+            return MEDGP_ERR_ARG;
+        }
+        n_max = std::max(n_max, n);
+    }
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const size_t total = (size_t)offsets[n_sets] - (size_t)offsets[0];
+    if (offsets[0] != 0) { ctx->err = "kde_mode: offsets must start at 0"; return MEDGP_ERR_ARG; }
+    double *d_data = nullptr, *d_bw = nullptr, *d_dens = nullptr, *d_mode = nullptr;
+    int *d_off = nullptr;
+    auto cleanup = [&]() { cudaFree(d_data); cudaFree(d_bw); cudaFree(d_dens); cudaFree(d_mode); cudaFree(d_off); };
+    if (cudaMalloc(&d_data, total * 8) != cudaSuccess || cudaMalloc(&d_dens, total * 8) != cudaSuccess ||
+        cudaMalloc(&d_bw, (size_t)n_sets * 8) != cudaSuccess || cudaMalloc(&d_mode, (size_t)n_sets * 8) != cudaSuccess ||
+        cudaMalloc(&d_off, (size_t)(n_sets + 1) * sizeof(int)) != cudaSuccess) {
+        cleanup();
+        ctx->err = "kde_mode: out of device memory";
+        return MEDGP_ERR_NOMEM;
+    }
+    cudaMemcpyAsync(d_data, data, total * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_bw, bandwidth, (size_t)n_sets * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_off, offsets, (size_t)(n_sets + 1) * sizeof(int), cudaMemcpyHostToDevice, st);
+    for (int s0 = 0; s0 < n_sets; s0 += 65535) {  // grid.y limit
+        const int ns = std::min(65535, n_sets - s0);
+        k_kde_density<<<dim3((n_max + MEDGP_KDE_THREADS - 1) / MEDGP_KDE_THREADS, ns), MEDGP_KDE_THREADS, 0, st>>>(
+            d_data, d_off + s0, d_bw + s0, d_dens);
+    }
+    k_kde_mode<<<n_sets, MEDGP_KDE_THREADS, 0, st>>>(d_data, d_off, d_dens, d_mode);
+    cudaMemcpyAsync(mode, d_mode, (size_t)n_sets * 8, cudaMemcpyDeviceToHost, st);
+    if (density) cudaMemcpyAsync(density, d_dens, total * 8, cudaMemcpyDeviceToHost, st);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    const cudaError_t e2 = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        ctx->err = std::string("kde_mode: ") + cudaGetErrorString(e != cudaSuccess ? e : e2);
+        return MEDGP_ERR_CUDA;
+    }
+    return MEDGP_OK;
 }
 
 MEDGP_API int medgp_cuda_debug_force_fail(medgp_ctx *ctx, int attempts)

@@ -127,46 +127,59 @@ void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPa
         }
         if (act.empty()) break;
         t_win += now_s() - tp;
-        // ---- (a) one momentum-SGD step on the past window where one is due (main_one_test.cpp:309-348)
+        // ---- one upload per super-step: the 72 h history of every patient that needs it, for the
+        //      update (more than 2 points, c_objective_one.cpp:51) and/or as the training set of
+        //      a stamp with a single observation
+        vector<size_t> upd;              // patients with an update due at this stamp
+        vector<long> past_sid(pats.size(), -1);
         {
-            vector<size_t> upd;        // patients with an update due
+            tp = now_s();
+            vector<size_t> need;
             vector<int> ns;
             vector<int32_t> cm;
             vector<float> cx, cy;
-            vector<size_t> evaluated;  // ... whose window can be evaluated (more than 2 points, c_objective_one.cpp:51)
             for (size_t k : act) {
                 UpdPatient &u = pats[k];
-                const float stamp = u.stamps[tt];
-                if (!((tt > 3) && (stamp - u.last_update) > 5.0 / 60.0)) continue;
-                u.last_update = stamp;
-                upd.push_back(k);
                 const Window &w = win[k];
-                if (w.past_t.size() <= 2) continue;
-                evaluated.push_back(k);
+                const float stamp = u.stamps[tt];
+                const bool due = (tt > 3) && (stamp - u.last_update) > 5.0 / 60.0;
+                if (due) {
+                    u.last_update = stamp;
+                    upd.push_back(k);
+                }
+                const bool for_update = due && w.past_t.size() > 2;
+                const bool for_predict = w.curr_t.size() == 1 && !w.past_t.empty() && online_paths_enabled();
+                if (!for_update && !for_predict) continue;
+                need.push_back(k);
                 ns.push_back((int)w.past_t.size());
                 cm.insert(cm.end(), w.past_m.begin(), w.past_m.end());
                 cx.insert(cx.end(), w.past_t.begin(), w.past_t.end());
                 cy.insert(cy.end(), w.past_v.begin(), w.past_v.end());
             }
-            vector<medgp_eval_result> res;
-            if (!evaluated.empty()) {
-                tp = now_s();
-                vector<int> sids(evaluated.size());
-                if (medgp_cuda_add_series_batch(ctx, (int)evaluated.size(), ns.data(), cm.data(), cx.data(), cy.data(),
+            if (!need.empty()) {
+                vector<int> sids(need.size());
+                if (medgp_cuda_add_series_batch(ctx, (int)need.size(), ns.data(), cm.data(), cx.data(), cy.data(),
                                                 MEDGP_ORDER_FEATURE, sids.data()) != MEDGP_OK) {
                     std::cerr << "ERROR: medgp_cuda_add_series_batch: " << medgp_cuda_last_error(ctx) << endl;
                     exit(1);
                 }
-                t_up_a += now_s() - tp;
-                tp = now_s();
-                vector<medgp_eval_request> reqs;
-                for (size_t q = 0; q < evaluated.size(); q++) reqs.push_back({sids[q], &pats[evaluated[q]].best, &prior});
-                batch.compute(true, reqs, res);
-                t_eval += now_s() - tp;
-                tp = now_s();
-                medgp_cuda_free_series_batch(ctx, (int)sids.size(), sids.data());
-                t_up_a += now_s() - tp;
+                for (size_t q = 0; q < need.size(); q++) past_sid[need[q]] = sids[q];
             }
+            t_up_a += now_s() - tp;
+        }
+        // ---- (a) one momentum-SGD step on the past window where one is due (main_one_test.cpp:309-348)
+        {
+            tp = now_s();
+            vector<size_t> evaluated;  // ... whose window can be evaluated
+            vector<medgp_eval_request> reqs;
+            for (size_t k : upd)
+                if (win[k].past_t.size() > 2) {
+                    evaluated.push_back(k);
+                    reqs.push_back({(int)past_sid[k], &pats[k].best, &prior});
+                }
+            vector<medgp_eval_result> res;
+            if (!reqs.empty()) batch.compute(true, reqs, res);
+            t_eval += now_s() - tp;
             tp = now_s();
             vector<long> slot(pats.size(), -1);  // patient -> its result, or -1: window too small
             for (size_t q = 0; q < evaluated.size(); q++) slot[evaluated[q]] = (long)q;
@@ -199,9 +212,11 @@ void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPa
             t_sgd += now_s() - tp;
         }
         // ---- (b) the observations of the stamp, each from "72 h history + the rest of the stamp"
-        //      (main_one_test.cpp:352-399): one factorisation of history + stamp per patient
+        //      (main_one_test.cpp:352-399)
         vector<size_t> first_task(pats.size(), 0);
-        vector<size_t> fit;  // patients with training data at this stamp
+        vector<size_t> fit;        // patients with training data at this stamp
+        vector<size_t> single;     // ... a single observation: predicted from the uploaded history
+        vector<size_t> multi;      // ... several: one factorisation of history + stamp (leave-one-out inside the stamp)
         vector<int> ns;
         vector<int32_t> cm;
         vector<float> cx, cy;
@@ -221,45 +236,80 @@ void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPa
             u.status.resize(u.tasks.size(), -1);
             if (w.past_t.size() + w.curr_t.size() <= 1) continue;  // no training data: zero-mean fallback at output
             fit.push_back(k);
+            if (w.curr_t.size() == 1) {
+                if (past_sid[k] >= 0) single.push_back(k);
+                continue;
+            }
+            multi.push_back(k);
             ns.push_back((int)(w.past_t.size() + w.curr_t.size()));
             cm.insert(cm.end(), w.past_m.begin(), w.past_m.end()); cm.insert(cm.end(), w.curr_m.begin(), w.curr_m.end());
             cx.insert(cx.end(), w.past_t.begin(), w.past_t.end()); cx.insert(cx.end(), w.curr_t.begin(), w.curr_t.end());
             cy.insert(cy.end(), w.past_v.begin(), w.past_v.end()); cy.insert(cy.end(), w.curr_v.begin(), w.curr_v.end());
         }
         vector<char> done(pats.size(), 0);
-        if (!fit.empty() && online_paths_enabled()) {
-            vector<int> sids(fit.size());
+        const size_t P = mode_parameter.size();
+        if (!single.empty()) {  // GP_Regression::train(false) + predict of one point (main_one_test.cpp:386-399), batched
             tp = now_s();
-            const int rc_up = medgp_cuda_add_series_batch(ctx, (int)fit.size(), ns.data(), cm.data(), cx.data(), cy.data(),
+            vector<int> sids(single.size()), offs(single.size() + 1, 0), st(single.size(), -1);
+            vector<int32_t> mstar(single.size());
+            vector<float> xstar(single.size());
+            vector<double> thetas(single.size() * P), m(single.size()), v(single.size());
+#pragma omp parallel for schedule(static)
+            for (long q = 0; q < (long)single.size(); q++) {
+                const size_t k = single[q];
+                sids[q] = (int)past_sid[k];
+                offs[q + 1] = (int)q + 1;
+                mstar[q] = win[k].curr_m[0];
+                xstar[q] = win[k].curr_t[0];
+                std::copy(pats[k].best.begin(), pats[k].best.end(), thetas.begin() + (size_t)q * P);
+            }
+            if (medgp_cuda_predict(ctx, (int)single.size(), sids.data(), thetas.data(), offs.data(), mstar.data(), xstar.data(),
+                                   m.data(), v.data(), st.data()) != MEDGP_OK) {
+                std::cerr << "ERROR: medgp_cuda_predict: " << medgp_cuda_last_error(ctx) << endl;
+                exit(1);
+            }
+            for (size_t q = 0; q < single.size(); q++) {
+                if (st[q] < 0) continue;
+                UpdPatient &u = pats[single[q]];
+                u.mean[first_task[single[q]]] = (double)(float)m[q];  // the reference returns float moments
+                u.var[first_task[single[q]]] = (double)(float)v[q];
+                u.status[first_task[single[q]]] = st[q];
+                done[single[q]] = 1;
+                n_predictions++;
+            }
+            t_pred += now_s() - tp;
+        }
+        if (!multi.empty() && online_paths_enabled()) {
+            vector<int> sids(multi.size());
+            tp = now_s();
+            const int rc_up = medgp_cuda_add_series_batch(ctx, (int)multi.size(), ns.data(), cm.data(), cx.data(), cy.data(),
                                                           MEDGP_ORDER_TIME, sids.data());
             t_up_b += now_s() - tp;
             if (rc_up == MEDGP_OK) {
                 tp = now_s();
                 size_t ntot = 0;
-                const size_t P = mode_parameter.size();
-                vector<double> thetas(fit.size() * P);
-                for (size_t q = 0; q < fit.size(); q++) ntot += (size_t)ns[q];
-#pragma omp parallel for schedule(static)
-                for (long q = 0; q < (long)fit.size(); q++)
-                    std::copy(pats[fit[q]].best.begin(), pats[fit[q]].best.end(), thetas.begin() + (size_t)q * P);
+                vector<double> thetas(multi.size() * P);
+                for (size_t q = 0; q < multi.size(); q++) ntot += (size_t)ns[q];
+                for (size_t q = 0; q < multi.size(); q++)
+                    std::copy(pats[multi[q]].best.begin(), pats[multi[q]].best.end(), thetas.begin() + q * P);
                 vector<double> m(ntot), v(ntot);
-                vector<int> st(fit.size(), -1);
-                if (medgp_cuda_predict_online(ctx, (int)fit.size(), sids.data(), thetas.data(), m.data(), v.data(), st.data()) != MEDGP_OK) {
+                vector<int> st(multi.size(), -1);
+                if (medgp_cuda_predict_online(ctx, (int)multi.size(), sids.data(), thetas.data(), m.data(), v.data(), st.data()) != MEDGP_OK) {
                     std::cerr << "ERROR: medgp_cuda_predict_online: " << medgp_cuda_last_error(ctx) << endl;
                     exit(1);
                 }
                 size_t off = 0;
-                for (size_t q = 0; q < fit.size(); q++) {
-                    UpdPatient &u = pats[fit[q]];
-                    const Window &w = win[fit[q]];
+                for (size_t q = 0; q < multi.size(); q++) {
+                    UpdPatient &u = pats[multi[q]];
+                    const Window &w = win[multi[q]];
                     const size_t np = w.past_t.size(), g = w.curr_t.size();
                     if (st[q] == 0) {
                         for (size_t jj = 0; jj < g; jj++) {
-                            u.mean[first_task[fit[q]] + jj] = (double)(float)m[off + np + jj];  // the reference returns float moments
-                            u.var[first_task[fit[q]] + jj] = (double)(float)v[off + np + jj];
-                            u.status[first_task[fit[q]] + jj] = 0;
+                            u.mean[first_task[multi[q]] + jj] = (double)(float)m[off + np + jj];  // the reference returns float moments
+                            u.var[first_task[multi[q]] + jj] = (double)(float)v[off + np + jj];
+                            u.status[first_task[multi[q]] + jj] = 0;
                         }
-                        done[fit[q]] = 1;
+                        done[multi[q]] = 1;
                         n_predictions += (long)g;
                     }
                     off += (size_t)ns[q];
@@ -269,6 +319,14 @@ void run_with_update(medgp_ctx *ctx, c_experiment &curr_exp, const vector<TestPa
                 medgp_cuda_free_series_batch(ctx, (int)sids.size(), sids.data());
                 t_up_b += now_s() - tp;
             }
+        }
+        {   // the histories of this super-step are done with
+            tp = now_s();
+            vector<int> sids;
+            for (size_t k : act)
+                if (past_sid[k] >= 0) sids.push_back((int)past_sid[k]);
+            if (!sids.empty()) medgp_cuda_free_series_batch(ctx, (int)sids.size(), sids.data());
+            t_up_a += now_s() - tp;
         }
         for (size_t k : fit) {  // whatever the batched path could not serve: the single-patient routine (refits, jitter)
             if (done[k]) continue;
