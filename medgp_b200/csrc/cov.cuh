@@ -86,22 +86,38 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
     exp_tab_stage(s_tab);
     const int Q = md.Q, D = md.D, tid = threadIdx.x, n = e.n, ld = e.npad;
     double *sB = sm, *sC = sm + Q * D * D;
-    for (int i = tid; i < Q * D * D; i += blockDim.x) sB[i] = e.par[md.oB + i];
+    __shared__ int s_frange[4];  // feature range of the tile's rows [0], [1] and columns [2], [3]
+    if (tid == 0) { s_frange[0] = D; s_frange[1] = 0; s_frange[2] = D; s_frange[3] = 0; }
+    __syncthreads();
     if (tid < Q) sC[tid] = e.par[md.oC + tid];
     if (tid < MEDGP_NB) {
         const int gi = ti * MEDGP_NB + tid;
+        const int m = gi < n ? e.meta[gi] : -1;
         s_tr[tid] = gi < n ? e.t[gi] : 0.0;
-        s_mr[tid] = gi < n ? e.meta[gi] : 0;
+        s_mr[tid] = m < 0 ? 0 : m;
+        if (m >= 0) { atomicMin(&s_frange[0], m); atomicMax(&s_frange[1], m); }
     } else if (tid < 2 * MEDGP_NB) {
         const int u = tid - MEDGP_NB, gj = tj * MEDGP_NB + u;
+        const int m = gj < n ? e.meta[gj] : -1;
         s_tc[u] = gj < n ? e.t[gj] : 0.0;
-        s_mc[u] = gj < n ? e.meta[gj] : 0;
+        s_mc[u] = m < 0 ? 0 : m;
+        if (m >= 0) { atomicMin(&s_frange[2], m); atomicMax(&s_frange[3], m); }
     }
     const double2 *cs = reinterpret_cast<const double2 *>(e.cs);
     for (int idx = tid; idx < Q * MEDGP_NB; idx += blockDim.x) {
         const int q = idx >> 6, u = idx & 63;
         s_csr[q][u] = cs[(size_t)q * ld + ti * MEDGP_NB + u];
         s_csc[q][u] = cs[(size_t)q * ld + tj * MEDGP_NB + u];
+    }
+    __syncthreads();
+    // Only the block of every B_q that the tile's features select is staged: with points in
+    // feature order a 64 x 64 tile touches a few of the D features, so this is a few hundred
+    // bytes instead of all Q D^2 doubles per CTA.  sB[(q nr + (f_i - r0)) nc + (f_j - c0)].
+    const int r0 = s_frange[0], c0 = s_frange[2];
+    const int nr = max(s_frange[1] - r0 + 1, 1), nc = max(s_frange[3] - c0 + 1, 1);
+    for (int i = tid; i < Q * nr * nc; i += blockDim.x) {
+        const int q = i / (nr * nc), rem = i - q * nr * nc, fr = rem / nc, fc = rem - fr * nc;
+        sB[i] = e.par[md.oB + (q * D + r0 + fr) * D + c0 + fc];
     }
     __syncthreads();
     const int r = tid & 63, g = tid >> 6;
@@ -114,12 +130,12 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
     double2 arow[QT];
 #pragma unroll
     for (int q = 0; q < QT; q++) arow[q] = s_csr[q][r];
-    const double *brow = sB + mr * D;  // + q*D*D + mc
+    const double *brow = sB + max(mr - r0, 0) * nc - c0;  // + q*nr*nc + mc (pad rows read entry 0: never used)
     double cmax = 0.0;
 #pragma unroll
     for (int q = 0; q < QT; q++) cmax = fmax(cmax, sC[q]);
     const bool fastexp = cmax * e.trange2 < MEDGP_EXP_UNCHECKED_MAX;  // uniform per evaluation
-    const int DD = D * D;
+    const int DD = nr * nc;
 #pragma unroll 2
     for (int u = 0; u < 16; u++) {
         const int c = g * 16 + u, gj = tj * MEDGP_NB + c;
@@ -173,7 +189,7 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
 #define MEDGP_GW 4   // warps (work items) per CTA
 #endif
 #ifndef MEDGP_GOCC
-#define MEDGP_GOCC 12  // resident warps per SM the register budget is set for
+#define MEDGP_GOCC 16  // resident warps per SM the register budget is set for (128 registers per thread, no spills at Q = 5)
 #endif
 #ifndef MEDGP_GPAIR
 #define MEDGP_GPAIR 1
@@ -364,8 +380,13 @@ __device__ __forceinline__ void grad_item(const EvalDesc &e, const ModelDims &md
     grad_flush<QT>(acc, e, md, lane, seg_end, head, mi, seg, fcur, cq);
 }
 
+// resident CTAs per SM the register budget is set for: 16 warps (128 registers per thread) up to
+// Q = 5, where that fits without spills; 12 warps for wider kernels
 template <int QT>
-__global__ void __launch_bounds__(32 * MEDGP_GW, MEDGP_GOCC / MEDGP_GW)
+constexpr int grad_min_blocks() { return (QT <= 5 ? MEDGP_GOCC : (MEDGP_GOCC < 12 ? MEDGP_GOCC : 12)) / MEDGP_GW; }
+
+template <int QT>
+__global__ void __launch_bounds__(32 * MEDGP_GW, grad_min_blocks<QT>())
 k_grad(const EvalDesc *__restrict__ descs, ModelDims md)
 {
     extern __shared__ __align__(16) unsigned char dsm[];

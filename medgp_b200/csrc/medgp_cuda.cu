@@ -1584,6 +1584,7 @@ struct medgp_scg {
     float *d_ppar = nullptr;
     int *h_active = nullptr;  // pinned: [0] = live count, [1 + b] = skip flag of instance b
     std::vector<int> live;    // instances that wanted an evaluation at the last poll
+    std::vector<int> launch;  // instances the super-steps are launched for (a superset of live)
     bool started = false;
 };
 
@@ -1681,6 +1682,7 @@ MEDGP_API int medgp_cuda_scg_start(medgp_scg *g, const int *series_id, const dou
     cudaFree(d_theta0);
     cudaFree(d_len);
     g->started = true;
+    g->launch.clear();
     return scg_count_active(g, nullptr);
 }
 
@@ -1706,6 +1708,12 @@ static int scg_count_active(medgp_scg *g, int *active_left)
     g->live.clear();
     for (int b = 0; b < g->S.count; b++)
         if (!g->h_active[1 + b]) g->live.push_back(b);
+    // Finished instances are passed over on the device, so the launch set only has to CONTAIN the
+    // live ones.  It is narrowed when enough of it has finished (a new set means a new captured
+    // launch sequence, so not at every poll): MEDGP_SCG_COMPACT = fraction of the launch set that
+    // must still be live to keep it (default 0.6; 0 never narrows, 1 narrows at every poll).
+    static const double keep = getenv("MEDGP_SCG_COMPACT") ? atof(getenv("MEDGP_SCG_COMPACT")) : 0.6;
+    if (g->launch.empty() || (double)g->live.size() < keep * (double)g->launch.size() || g->live.empty()) g->launch = g->live;
     if (active_left) *active_left = *g->h_active;
     return MEDGP_OK;
 }
@@ -1720,7 +1728,7 @@ MEDGP_API int medgp_cuda_scg_run(medgp_scg *g, int super_steps, int *active_left
     cudaSetDevice(ctx->device);
     const int count = g->S.count;
     std::vector<Request> reqs;
-    for (int b : g->live) reqs.push_back({g->series[b], b, 0, 0, 0});
+    for (int b : g->launch) reqs.push_back({g->series[b], b, 0, 0, 0});
     for (int step = 0; step < super_steps && !reqs.empty(); step++) {
         int rc = ensure_staging(ctx, count, 0);
         if (rc) return rc;
