@@ -85,7 +85,9 @@ int medgp_cuda_add_series(medgp_ctx *ctx, int n, const int32_t *meta, const floa
 /* Internal point order of an uploaded series.  FEATURE (what medgp_cuda_add_series uses) serves
  * NLML, gradients and medgp_cuda_predict; TIME serves medgp_cuda_predict_online (and NLML /
  * medgp_cuda_predict), not gradients.  At most 32 points may share one timestamp with TIME. */
-enum { MEDGP_ORDER_FEATURE = 0, MEDGP_ORDER_TIME = 1 };
+enum { MEDGP_ORDER_FEATURE = 0, MEDGP_ORDER_TIME = 1, MEDGP_ORDER_GIVEN = 2 };
+/* GIVEN keeps the caller's point order (what medgp_cuda_export_factors refers to); NLML and
+ * medgp_cuda_predict work on it, gradients only if that order is feature-major already. */
 int medgp_cuda_add_series_ordered(medgp_ctx *ctx, int n, const int32_t *meta, const float *x,
                                   const float *y, int order, int *out_series_id);
 /* `count` series in one call -- one device allocation, one host-to-device copy: n[b] points each,
@@ -138,6 +140,15 @@ int medgp_cuda_predict(medgp_ctx *ctx, int batch, const int *series_id, const do
  * observation, which retries with jitter exactly as the reference does. */
 int medgp_cuda_predict_online(medgp_ctx *ctx, int batch, const int *series_id, const double *theta,
                               double *mean, double *var, int *status);
+
+/* The out-parameters of c_inference::compute_nlml for callers that keep the reference's own
+ * GP_Regression::predict (core/gp_regression.cpp:169-196): chol_alpha = K^-1 y (n floats) and
+ * chol_factor_inv = L^-1 (n*n floats, row-major, lower, strict upper part zero:
+ * inference/c_inference_exact.cpp:124-143), plus the NLML and the jitter status, for a series
+ * uploaded with MEDGP_ORDER_GIVEN.  One factorisation + triangular inverse on the GPU, then an
+ * n^2 read-back; the batched medgp_cuda_predict / medgp_cuda_predict_online are the fast path. */
+int medgp_cuda_export_factors(medgp_ctx *ctx, int series_id, const double *theta, float *alpha,
+                              float *Linv, double *nlml, int *status);
 
 /* Debug/parity taps (tests only; one evaluation): the assembled K+noise (n*n, row-major,
  * full symmetric) for kernel (1); the Cholesky factor L (n*n row-major lower) and

@@ -15,7 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MEDGP_LIB", os.path.join(HERE, "libmedgp_cuda.so"))  # MEDGP_LIB: experiments only
 PI_REF = 3.14159265  # medgpc/src/util/global_settings.h:6
-ORDER_FEATURE, ORDER_TIME = 0, 1  # include/medgp_cuda.h: MEDGP_ORDER_*
+ORDER_FEATURE, ORDER_TIME, ORDER_GIVEN = 0, 1, 2  # include/medgp_cuda.h: MEDGP_ORDER_*
 
 STAGES = ["prep", "assemble", "potrf", "diag", "solve", "trtri", "lauum", "grad", "predict"]
 
@@ -27,7 +27,7 @@ SYMBOLS = [
     "medgp_cuda_sync", "medgp_cuda_predict", "medgp_cuda_predict_online", "medgp_cuda_debug_matrices", "medgp_cuda_debug_force_fail", "medgp_cuda_profile",
     "medgp_cuda_stage_times", "medgp_cuda_malloc", "medgp_cuda_free", "medgp_cuda_memcpy_h2d",
     "medgp_cuda_memcpy_d2h", "medgp_cuda_host_alloc", "medgp_cuda_host_free", "medgp_cuda_stream",
-    "medgp_cuda_kde_mode", "medgp_cuda_add_series_batch", "medgp_cuda_free_series_batch", "medgp_cuda_scg_create", "medgp_cuda_scg_destroy", "medgp_cuda_scg_start", "medgp_cuda_scg_run",
+    "medgp_cuda_kde_mode", "medgp_cuda_export_factors", "medgp_cuda_add_series_batch", "medgp_cuda_free_series_batch", "medgp_cuda_scg_create", "medgp_cuda_scg_destroy", "medgp_cuda_scg_start", "medgp_cuda_scg_run",
     "medgp_cuda_scg_result", "medgp_cuda_scg_points", "medgp_cuda_scg_feed",
 ]
 
@@ -92,6 +92,7 @@ def load_library():
     lib.medgp_cuda_stream.restype = vp
     bp = ctypes.POINTER(ctypes.c_byte)
     lib.medgp_cuda_kde_mode.argtypes = [vp, i, ip, dp, dp, dp, dp]
+    lib.medgp_cuda_export_factors.argtypes = [vp, i, dp, fp, fp, dp, ip]
     lib.medgp_cuda_scg_create.argtypes = [vp, i, ctypes.POINTER(vp)]
     lib.medgp_cuda_scg_destroy.argtypes = [vp]
     lib.medgp_cuda_scg_destroy.restype = None
@@ -268,6 +269,16 @@ class Context:
             if v is not None:
                 out[k] = v
         return out
+
+    def export_factors(self, sid, theta):
+        """(alpha float32[n], L^-1 float32[n,n] lower, nlml, status) of a series uploaded with ORDER_GIVEN."""
+        n = self._n[int(sid)]
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        alpha, linv = np.zeros(n, dtype=np.float32), np.zeros((n, n), dtype=np.float32)
+        nlml, status = ctypes.c_double(0.0), ctypes.c_int(0)
+        self._check(self.lib.medgp_cuda_export_factors(self.h, int(sid), _dp(theta), _fp(alpha), _fp(linv),
+                                                       ctypes.byref(nlml), ctypes.byref(status)))
+        return alpha, linv, nlml.value, status.value
 
     def kde_mode(self, sets, bandwidth, want_density=False):
         """Gaussian-KDE mode (density-weighted mean) of every 1-D array in `sets` (medgp_cuda_kde_mode)."""

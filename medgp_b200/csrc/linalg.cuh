@@ -770,6 +770,30 @@ k_lauum(const EvalDesc *__restrict__ descs)
     }
 }
 
+// ------------------------------------------------------------------ alpha without K^-1
+// alpha = K^-1 y = L^-T z = U z after the triangular inverse, for callers that want the factor
+// itself (medgp_cuda_export_factors) and therefore skip k_lauum, which forms alpha on the gradient
+// path.  grid (block rows, evaluations), 128 threads: alpha_i = sum_{l >= i} U_il z_l with
+// U_ii = X_ii^T (dinvT) and U_il the strictly-upper tiles.
+__global__ void __launch_bounds__(128)
+k_alpha(const EvalDesc *__restrict__ descs)
+{
+    __shared__ double red[2 * MEDGP_NB];
+    const EvalDesc &e = descs[blockIdx.y];
+    const int i = blockIdx.x, T = e.T;
+    if (i >= T || e.skip) return;
+    const int r = threadIdx.x & 63, half = threadIdx.x >> 6;
+    double s = 0.0;
+    for (int l = i; l < T; l++) {
+        const double *U = (l == i) ? e.dinvT + (size_t)i * kTileElems : e.M + tile_off(T, i, l);
+        const double *z = e.rhs + l * MEDGP_NB;
+        for (int c = half; c < MEDGP_NB; c += 2) s = fma(U[c * MEDGP_SLD + r], __ldg(z + c), s);
+    }
+    red[half * MEDGP_NB + r] = s;
+    __syncthreads();
+    if (half == 0) e.alpha[i * MEDGP_NB + r] = red[r] + red[MEDGP_NB + r];
+}
+
 // ------------------------------------------------------------------ NLML
 // One CTA per evaluation, after the factorisation (which carried the forward solve along):
 //   nlml = 1/2 z^T z + sum log L_ii + n log(2 PI)/2     (c_inference_exact.cpp:118-120,146-152)

@@ -96,6 +96,8 @@ struct Series {
     int n = 0, npad = 0, T = 0, nitems = 0, nseg = 0;
     double trange2 = 0.0;   // (max t - min t)^2
     bool time_order = false; // points sorted by time (online imputation) instead of by feature
+    bool given_order = false; // points kept in the caller's order (factor export)
+    bool grad_ok = true;      // feature-major: the gradient kernel's work items exist
     int ngroups = 0;         // same-timestamp groups of a time-ordered series
     int *d_gstart = nullptr, *d_perm = nullptr;
     double *d_t = nullptr, *d_y = nullptr;
@@ -539,7 +541,7 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     begin(MEDGP_STAGE_SOLVE);
     out.push_back([=]() { k_solve<<<ncta, 256, 0, st>>>(dd, md, d_nlml, d_status, d_fail, force_fail); L[MEDGP_STAGE_SOLVE]++; });
     end(MEDGP_STAGE_SOLVE);
-    if (grad) {
+    if (grad || mode == 4) {
         begin(MEDGP_STAGE_TRTRI);
         for (int i = 1; i < Tmax; i++) {
             const unsigned ai = sc.act(i);
@@ -550,6 +552,13 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
             out.push_back([=]() { k_trtri_row<<<dim3(i, ai), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, i, rl ? 1 : 0); L[MEDGP_STAGE_TRTRI]++; });
         }
         end(MEDGP_STAGE_TRTRI);
+    }
+    if (mode == 4) {  // factor export: alpha from U, no K^-1
+        begin(MEDGP_STAGE_SOLVE);
+        out.push_back([=]() { k_alpha<<<dim3(Tmax, ncta), 128, 0, st>>>(dd); L[MEDGP_STAGE_SOLVE]++; });
+        end(MEDGP_STAGE_SOLVE);
+    }
+    if (grad) {
         begin(MEDGP_STAGE_LAUUM);
         out.push_back([=]() { k_lauum<<<dim3(ntri, ncta), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd); L[MEDGP_STAGE_LAUUM]++; });
         end(MEDGP_STAGE_LAUUM);
@@ -578,7 +587,8 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
 
 // The core: run `reqs` (any sizes) through the stage sequence.  d_theta is indexed by
 // out_index.  mode: 0 = NLML only, 1 = NLML + gradient, 2 = prediction, 3 = online imputation
-// (time-ordered series; star_off of the request = offset of the series in d_mean / d_var).
+// (time-ordered series; star_off of the request = offset of the series in d_mean / d_var),
+// 4 = NLML + triangular inverse + alpha (medgp_cuda_export_factors).
 // Evaluations are sorted by size, cut into chunks that fit the arena, and every chunk is dealt
 // round-robin into up to kMaxStreams sub-chunks that run on their own streams, so the
 // latency-bound phases of one sub-chunk (diagonal blocks, small trtri rows, tails) overlap the
@@ -979,7 +989,7 @@ struct SeriesLayout {  // byte offsets of a series' arrays inside its device blo
 int prepare_series(int D, int n, const int32_t *meta, const float *x, const float *y, int order,
                    Series &s, std::vector<char> &blob, SeriesLayout &lay, std::string &err)
 {
-    if (n < 1 || (order != MEDGP_ORDER_FEATURE && order != MEDGP_ORDER_TIME)) {
+    if (n < 1 || (order != MEDGP_ORDER_FEATURE && order != MEDGP_ORDER_TIME && order != MEDGP_ORDER_GIVEN)) {
         err = "add_series: bad argument";
         return MEDGP_ERR_ARG;
     }
@@ -995,13 +1005,20 @@ int prepare_series(int D, int n, const int32_t *meta, const float *x, const floa
     // feature-major internal order (stable): results are order independent, and the gradient
     // kernel's work items need every feature contiguous.  Time-major (stable) for online
     // imputation: every sliding-window training set is then a leading block plus its group.
+    // MEDGP_ORDER_GIVEN keeps the caller's order (the exported factor then refers to it); gradients
+    // are available on such a series only when that order happens to be feature-major.
     s.time_order = (order == MEDGP_ORDER_TIME);
+    s.given_order = (order == MEDGP_ORDER_GIVEN);
     s.perm.resize(n);
     std::iota(s.perm.begin(), s.perm.end(), 0);
     if (s.time_order)
         std::stable_sort(s.perm.begin(), s.perm.end(), [&](int a, int b) { return x[a] < x[b]; });
-    else
+    else if (!s.given_order)
         std::stable_sort(s.perm.begin(), s.perm.end(), [&](int a, int b) { return meta[a] < meta[b]; });
+    s.grad_ok = !s.time_order;
+    if (s.given_order)
+        for (int i = 1; i < n; i++)
+            if (meta[i] < meta[i - 1]) s.grad_ok = false;
     std::vector<double> ht(s.npad, 0.0), hy(s.npad, 0.0);
     std::vector<int> hm(s.npad, 0), off(D + 1, 0);
     for (int i = 0; i < n; i++) {
@@ -1023,7 +1040,7 @@ int prepare_series(int D, int n, const int32_t *meta, const float *x, const floa
     std::vector<int4> items;
     std::vector<int> seg_start(D + 1, 0);
     int nseg = 0;
-    for (int i0 = 0; i0 < n && !s.time_order; i0 += kGradRows) {
+    for (int i0 = 0; i0 < n && s.grad_ok; i0 += kGradRows) {
         const int i1 = std::min(i0 + kGradRows, n);
         int jb = 0;
         for (int f = 0; f < D && off[f] < i1; f++) {
@@ -1275,7 +1292,7 @@ MEDGP_API int medgp_cuda_nlml_grad_device(medgp_ctx *ctx, int batch, const int *
     if (rc) return rc;
     if (want_grad)
         for (int b = 0; b < batch; b++)
-            if (ctx->series[series_id[b]].time_order) {
+            if (!ctx->series[series_id[b]].grad_ok) {
                 ctx->err = "nlml_grad_device: gradients need a feature-ordered series (medgp_cuda_add_series)";
                 return MEDGP_ERR_ARG;
             }
@@ -1340,7 +1357,7 @@ MEDGP_API int medgp_cuda_nlml_grad(medgp_ctx *ctx, int batch, const int *series_
     if (rc) return rc;
     if (want_grad)
         for (int b = 0; b < batch; b++)
-            if (ctx->series[series_id[b]].time_order) {
+            if (!ctx->series[series_id[b]].grad_ok) {
                 ctx->err = "nlml_grad: gradients need a feature-ordered series (medgp_cuda_add_series)";
                 return MEDGP_ERR_ARG;
             }
@@ -1505,7 +1522,7 @@ MEDGP_API int medgp_cuda_debug_matrices(medgp_ctx *ctx, int series_id, const dou
     rc = ensure_staging(ctx, 1, 0);
     if (rc) return rc;
     const Series &s = ctx->series[series_id];
-    if (s.time_order && (alpha || Kinv)) {
+    if (!s.grad_ok && (alpha || Kinv)) {
         ctx->err = "debug_matrices: alpha / K^-1 need a feature-ordered series (they come from the gradient path)";
         return MEDGP_ERR_ARG;
     }
@@ -1646,7 +1663,7 @@ MEDGP_API int medgp_cuda_scg_start(medgp_scg *g, const int *series_id, const dou
     int rc = check_series_ids(ctx, count, series_id);
     if (rc) return rc;
     for (int b = 0; b < count; b++) {
-        if (ctx->series[series_id[b]].time_order) {
+        if (!ctx->series[series_id[b]].grad_ok) {
             ctx->err = "scg_start: gradients need a feature-ordered series (medgp_cuda_add_series)";
             return MEDGP_ERR_ARG;
         }
@@ -1857,6 +1874,72 @@ MEDGP_API int medgp_cuda_debug_force_fail(medgp_ctx *ctx, int attempts)
 {
     if (!ctx || attempts < 0) return MEDGP_ERR_ARG;
     ctx->force_fail = attempts;
+    return MEDGP_OK;
+}
+
+// The reference's out-parameters of c_inference::compute_nlml (chol_alpha, chol_factor_inv:
+// inference/c_inference_exact.cpp:124-143), for callers that keep the reference's own
+// GP_Regression::predict: alpha = K^-1 y and the row-major lower-triangular L^-1 (strict upper
+// part zero), as floats, in the point order of the series -- which must have been uploaded with
+// MEDGP_ORDER_GIVEN so that this is the caller's order.
+MEDGP_API int medgp_cuda_export_factors(medgp_ctx *ctx, int series_id, const double *theta, float *alpha,
+                                        float *Linv, double *nlml, int *status)
+{
+    if (!ctx || !ctx->model_set || !theta || !alpha || !Linv || !nlml || !status) {
+        if (ctx) ctx->err = "export_factors: bad argument";
+        return MEDGP_ERR_ARG;
+    }
+    cudaSetDevice(ctx->device);
+    int rc = check_series_ids(ctx, 1, &series_id);
+    if (rc) return rc;
+    const Series &s = ctx->series[series_id];
+    if (!s.given_order) {
+        ctx->err = "export_factors: the series must be uploaded with MEDGP_ORDER_GIVEN (the factor refers to the point order)";
+        return MEDGP_ERR_ARG;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    rc = ensure_staging(ctx, 1, 0);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const size_t n = s.n, np = s.npad, T = s.T;
+    CU(cudaMemcpyAsync(ctx->d_theta, theta, (size_t)ctx->md.P * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(ctx->d_fail, 0, sizeof(int), st));
+    std::vector<Request> one = {{series_id, 0, 0, 0, 0}};
+    rc = run_batch(ctx, one, ctx->d_theta, 4, ctx->d_out, nullptr, ctx->d_status, nullptr, nullptr, 0);
+    if (rc) return rc;
+    if (!ctx->retry_on_device) {
+        rc = host_retry_rounds(ctx, one, 1, ctx->d_theta, 4, ctx->d_out, nullptr, ctx->d_status, nullptr, nullptr);
+        if (rc) return rc;
+    }
+    rc = release_desc_slot(ctx);
+    if (rc) return rc;
+    // the single evaluation's buffers are the first arena allocations (see run_batch's carving)
+    const EvalDesc &e = ctx->h_descs[0];
+    std::vector<double> hT(T * T * kTileElems), hX(T * kTileElems), ha(np);
+    CU(cudaMemcpyAsync(hT.data(), e.M, hT.size() * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hX.data(), e.dinv, hX.size() * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ha.data(), e.alpha, np * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    resolve_marks(ctx);
+    *status = ctx->h_status[0];
+    *nlml = ctx->h_out[0];
+    if (*status < 0) return MEDGP_OK;
+    for (size_t i = 0; i < n; i++) {
+        alpha[i] = (float)ha[i];
+        float *row = Linv + i * n;
+        for (size_t j = 0; j < n; j++) {
+            double v = 0.0;
+            if (j <= i) {
+                // L^-1(i, j) = U(j, i): off-diagonal tiles of U live strictly above the diagonal
+                // of M; the diagonal tiles of L^-1 are X_kk (dinv)
+                v = ((i >> 6) == (j >> 6)) ? hX[(i >> 6) * (size_t)kTileElems + (j & 63) * MEDGP_SLD + (i & 63)]
+                                           : hT[elem_off((int)T, (int)j, (int)i)];
+            }
+            row[j] = (float)v;
+        }
+    }
     return MEDGP_OK;
 }
 

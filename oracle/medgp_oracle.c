@@ -389,6 +389,24 @@ ORACLE_API int medgp_oracle_fit(int Q, int D, int R, double pi, int n, const int
     return 0;
 }
 
+/* The out-parameters of c_inference_exact::compute_nlml (c_inference_exact.cpp:124-152):
+ * alpha = K^-1 y, L^-1 (row-major lower), nlml, jitter status -- in the caller's point order. */
+ORACLE_API int medgp_oracle_factors(int Q, int D, int R, double pi, int n, const int32_t *meta,
+                                    const float *x, const float *y, const double *theta,
+                                    double *alpha, double *Linv, double *nlml, int *status)
+{
+    hyp_t *h = hyp_unpack(Q, D, R, pi, theta);
+    fit_t *f = fit_series(h, n, meta, x, y);
+    hyp_free(h);
+    if (!f) { *status = -1; return -1; }
+    *status = f->jitter;
+    *nlml = 0.5 * f->quad + f->logdet + n * log(2.0 * pi) / 2.0;
+    memcpy(alpha, f->alpha, sizeof(double) * n);
+    tri_inverse_lower(n, f->L, Linv);
+    fit_free(f);
+    return 0;
+}
+
 /* Prediction at m test points from n training points
  * (medgpc/src/core/gp_regression.cpp:128-214; cross-cov c_kernel_LMC_SM.cpp:329-372;
  * prior variance c_kernel_LMC_SM.cpp:122-150):

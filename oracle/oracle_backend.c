@@ -21,6 +21,8 @@ int medgp_oracle_predict(int Q, int D, int R, double pi, int n, const int32_t *m
                          const float *y, const double *theta, int m, const int32_t *meta_star,
                          const float *x_star, double *mean, double *var, int *status);
 void medgp_oracle_force_fail(int attempts);
+int medgp_oracle_factors(int Q, int D, int R, double pi, int n, const int32_t *meta, const float *x, const float *y,
+                         const double *theta, double *alpha, double *Linv, double *nlml, int *status);
 
 typedef struct { int n; int32_t *meta; float *x, *y; } series_t;
 struct medgp_ctx { int Q, D, R, P; double pi; series_t *s; int ns, cap; };
@@ -74,6 +76,21 @@ int medgp_cuda_free_series(medgp_ctx *c, int id)
     if (id < 0 || id >= c->ns || c->s[id].n == 0) return MEDGP_ERR_ARG;
     free(c->s[id].meta); free(c->s[id].x); free(c->s[id].y);
     memset(&c->s[id], 0, sizeof(series_t));
+    return MEDGP_OK;
+}
+int medgp_cuda_export_factors(medgp_ctx *c, int sid, const double *theta, float *alpha, float *Linv, double *nlml, int *status)
+{
+    const series_t *s = &c->s[sid];
+    const size_t n = (size_t)s->n;
+    double *a = (double *)malloc(sizeof(double) * n), *X = (double *)malloc(sizeof(double) * n * n);
+    int rc = medgp_oracle_factors(c->Q, c->D, c->R, c->pi, s->n, s->meta, s->x, s->y, theta, a, X, nlml, status);
+    if (rc == 0) {
+        for (size_t i = 0; i < n; i++) alpha[i] = (float)a[i];
+        for (size_t i = 0; i < n * n; i++) Linv[i] = (float)X[i];
+    } else {
+        *nlml = NAN;
+    }
+    free(a); free(X);
     return MEDGP_OK;
 }
 int medgp_cuda_free_series_batch(medgp_ctx *c, int count, const int *ids)

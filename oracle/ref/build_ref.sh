@@ -5,11 +5,11 @@
 #   oracle/_ref/main_one_train.o, main_one_test.o  -- the reference executables
 #   oracle/_ref/ref_eval                           -- one-evaluation driver (oracle/ref/ref_eval.cpp)
 #   oracle/_ref/ref_scg                            -- reference SCG on an analytic objective
-#   oracle/_ref/main_one_train_cuda.o, ref_eval_cuda -- the SAME unmodified sources with the
+#   oracle/_ref/main_one_train_cuda.o, main_one_test_cuda.o, ref_eval_cuda -- the SAME unmodified sources with the
 #       reference-side binding c_inference_cuda (oracle/ref/c_inference_cuda.{h,cpp}) taking the
 #       place of c_inference_prior, linked against medgp_b200/libmedgp_cuda.so: the drop-in
 #       boundary proven by compilation
-#   oracle/_ref/main_one_train_orb.o, ref_eval_orb  -- the same with the oracle behind the C ABI
+#   oracle/_ref/main_one_{train,test}_orb.o, ref_eval_orb  -- the same with the oracle behind the C ABI
 #       (oracle/_build/liborb.a), so the binding itself is testable without a GPU
 # BLAS/LAPACK: the LP64 OpenBLAS bundled in the scipy wheel via the mkl.h shim (NOT Intel MKL;
 # g++ not icpc) -- stated wherever a number from these binaries is reported.
@@ -48,11 +48,13 @@ CUDALIB="$ROOT/medgp_b200"
 if [ -f "$CUDALIB/libmedgp_cuda.so" ]; then
   CUDALINK="-L$CUDALIB -lmedgp_cuda -Wl,-rpath,\$ORIGIN/../../medgp_b200 -Wl,-rpath,/usr/local/cuda/lib64 -Wl,-rpath-link,/usr/local/cuda/lib64"
   $CXX $FLAGS $BIND -o "$OUT/main_one_train_cuda.o" "${objs[@]}" "$OUT/obj/c_inference_cuda.o" "$SRC/main_one_train.cpp" $LINK $CUDALINK &
+  $CXX $FLAGS $BIND -o "$OUT/main_one_test_cuda.o" "${objs[@]}" "$OUT/obj/c_inference_cuda.o" "$SRC/main_one_test.cpp" $LINK $CUDALINK &
   $CXX $FLAGS $BIND -o "$OUT/ref_eval_cuda" "${objs[@]}" "$OUT/obj/c_inference_cuda.o" "$HERE/ref_eval.cpp" $LINK $CUDALINK &
 fi
 ORB="$HERE/../_build/liborb.a"
 if [ -f "$ORB" ]; then
   $CXX $FLAGS $BIND -o "$OUT/main_one_train_orb.o" "${objs[@]}" "$OUT/obj/c_inference_cuda.o" "$SRC/main_one_train.cpp" "$ORB" $LINK &
+  $CXX $FLAGS $BIND -o "$OUT/main_one_test_orb.o" "${objs[@]}" "$OUT/obj/c_inference_cuda.o" "$SRC/main_one_test.cpp" "$ORB" $LINK &
   $CXX $FLAGS $BIND -o "$OUT/ref_eval_orb" "${objs[@]}" "$OUT/obj/c_inference_cuda.o" "$HERE/ref_eval.cpp" "$ORB" $LINK &
 fi
 wait

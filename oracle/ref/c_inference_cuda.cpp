@@ -9,13 +9,13 @@
 
 using namespace std;
 
-c_inference_cuda::c_inference_cuda() : ctx_(NULL), Q_(0), D_(0), R_(0), sid_(-1), status_(0)
+c_inference_cuda::c_inference_cuda() : ctx_(NULL), Q_(0), D_(0), R_(0), sid_(-1), status_(0), order_(-1)
 {
     inffunc_name = "c_inference_cuda";
     inf_thread_num = 1;
 }
 
-c_inference_cuda::c_inference_cuda(const int &thread_num) : ctx_(NULL), Q_(0), D_(0), R_(0), sid_(-1), status_(0)
+c_inference_cuda::c_inference_cuda(const int &thread_num) : ctx_(NULL), Q_(0), D_(0), R_(0), sid_(-1), status_(0), order_(-1)
 {
     inffunc_name = "c_inference_cuda";
     inf_thread_num = thread_num;  // kept for the CLI; the GPU path does not use host threads
@@ -59,14 +59,14 @@ void c_inference_cuda::bind(c_kernel *kernel)
 
 // the data set is uploaded once and reused for as long as the caller passes the same arrays
 // (every evaluation of an optimiser run does)
-void c_inference_cuda::upload(const vector<int> &meta, const vector<float> &x, const vector<float> &y)
+void c_inference_cuda::upload(const vector<int> &meta, const vector<float> &x, const vector<float> &y, int order)
 {
-    if (sid_ >= 0 && meta == meta_ && x == x_ && y == y_) return;
+    if (sid_ >= 0 && order == order_ && meta == meta_ && x == x_ && y == y_) return;
     if (sid_ >= 0) medgp_cuda_free_series(ctx_, sid_);
     vector<int32_t> m(meta.begin(), meta.end());
-    int rc = medgp_cuda_add_series(ctx_, (int)x.size(), &m[0], &x[0], &y[0], &sid_);
-    if (rc != MEDGP_OK) die("medgp_cuda_add_series", ctx_, rc);
-    meta_ = meta; x_ = x; y_ = y;
+    int rc = medgp_cuda_add_series_ordered(ctx_, (int)x.size(), &m[0], &x[0], &y[0], order, &sid_);
+    if (rc != MEDGP_OK) die("medgp_cuda_add_series_ordered", ctx_, rc);
+    meta_ = meta; x_ = x; y_ = y; order_ = order;
 }
 
 bool c_inference_cuda::compute_nlml(const bool &flag_grad, const vector<int> &meta, const vector<float> &x,
@@ -74,13 +74,14 @@ bool c_inference_cuda::compute_nlml(const bool &flag_grad, const vector<int> &me
                                     c_likelihood *likfunc, c_prior *prior, float *&chol_alpha,
                                     float *&chol_factor_inv, float &beta, double &nlml, vector<double> &dnlml)
 {
-    (void)chol_alpha; (void)chol_factor_inv; (void)beta;
     if (meanfunc->get_meanfunc_hyp_num() != 0) {
         cout << "ERROR: c_inference_cuda implements the zero mean function only" << endl;
         exit(1);
     }
     bind(kernel);
-    upload(meta, x, y);
+    // without gradient the caller wants the factor back, in ITS point order; with gradient the
+    // library's feature-major order serves the fused gradient kernel
+    upload(meta, x, y, flag_grad ? MEDGP_ORDER_FEATURE : MEDGP_ORDER_GIVEN);
     // theta = [log sigma (D) | A raw | log mu | log v | log kappa]: set_kernel_hyp / set_likfunc_hyp
     // keep the TRANSFORMED values only (c_kernel_LMC_SM.cpp:57-59, c_likelihood.cpp:41), so the
     // stored ones are recovered with log()
@@ -95,9 +96,19 @@ bool c_inference_cuda::compute_nlml(const bool &flag_grad, const vector<int> &me
     }
     vector<double> grad(theta_.size(), 0.0);
     double value = 0.0;
-    int rc = medgp_cuda_nlml_grad(ctx_, 1, &sid_, &theta_[0], flag_grad ? 1 : 0, &value,
-                                  flag_grad ? &grad[0] : NULL, &status_);
-    if (rc != MEDGP_OK) die("medgp_cuda_nlml_grad", ctx_, rc);
+    if (flag_grad) {
+        int rc = medgp_cuda_nlml_grad(ctx_, 1, &sid_, &theta_[0], 1, &value, &grad[0], &status_);
+        if (rc != MEDGP_OK) die("medgp_cuda_nlml_grad", ctx_, rc);
+    } else {
+        // chol_alpha / chol_factor_inv are the caller's n*n float buffers (gp_regression.cpp:116-117)
+        int rc = medgp_cuda_export_factors(ctx_, sid_, &theta_[0], chol_alpha, chol_factor_inv, &value, &status_);
+        if (rc != MEDGP_OK) die("medgp_cuda_export_factors", ctx_, rc);
+        if (status_ >= 0) {
+            double quad = 0.0;
+            for (size_t i = 0; i < y.size(); i++) quad += (double)y[i] * (double)chol_alpha[i];
+            beta = (float)quad;  // c_inference_exact.cpp:146-147
+        }
+    }
     if (status_ > 0) cout << "WARNING: Cholesky decomposition failed! jittered " << status_ << " time(s)" << endl;
     if (status_ < 0) return false;  // as spotrf failing after 10 additions (c_inference_exact.cpp:109-111)
     nlml = value;

@@ -34,9 +34,12 @@ class c_inference_cuda : public c_inference {
 
     // Contract of c_inference::compute_nlml.  nlml and dnlml ([lik | cov | mean] order, prior
     // terms included) are filled; false when the Cholesky still fails after 10 jitter additions.
-    // chol_alpha / chol_factor_inv / beta are NOT filled: the factor stays on the GPU, and
-    // prediction is served by predict() below (medgp_cuda_predict) instead of the BLAS block of
-    // GP_Regression::predict (core/gp_regression.cpp:169-196).
+    // The out-parameters chol_alpha (K^-1 y), chol_factor_inv (row-major lower L^-1) and beta
+    // (y^T alpha) are filled on the calls WITHOUT gradient -- the calls the reference follows with
+    // GP_Regression::predict (main_one_test.cpp:386-399, gp_regression.cpp:165-196), which reads
+    // them -- through medgp_cuda_export_factors; gradient calls (optimiser iterations, whose
+    // GP_Regression object is dropped at once, c_objective_one.cpp:61-79) leave the factor on the
+    // GPU.  predict() below is the faster route for new code: no n^2 read-back.
     bool compute_nlml(const bool &flag_grad, const vector<int> &meta, const vector<float> &x,
                       const vector<float> &y, c_kernel *kernel, c_meanfunc *meanfunc,
                       c_likelihood *likfunc, c_prior *prior, float *&chol_alpha,
@@ -50,9 +53,9 @@ class c_inference_cuda : public c_inference {
 
   private:
     void bind(c_kernel *kernel);
-    void upload(const vector<int> &meta, const vector<float> &x, const vector<float> &y);
+    void upload(const vector<int> &meta, const vector<float> &x, const vector<float> &y, int order);
     medgp_ctx *ctx_;
-    int Q_, D_, R_, sid_, status_;
+    int Q_, D_, R_, sid_, status_, order_;
     vector<int> meta_;
     vector<float> x_, y_;
     vector<double> theta_;

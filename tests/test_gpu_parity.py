@@ -229,6 +229,41 @@ def test_device_path_needs_no_host_round_trip_and_mixed_statuses(api, oracle):
     ctx.close()
 
 
+def test_export_factors_in_the_callers_order(api, oracle):
+    """chol_alpha / chol_factor_inv, the out-parameters of the reference's compute_nlml
+    (c_inference_exact.cpp:124-143), for a series in an arbitrary point order: alpha = K^-1 y and the
+    lower-triangular L^-1 of THAT order, as floats (compared at float resolution with the oracle's
+    factor), and NLML at 1e-9."""
+    Q, D, R = 3, 4, 2
+    rng = np.random.default_rng(12)
+    ctx = api.Context(Q, D, R, workspace_bytes=1 << 30)
+    from medgp_b200.api import ORDER_GIVEN
+    for n, seed in ((37, 1), (64, 2), (150, 3), (333, 4)):
+        meta, x, y = synth.make_patient(D, n, seed=60 + seed)
+        p = rng.permutation(n)
+        meta, x, y = meta[p], x[p], y[p]          # not feature-major: the factor depends on the order
+        theta = synth.init_hyp_lmc_sm(Q, D, R, 1, seed=seed)[0]
+        sid = ctx.add_series(meta, x, y, order=ORDER_GIVEN)
+        alpha, linv, nlml, st = ctx.export_factors(sid, theta)
+        a0, L0, _ = oracle.fit(Q, D, R, meta, x, y, theta)
+        f0 = oracle.nlml_grad(Q, D, R, meta, x, y, theta, want_grad=False)[0]
+        X0 = np.linalg.inv(L0)
+        assert st == 0 and abs(nlml - f0) <= RTOL * abs(f0)
+        assert np.abs(alpha - a0).max() <= 2e-7 * np.abs(a0).max()
+        assert np.abs(linv - X0).max() <= 2e-7 * np.abs(X0).max()
+        assert (np.triu(linv, 1) == 0).all()
+        # NLML and predictions are available on such a series, gradients are not
+        f, _, _ = ctx.nlml_grad([sid], theta[None], False)
+        assert abs(f[0] - f0) <= RTOL * abs(f0)
+        with pytest.raises(api.MedgpError):
+            ctx.nlml_grad([sid], theta[None], True)
+    # a FEATURE-ordered series has no exportable factor (its internal order is the library's)
+    sid = ctx.add_series(meta, x, y)
+    with pytest.raises(api.MedgpError):
+        ctx.export_factors(sid, theta)
+    ctx.close()
+
+
 def test_predict(api, oracle):
     Q, D, R = 3, 4, 2
     ctx = api.Context(Q, D, R, workspace_bytes=1 << 30)

@@ -341,6 +341,19 @@ def run_reference_binding_checks(suffix, tmp_path, oracle):
         assert r["ok"] and abs(r["nlml"] - c["nlml"]) <= 2e-6 * abs(c["nlml"])
         gref = np.array(c["grad"])
         assert np.abs(r["values"] - gref).max() <= 5e-5 * np.abs(gref).max()
+        # the reference's own GP_Regression::predict on the exported chol_alpha / chol_factor_inv
+        oracle.write_case(path, c["Q"], c["D"], c["R"], meta, x, y, theta, np.array(c["star_meta"]),
+                          np.array(c["star_x"], dtype=np.float32))
+        out = subprocess.run([os.path.join(REF, f"ref_eval_{suffix}"), path, "2", "1", "1"], check=True,
+                             capture_output=True, text=True, timeout=600, env=env).stdout
+        r = oracle.parse_ref_output(out)
+        m = len(c["star_x"])
+        assert r["ok"]
+        assert np.abs(r["values"][:m] - np.array(c["pred_mean"])).max() <= 2e-4
+        assert np.abs(r["values"][m:2 * m] - np.array(c["pred_var"])).max() <= 2e-4
+    # the reference's test executable with the binding (factors exported for every held-out fit),
+    # against the committed outputs of the reference's own main_one_test.o
+    run_test_executable_against_golden(os.path.join(REF, f"main_one_test_{suffix}.o"), str(tmp_path / "test_exe"), env=env)
 
 
 @needs_ref
