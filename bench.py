@@ -476,9 +476,16 @@ def run_ours(args):
         dom = max(merged, key=lambda k: merged[k]["ms"])
         roofline = stage_roofline(dom)
         tr = traffic.get(dom)
-        roofline["traffic"] = tr.get("bytes_per_launch") if isinstance(tr, dict) else tr
-        roofline["traffic_source"] = (traffic.get("source", "profiles/traffic.json") + " (imported from a committed ncu "
-                                      "capture, not measured in this run)") if tr is not None else None
+        if isinstance(tr, dict) and "dram_bytes_per_n2" in tr:
+            # DRAM bytes of the stage per unit of n^2 (ncu, reduced C3 cohort) x this shard's sum of n^2, per launch
+            n2 = float(np.sum(sizes[mine].astype(np.float64) ** 2)) * N_INITS
+            roofline["traffic"] = tr["dram_bytes_per_n2"] * n2 / max(1.0, roofline["launches_per_step"])
+            roofline["traffic_source"] = ("IMPORTED, not measured in this run: " + traffic.get("source", "profiles/traffic.json"))
+        else:
+            roofline["traffic"], roofline["traffic_source"] = None, None
+        for k in ("grad_fp64_pipe_pct", "assemble_fp64_pipe_pct"):
+            if k in traffic:
+                roofline[k + "_ncu"] = traffic[k]
         roofline["peak_source"] = ((f"FP64 tensor (DMMA): cuBLAS DGEMM 8192^3 measured in this run, "
                                     f"{'sustained over 3 s' if fp64_sustained else 'burst (best of 5)'} "
                                     f"(burst {fp64_burst:.1f}, sustained {fp64_sustained if fp64_sustained else float('nan'):.1f} TFLOP/s); "
