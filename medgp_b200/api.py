@@ -54,10 +54,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise MedgpError(f"{LIB_PATH} is missing: build it with `make -C medgp_b200/csrc` "
+    path = os.environ.get("MEDGP_LIB", LIB_PATH)  # experiments: an alternative build of the same library
+    if not os.path.exists(path):
+        raise MedgpError(f"{path} is missing: build it with `make -C medgp_b200/csrc` "
                          "(there is no CPU fallback)")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     vp, i, dp, ip = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
     fp = ctypes.POINTER(ctypes.c_float)
     lib.medgp_cuda_create.argtypes = [ctypes.POINTER(vp), i, ctypes.c_size_t]

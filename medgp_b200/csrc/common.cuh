@@ -50,6 +50,7 @@ struct __align__(16) EvalDesc {
     const int *gstart;       // time-ordered series: first point of every same-timestamp group (ngroups + 1)
     const int *perm;         // internal position -> caller's point index
     int ngroups, pad1;
+    const int2 *frange;      // per 64-point block of the series: (lowest, highest) feature among its points
 };
 
 // tile-major addressing (kTileElems doubles per tile, column pitch MEDGP_SLD)

@@ -70,8 +70,13 @@ k_prep(const EvalDesc *__restrict__ descs, ModelDims md, const double *__restric
 // grid (lower tiles, evaluations), 256 threads, one 64x64 tile of K + noise per CTA, written
 // column-major (lanes along rows: coalesced 512 B column segments).  Rows/cols >= n are the
 // identity.  dynamic smem: B (Q*D*D) + c (Q) doubles.
+// resident CTAs per SM the register budget of k_assemble is set for: 4 (64 registers, no
+// spills) up to Q = 5, 2 for wider kernels
+#ifndef MEDGP_AOCC
+#define MEDGP_AOCC 4
+#endif
 template <int QT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, QT <= 5 ? MEDGP_AOCC : 2)
 k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
 {
     extern __shared__ __align__(16) double sm[];
@@ -86,38 +91,31 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
     exp_tab_stage(s_tab);
     const int Q = md.Q, D = md.D, tid = threadIdx.x, n = e.n, ld = e.npad;
     double *sB = sm, *sC = sm + Q * D * D;
-    __shared__ int s_frange[4];  // feature range of the tile's rows [0], [1] and columns [2], [3]
-    if (tid == 0) { s_frange[0] = D; s_frange[1] = 0; s_frange[2] = D; s_frange[3] = 0; }
-    __syncthreads();
+    // Only the block of every B_q that the tile's features select is staged: with points in
+    // feature order a 64 x 64 tile touches a few of the D features, so this is a few hundred
+    // bytes instead of all Q D^2 doubles per CTA.  sB[(q nr + (f_i - r0)) nc + (f_j - c0)].  The
+    // feature range of every 64-point block comes with the series (no dependent round of loads).
+    const int2 fr_r = e.frange[ti], fr_c = e.frange[tj];
+    const int r0 = fr_r.x, c0 = fr_c.x, nr = fr_r.y - fr_r.x + 1, nc = fr_c.y - fr_c.x + 1;
+    for (int i = tid; i < Q * nr * nc; i += blockDim.x) {
+        const int q = i / (nr * nc), rem = i - q * nr * nc, fr = rem / nc, fc = rem - fr * nc;
+        sB[i] = e.par[md.oB + (q * D + r0 + fr) * D + c0 + fc];
+    }
     if (tid < Q) sC[tid] = e.par[md.oC + tid];
     if (tid < MEDGP_NB) {
         const int gi = ti * MEDGP_NB + tid;
-        const int m = gi < n ? e.meta[gi] : -1;
         s_tr[tid] = gi < n ? e.t[gi] : 0.0;
-        s_mr[tid] = m < 0 ? 0 : m;
-        if (m >= 0) { atomicMin(&s_frange[0], m); atomicMax(&s_frange[1], m); }
+        s_mr[tid] = gi < n ? e.meta[gi] : r0;
     } else if (tid < 2 * MEDGP_NB) {
         const int u = tid - MEDGP_NB, gj = tj * MEDGP_NB + u;
-        const int m = gj < n ? e.meta[gj] : -1;
         s_tc[u] = gj < n ? e.t[gj] : 0.0;
-        s_mc[u] = m < 0 ? 0 : m;
-        if (m >= 0) { atomicMin(&s_frange[2], m); atomicMax(&s_frange[3], m); }
+        s_mc[u] = gj < n ? e.meta[gj] : c0;
     }
     const double2 *cs = reinterpret_cast<const double2 *>(e.cs);
     for (int idx = tid; idx < Q * MEDGP_NB; idx += blockDim.x) {
         const int q = idx >> 6, u = idx & 63;
         s_csr[q][u] = cs[(size_t)q * ld + ti * MEDGP_NB + u];
         s_csc[q][u] = cs[(size_t)q * ld + tj * MEDGP_NB + u];
-    }
-    __syncthreads();
-    // Only the block of every B_q that the tile's features select is staged: with points in
-    // feature order a 64 x 64 tile touches a few of the D features, so this is a few hundred
-    // bytes instead of all Q D^2 doubles per CTA.  sB[(q nr + (f_i - r0)) nc + (f_j - c0)].
-    const int r0 = s_frange[0], c0 = s_frange[2];
-    const int nr = max(s_frange[1] - r0 + 1, 1), nc = max(s_frange[3] - c0 + 1, 1);
-    for (int i = tid; i < Q * nr * nc; i += blockDim.x) {
-        const int q = i / (nr * nc), rem = i - q * nr * nc, fr = rem / nc, fc = rem - fr * nc;
-        sB[i] = e.par[md.oB + (q * D + r0 + fr) * D + c0 + fc];
     }
     __syncthreads();
     const int r = tid & 63, g = tid >> 6;
@@ -130,7 +128,7 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
     double2 arow[QT];
 #pragma unroll
     for (int q = 0; q < QT; q++) arow[q] = s_csr[q][r];
-    const double *brow = sB + max(mr - r0, 0) * nc - c0;  // + q*nr*nc + mc (pad rows read entry 0: never used)
+    const double *brow = sB + (mr - r0) * nc - c0;  // + q*nr*nc + mc
     double cmax = 0.0;
 #pragma unroll
     for (int q = 0; q < QT; q++) cmax = fmax(cmax, sC[q]);

@@ -100,6 +100,7 @@ struct Series {
     bool grad_ok = true;      // feature-major: the gradient kernel's work items exist
     int ngroups = 0;         // same-timestamp groups of a time-ordered series
     int *d_gstart = nullptr, *d_perm = nullptr;
+    int2 *d_frange = nullptr;  // feature range of every 64-point block
     double *d_t = nullptr, *d_y = nullptr;
     int *d_meta = nullptr, *d_off = nullptr, *d_seg_start = nullptr;
     int4 *d_items = nullptr;
@@ -673,7 +674,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
                 e.jitter = rq.jitter; e.nrhs = 1 + rq.nstar; e.nstar = rq.nstar;
                 e.out_index = rq.out_index; e.star_out = rq.star_off;
                 e.skip = 0; e.trange2 = s.trange2; e.pad1 = 0;
-                e.gstart = s.d_gstart; e.perm = s.d_perm; e.ngroups = s.ngroups;
+                e.gstart = s.d_gstart; e.perm = s.d_perm; e.ngroups = s.ngroups; e.frange = s.d_frange;
                 sc.T.push_back(s.T);
                 sc.cnt++;
                 sc.Tmax = std::max(sc.Tmax, s.T);
@@ -981,7 +982,7 @@ MEDGP_API int medgp_cuda_num_hyp(const medgp_ctx *ctx)
 namespace {
 
 struct SeriesLayout {  // byte offsets of a series' arrays inside its device blob
-    size_t o_t, o_y, o_meta, o_off, o_items, o_pair, o_gs, o_perm, total;
+    size_t o_t, o_y, o_meta, o_off, o_items, o_pair, o_gs, o_perm, o_fr, total;
 };
 
 // Host side of an upload: validate, sort, build the gradient work items / timestamp groups,
@@ -1080,7 +1081,8 @@ int prepare_series(int D, int n, const int32_t *meta, const float *x, const floa
     lay.o_pair = lay.o_items + std::max<size_t>(1, items.size()) * sizeof(int4);
     lay.o_gs = align_up(lay.o_pair + seg_start.size() * sizeof(int), 16);
     lay.o_perm = lay.o_gs + gstart.size() * sizeof(int);
-    lay.total = lay.o_perm + (s.time_order ? (size_t)n * sizeof(int) : 0);
+    lay.o_fr = align_up(lay.o_perm + (s.time_order ? (size_t)n * sizeof(int) : 0), 16);
+    lay.total = lay.o_fr + (size_t)s.T * sizeof(int2);
     const size_t base = blob.size();  // 256-aligned by the callers
     blob.resize(base + align_up(lay.total, 256), 0);
     char *bp = blob.data() + base;
@@ -1094,6 +1096,17 @@ int prepare_series(int D, int n, const int32_t *meta, const float *x, const floa
         memcpy(bp + lay.o_gs, gstart.data(), gstart.size() * sizeof(int));
         memcpy(bp + lay.o_perm, s.perm.data(), (size_t)n * sizeof(int));
     }
+    // feature range of every 64-point block: the assembly kernel stages only that part of B_q
+    std::vector<int2> fr(s.T);
+    for (int b = 0; b < s.T; b++) {
+        int lo = D - 1, hi = 0;
+        for (int i = b * MEDGP_NB; i < std::min(n, (b + 1) * MEDGP_NB); i++) {
+            lo = std::min(lo, hm[i]);
+            hi = std::max(hi, hm[i]);
+        }
+        fr[b] = make_int2(std::min(lo, hi), hi);
+    }
+    memcpy(bp + lay.o_fr, fr.data(), fr.size() * sizeof(int2));
     return MEDGP_OK;
 }
 
@@ -1106,6 +1119,7 @@ void bind_series(Series &s, const SeriesLayout &lay, char *d_base, const std::sh
     s.d_off = (int *)(d_base + lay.o_off);
     s.d_items = (int4 *)(d_base + lay.o_items);
     s.d_seg_start = (int *)(d_base + lay.o_pair);
+    s.d_frange = (int2 *)(d_base + lay.o_fr);
     if (s.time_order) {
         s.d_gstart = (int *)(d_base + lay.o_gs);
         s.d_perm = (int *)(d_base + lay.o_perm);
