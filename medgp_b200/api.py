@@ -154,6 +154,12 @@ class Context:
         except Exception:
             pass
 
+    def set_model(self, Q, D, R, pi=PI_REF):
+        """Change the kernel shape of this context (its series must have been cleared)."""
+        self._check(self.lib.medgp_cuda_model(self.h, int(Q), int(D), int(R), float(pi)))
+        self.Q, self.D, self.R = int(Q), int(D), int(R)
+        self.P = self.lib.medgp_cuda_num_hyp(self.h)
+
     # ------------------------------------------------------------------ series
     def add_series(self, meta, x, y, order=ORDER_FEATURE):
         """order=ORDER_TIME uploads the series for predict_online (no gradients on it)."""

@@ -800,7 +800,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
                     auto victim = ctx->graphs.begin();
                     for (auto g = ctx->graphs.begin(); g != ctx->graphs.end(); ++g)
                         if (g->second.last_use < victim->second.last_use) victim = g;
-                    // an exec may still be running: destruction is deferred by the runtime until it has completed
+                    cudaStreamSynchronize(st);  // the victim may still be running (evictions are rare)
                     cudaGraphExecDestroy(victim->second.exec);
                     ctx->graphs.erase(victim);
                 }

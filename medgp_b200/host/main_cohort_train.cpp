@@ -1,6 +1,8 @@
 // main_cohort_train -- train a whole cohort (or one shard of it) on one GPU in lock-step.
 //   main_cohort_train --cfg exp_setup.json --pans <file with one PAN per line>
-//                     [--device d] [--shard i/N] [--host-optimizer] [--max-evals E]
+//                     [--device d] [--shard i/N] [--resume] [--host-optimizer] [--max-evals E]
+// --resume skips the patients whose train_flag_<PAN>.txt already says 1 (the reference's way of
+// resuming is to re-submit the jobs of the patients without results).
 // Per patient this produces exactly the files main_one_train writes and
 // follows the same procedure (score random_init_num random initialisations, optimise the best
 // with SCG or variational EM), but every optimiser super-step evaluates ALL active patients at
@@ -56,20 +58,21 @@ int main(int argc, const char *argv[])
     string exp_cfg, pan_file;
     int device = 0, shard = 0, nshard = 1;
     long max_evals = -1;
-    bool host_optimizer = false;
+    bool host_optimizer = false, resume = false;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--cfg") && i + 1 < argc) exp_cfg = argv[++i];
         else if (!strcmp(argv[i], "--pans") && i + 1 < argc) pan_file = argv[++i];
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--max-evals") && i + 1 < argc) max_evals = atol(argv[++i]);
         else if (!strcmp(argv[i], "--host-optimizer")) host_optimizer = true;
+        else if (!strcmp(argv[i], "--resume")) resume = true;
         else if (!strcmp(argv[i], "--shard") && i + 1 < argc) {
             if (sscanf(argv[++i], "%d/%d", &shard, &nshard) != 2 || nshard < 1 || shard < 0 || shard >= nshard) {
                 cout << "Error: --shard expects i/N" << endl;
                 return 1;
             }
         } else {
-            cout << "usage: main_cohort_train --cfg exp_setup.json --pans list.txt [--device d] [--shard i/N] [--host-optimizer] [--max-evals E]" << endl;
+            cout << "usage: main_cohort_train --cfg exp_setup.json --pans list.txt [--device d] [--shard i/N] [--resume] [--host-optimizer] [--max-evals E]" << endl;
             return 1;
         }
     }
@@ -94,8 +97,18 @@ int main(int argc, const char *argv[])
     const vector<int> sizes = curr_exp.get_cohort_sizes(pans);
     const vector<int> shard_of = medgp_lpt_assign(sizes, nshard);
     vector<string> my_pans;
-    for (size_t k = 0; k < pans.size(); k++)
-        if (shard_of[k] == shard) my_pans.push_back(pans[k]);
+    size_t resumed = 0;
+    for (size_t k = 0; k < pans.size(); k++) {
+        if (shard_of[k] != shard) continue;
+        if (resume) {  // already trained in an earlier run?
+            std::ifstream flag((curr_exp.get_exp_train_dir() + "train_flag_" + pans[k] + ".txt").c_str());
+            std::ifstream hyp((curr_exp.get_exp_train_dir() + "train_hyp_" + pans[k] + ".bin").c_str());
+            int v = 0;
+            if ((flag >> v) && v == 1 && hyp.good()) { resumed++; continue; }
+        }
+        my_pans.push_back(pans[k]);
+    }
+    if (resume) cout << "resume: " << resumed << " patients of this shard already have results" << endl;
     vector<c_experiment::patient_data> loaded;
     curr_exp.get_cohort_data(my_pans, loaded);
     vector<Patient> all(my_pans.size());

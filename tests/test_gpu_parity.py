@@ -264,6 +264,54 @@ def test_export_factors_in_the_callers_order(api, oracle):
     ctx.close()
 
 
+def test_changing_the_model_on_a_live_context(api, oracle):
+    """medgp_cuda_model on a context that already captured launch sequences: the graphs bake in the
+    model (dimensions by value, Q-templated kernels, shared-memory sizes), so none may survive.
+    The same series evaluated under three models in a row -- including larger -> smaller Q with
+    identically shaped batches, the case a stale graph would silently answer."""
+    meta, x, y = synth.make_patient(2, 150, seed=31)
+    ctx = api.Context(3, 2, 2, workspace_bytes=1 << 29)
+    for (Q, D, R) in ((3, 2, 2), (1, 2, 2), (3, 2, 1), (3, 2, 2)):
+        ctx.clear_series()
+        ctx.set_model(Q, D, R)
+        sids = [ctx.add_series(meta, x, y) for _ in range(3)]
+        thetas = synth.init_hyp_lmc_sm(Q, D, R, 3, seed=8)
+        for _ in range(2):  # the second call replays what the first one captured
+            f, g, st = ctx.nlml_grad(sids, thetas, True)
+        for b in range(3):
+            f0, g0, _ = oracle.nlml_grad(Q, D, R, meta, x, y, thetas[b])
+            assert st[b] == 0 and abs(f[b] - f0) <= RTOL * abs(f0) and rel(g[b], g0) <= RTOL
+    with pytest.raises(api.MedgpError):
+        ctx.set_model(2, 2, 2)   # series still uploaded
+    ctx.close()
+
+
+def test_argument_checks(api):
+    Q, D, R = 2, 2, 1
+    ctx = api.Context(Q, D, R, workspace_bytes=1 << 28)
+    meta, x, y = synth.make_patient(D, 30, seed=1)
+    from medgp_b200.api import ORDER_TIME
+    s_time = ctx.add_series(meta, x, y, order=ORDER_TIME)
+    theta = synth.init_hyp_lmc_sm(Q, D, R, 1, seed=1)
+    f, _, st = ctx.nlml_grad([s_time], theta, False)          # NLML works on a time-ordered series
+    assert st[0] == 0 and np.isfinite(f[0])
+    with pytest.raises(api.MedgpError):                        # gradients do not: host entry point ...
+        ctx.nlml_grad([s_time], theta, True)
+    d = [ctx.malloc(ctx.P * 8), ctx.malloc(8), ctx.malloc(ctx.P * 8), ctx.malloc(4)]
+    ctx.h2d(d[0], theta)
+    with pytest.raises(api.MedgpError):                        # ... and device-resident entry point alike
+        ctx.nlml_grad_device(np.array([s_time], dtype=np.int32), d[0], True, d[1], d[2], d[3])
+    with pytest.raises(api.MedgpError):
+        ctx.nlml_grad([12345], theta, False)                   # unknown series
+    with pytest.raises(api.MedgpError):
+        ctx.add_series(np.array([0, 5], dtype=np.int32), x[:2], y[:2])   # feature slot out of range
+    f, g, st = ctx.nlml_grad([], np.zeros((0, ctx.P)), True)   # empty batch
+    assert len(f) == 0
+    for p in d:
+        ctx.free(p)
+    ctx.close()
+
+
 def test_predict(api, oracle):
     Q, D, R = 3, 4, 2
     ctx = api.Context(Q, D, R, workspace_bytes=1 << 30)

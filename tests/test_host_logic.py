@@ -164,6 +164,24 @@ def test_cohort_loader_equals_patient_loader(tmp_path):
     assert ns == [len(p[1]) for p in pats.values()] and same == [1] * len(pats)
 
 
+def test_cohort_driver_resumes(tmp_path):
+    """--resume leaves the patients with train_flag 1 alone and trains the others"""
+    Q, D, R = 2, 2, 2
+    pats = _patients(D, [40, 55, 33], 70)
+    top = str(tmp_path)
+    cfg = expfiles.write_experiment(top, Q, D, R, [18, 19], pats, random_init_num=4, top_iteration_num=8)
+    cohort = os.path.join(top, "data", "cohort.txt")
+    run([os.path.join(BUILD, "main_cohort_train"), "--cfg", cfg, "--pans", cohort])
+    first = {pan: expfiles.read_double_bin(os.path.join(top, "train", f"train_hyp_{pan}.bin")) for pan in pats}
+    os.remove(os.path.join(top, "train", "train_flag_p1.txt"))
+    np.zeros(3).tofile(os.path.join(top, "train", "train_hyp_p0.bin"))       # would be overwritten by a re-train
+    out = run([os.path.join(BUILD, "main_cohort_train"), "--cfg", cfg, "--pans", cohort, "--resume"])
+    assert "resume: 2 patients" in out
+    assert np.array_equal(expfiles.read_double_bin(os.path.join(top, "train", "train_hyp_p0.bin")), np.zeros(3))
+    assert np.array_equal(expfiles.read_double_bin(os.path.join(top, "train", "train_hyp_p1.bin")), first["p1"])
+    assert expfiles.read_int_txt(os.path.join(top, "train", "train_flag_p1.txt")) == [1]
+
+
 def test_cohort_sharding_covers_every_patient(tmp_path):
     Q, D, R = 1, 2, 1
     pats = _patients(D, [30, 45, 38, 52, 41], 80)
