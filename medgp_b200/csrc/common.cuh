@@ -131,6 +131,24 @@ __device__ __forceinline__ int flag_acquire(const int *flag)
     return v;
 }
 
+// Warp -> quadrant assignment of the tile GEMM kernels.  The hardware places warp w of a CTA on
+// SM sub-partition w % 4, each with its own FP64 tensor pipe.  Wherever a quadrant of a tile
+// product is skipped (zero blocks of triangular operands, the unused part of symmetric results,
+// rows beyond the end of a ragged matrix) the same sub-partitions would idle in EVERY resident
+// CTA while the others stay the bottleneck; rotating the assignment by the block index spreads
+// the skipped quadrants over all four pipes.
+#ifndef MEDGP_WARP_ROT
+#define MEDGP_WARP_ROT 1
+#endif
+__device__ __forceinline__ int gemm_warp()
+{
+#if MEDGP_WARP_ROT
+    return ((threadIdx.x >> 5) + blockIdx.x + blockIdx.y) & 3;
+#else
+    return threadIdx.x >> 5;
+#endif
+}
+
 // D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor core (SASS: DMMA.8x8x4)
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
@@ -275,6 +293,9 @@ __device__ __forceinline__ void acc_zero(double (&acc)[4][4][2])
 __device__ __forceinline__ void mma_panels(double (&acc)[4][4][2], const double *sA,
                                            const double *sB, int depth4, int wm, int wn, int lane)
 {
+#ifdef MEDGP_X_NODMMA  // timing experiment: the floor set by everything but the DMMAs (results are wrong)
+    return;
+#endif
     const int r = lane >> 2, kq = lane & 3;
     const double *pa = sA + kq * MEDGP_SLD + wm * 32 + r;
     const double *pb = sB + kq * MEDGP_SLD + wn * 32 + r;
@@ -295,6 +316,47 @@ __device__ __forceinline__ void mma_panels(double (&acc)[4][4][2], const double 
     }
 }
 
+// the same for a tile at the ragged end of a matrix: only the first mx (ny) 8-row sub-tiles of this
+// warp's quadrant hold rows (columns) below n; the others are known to be zero and stay untouched
+__device__ __forceinline__ void mma_panels_edge(double (&acc)[4][4][2], const double *sA,
+                                                const double *sB, int depth4, int wm, int wn, int lane,
+                                                int mx, int ny)
+{
+    const int r = lane >> 2, kq = lane & 3;
+    const double *pa = sA + kq * MEDGP_SLD + wm * 32 + r;
+    const double *pb = sB + kq * MEDGP_SLD + wn * 32 + r;
+#pragma unroll 2
+    for (int kk = 0; kk < depth4; kk++) {
+        double a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            a[u] = pa[8 * u];
+            b[u] = pb[8 * u];
+        }
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+            if (x < mx) {
+#pragma unroll
+                for (int y = 0; y < 4; y++)
+                    if (y < ny) dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+            }
+        pa += 4 * MEDGP_SLD;
+        pb += 4 * MEDGP_SLD;
+    }
+}
+
+// Ragged end of a matrix (n is not a multiple of 64; the padding is the identity, so the
+// off-diagonal tiles of the last block row / column are zero beyond n): m = rows of the A tiles
+// that can be non-zero, n = rows of the B tiles, klast = columns of the LAST tile pair of the sum.
+struct TileEdge {
+    int m = MEDGP_NB, n = MEDGP_NB, klast = MEDGP_NB;
+};
+// number of 8-row sub-tiles of quadrant w (rows 32w ..) that start below `valid`
+__device__ __forceinline__ int edge_subtiles(int valid, int w)
+{
+    return min(4, max(0, (valid - 32 * w + 7) >> 3));
+}
+
 struct NoStageFn {
     __device__ __forceinline__ void operator()(int, const double *) const {}
 };
@@ -308,46 +370,60 @@ struct NoSkipFn {
 // SLD) before it is handed back to the copy engine.
 // SkipFn: bool operator()(int ch, int wm, int wn): true when the 32x32 quadrant (wm, wn) of this
 // warp gets nothing from k-panel ch (a zero block of a triangular operand): its DMMAs are skipped.
-template <class TileFn, class StageFn = NoStageFn, class SkipFn = NoSkipFn>
+template <int NST = MEDGP_NSTAGE, class TileFn, class StageFn = NoStageFn, class SkipFn = NoSkipFn>
 __device__ __forceinline__ void gemm_nt_tiles(double (&acc)[4][4][2], int nl, TileFn tiles,
                                               double *smem, GemmBars *bars, StageFn stagefn = StageFn(),
-                                              SkipFn skipfn = SkipFn())
+                                              SkipFn skipfn = SkipFn(), TileEdge edge = TileEdge())
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = gemm_warp(), lane = threadIdx.x & 31;
     const int wm = warp & 1, wn = warp >> 1;
     const int nch = nl * (MEDGP_NB / MEDGP_KC);
+    const int mx = edge_subtiles(edge.m, wm), ny = edge_subtiles(edge.n, wn);
+    const bool ragged = (mx < 4) || (ny < 4);
     constexpr uint32_t kPanelBytes = kPanelElems * 8;  // 8704 B, one bulk copy
 
     auto issue = [&](int ch) {
         if (lane == 0) {
-            const int s = ch % MEDGP_NSTAGE;
+            const int s = ch % NST;
             const int l = ch / (MEDGP_NB / MEDGP_KC), cc = ch % (MEDGP_NB / MEDGP_KC);
             const double *A, *B;
             tiles(l, A, B);
+#ifdef MEDGP_X_NOLOAD  // timing experiment: the floor set by the DMMAs alone (operands are never fetched)
+            mbar_arrive(&bars->full[s]);
+#else
             mbar_arrive_expect_tx(&bars->full[s], 2 * kPanelBytes);
             double *stage = smem + s * kStageElems;
             bulk_g2s(stage, A + cc * kPanelElems, kPanelBytes, &bars->full[s]);
             bulk_g2s(stage + kPanelElems, B + cc * kPanelElems, kPanelBytes, &bars->full[s]);
+#endif
         }
         __syncwarp();
     };
 
     if (warp == 0)
-        for (int ch = 0; ch < MEDGP_NSTAGE - 1 && ch < nch; ch++) issue(ch);
+        for (int ch = 0; ch < NST - 1 && ch < nch; ch++) issue(ch);
 
     for (int ch = 0; ch < nch; ch++) {
-        const int s = ch % MEDGP_NSTAGE;
+        const int s = ch % NST;
         if (warp == 0) {
-            const int nxt = ch + MEDGP_NSTAGE - 1;
+            const int nxt = ch + NST - 1;
             if (nxt < nch) {
-                if (nxt >= MEDGP_NSTAGE)
-                    mbar_wait(&bars->empty[nxt % MEDGP_NSTAGE], ((nxt / MEDGP_NSTAGE) - 1) & 1);
+                if (nxt >= NST)
+                    mbar_wait(&bars->empty[nxt % NST], ((nxt / NST) - 1) & 1);
                 issue(nxt);
             }
         }
-        mbar_wait(&bars->full[s], (ch / MEDGP_NSTAGE) & 1);
+        mbar_wait(&bars->full[s], (ch / NST) & 1);
         const double *stage = smem + s * kStageElems;
-        if (!skipfn(ch, wm, wn)) mma_panels(acc, stage, stage + kPanelElems, MEDGP_KC / 4, wm, wn, lane);
+        int d4 = MEDGP_KC / 4;
+        if (edge.klast < MEDGP_NB && ch >= nch - MEDGP_NB / MEDGP_KC)  // k-steps of the last tile pair below klast
+            d4 = min(d4, max(0, (edge.klast - MEDGP_KC * (ch & (MEDGP_NB / MEDGP_KC - 1)) + 3) >> 2));
+        if (!skipfn(ch, wm, wn)) {
+            if (ragged || d4 < MEDGP_KC / 4)
+                mma_panels_edge(acc, stage, stage + kPanelElems, d4, wm, wn, lane, mx, ny);
+            else
+                mma_panels(acc, stage, stage + kPanelElems, MEDGP_KC / 4, wm, wn, lane);
+        }
         stagefn(ch, stage);
         // The stage is about to be handed back to the async proxy (bulk copy): order this
         // thread's generic-proxy reads before it.  Without the fence the refill was observed
@@ -361,7 +437,7 @@ __device__ __forceinline__ void gemm_nt_tiles(double (&acc)[4][4][2], int nl, Ti
 // write the accumulator tile (times sign) into a pitch-SLD column-major shared tile
 __device__ __forceinline__ void acc_to_smem(const double (&acc)[4][4][2], double *sT, double sign)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = gemm_warp(), lane = threadIdx.x & 31;
     const int wm = warp & 1, wn = warp >> 1, r = lane >> 2, kq = lane & 3;
 #pragma unroll
     for (int a = 0; a < 4; a++)
@@ -376,7 +452,7 @@ __device__ __forceinline__ void acc_to_smem(const double (&acc)[4][4][2], double
 // acc = base - acc, base a pitch-SLD HBM tile
 __device__ __forceinline__ void acc_rsub_global(double (&acc)[4][4][2], const double *G)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = gemm_warp(), lane = threadIdx.x & 31;
     const int wm = warp & 1, wn = warp >> 1, r = lane >> 2, kq = lane & 3;
 #pragma unroll
     for (int a = 0; a < 4; a++)
@@ -390,7 +466,7 @@ __device__ __forceinline__ void acc_rsub_global(double (&acc)[4][4][2], const do
 
 __device__ __forceinline__ void acc_to_global(const double (&acc)[4][4][2], double *G)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = gemm_warp(), lane = threadIdx.x & 31;
     const int wm = warp & 1, wn = warp >> 1, r = lane >> 2, kq = lane & 3;
 #pragma unroll
     for (int a = 0; a < 4; a++)

@@ -18,15 +18,77 @@ __device__ __forceinline__ double *tile_ptr(double *M, int T, int ti, int tj)
 }
 
 // second product of the panel kernels: acc = sP * X^T with sP, sX pitch-SLD tiles in smem,
-// sP[c][m] (column-major), sX[c][n] = X(n,c)
-__device__ __forceinline__ void gemm2_smem(double (&acc)[4][4][2], const double *sP,
-                                           const double *sX)
+// sP[c][m] (column-major), sX[c][n] = X(n,c), X LOWER triangular: X(n, c) = 0 for c > n, so the
+// 8-column sub-tile starting at column n0 only needs the k-steps (of 4) below (n0 + 8) / 4 --
+// 288 DMMAs per tile instead of 512 (the warp rotation of gemm_warp() evens the two column
+// halves out over the SM's four pipes).  RAGGED: the tile touches the end of the matrix -- only
+// mx / ny sub-tiles of this warp hold rows / columns below n and P is zero from column 4 k4max on.
+template <int WN, bool RAGGED>
+__device__ __forceinline__ void gemm2_tri_half(double (&acc)[4][4][2], const double *sP, const double *sX,
+                                               int wm, int lane, int mx, int ny, int k4max)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wn = warp >> 1;
+    const int r = lane >> 2, kq = lane & 3;
+    const double *pa = sP + kq * MEDGP_SLD + wm * 32 + r;
+    const double *pb = sX + kq * MEDGP_SLD + WN * 32 + r;
+#pragma unroll
+    for (int kk = 0; kk < 8 * WN + 8; kk++) {
+        if (RAGGED && kk >= k4max) break;
+        double a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            a[u] = pa[kk * 4 * MEDGP_SLD + 8 * u];
+            if (kk < 8 * WN + 2 * u + 2) b[u] = pb[kk * 4 * MEDGP_SLD + 8 * u];
+        }
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            if (RAGGED && x >= mx) continue;
+#pragma unroll
+            for (int y = 0; y < 4; y++) {
+                if (kk >= 8 * WN + 2 * y + 2) continue;
+                if (RAGGED && y >= ny) continue;
+                dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+            }
+        }
+    }
+}
+
+// m_valid / n_valid: rows / columns of the result that can be non-zero (64 away from the ragged
+// end); with n_valid < 64 the columns of sP from n_valid on are zero as well (trtri, last row)
+__device__ __forceinline__ void gemm2_smem(double (&acc)[4][4][2], const double *sP, const double *sX,
+                                           int m_valid = MEDGP_NB, int n_valid = MEDGP_NB)
+{
+    const int warp = gemm_warp(), lane = threadIdx.x & 31;
+    const int wm = warp & 1, wn = warp >> 1;
     acc_zero(acc);
-    // X(n, c) = 0 for c > n: output columns 0..31 (wn == 0) only need the first 32 k-steps
-    mma_panels(acc, sP, sX, wn == 0 ? MEDGP_NB / 8 : MEDGP_NB / 4, warp & 1, wn, lane);
+    if (m_valid < MEDGP_NB || n_valid < MEDGP_NB) {
+        const int mx = edge_subtiles(m_valid, wm), ny = edge_subtiles(n_valid, wn);
+        const int k4max = n_valid < MEDGP_NB ? (n_valid + 3) >> 2 : MEDGP_NB / 4;
+        if (wn == 0) gemm2_tri_half<0, true>(acc, sP, sX, wm, lane, mx, ny, k4max);
+        else gemm2_tri_half<1, true>(acc, sP, sX, wm, lane, mx, ny, k4max);
+    } else {
+        if (wn == 0) gemm2_tri_half<0, false>(acc, sP, sX, wm, lane, 4, 4, MEDGP_NB / 4);
+        else gemm2_tri_half<1, false>(acc, sP, sX, wm, lane, 4, 4, MEDGP_NB / 4);
+    }
+}
+
+// symmetric product acc = sP sP^T of which only the lower part is used (the fold of a fresh panel
+// tile into its diagonal block): the upper-right quadrant is skipped; valid = rows of sP below n
+__device__ __forceinline__ void syrk_smem(double (&acc)[4][4][2], const double *sP, int valid = MEDGP_NB)
+{
+    const int warp = gemm_warp(), lane = threadIdx.x & 31;
+    const int wm = warp & 1, wn = warp >> 1;
+    acc_zero(acc);
+    if (wm == 0 && wn == 1) return;
+    if (valid < MEDGP_NB)
+        mma_panels_edge(acc, sP, sP, MEDGP_NB / 4, wm, wn, lane, edge_subtiles(valid, wm), edge_subtiles(valid, wn));
+    else
+        mma_panels(acc, sP, sP, MEDGP_NB / 4, wm, wn, lane);
+}
+
+// rows of the last block row of an evaluation that lie below n (64 for every other block row)
+__device__ __forceinline__ int rows_valid(const EvalDesc &e, int ti)
+{
+    return ti == e.T - 1 ? e.n - MEDGP_NB * (e.T - 1) : MEDGP_NB;
 }
 
 // lower-triangle tile enumeration: p -> (ti, tj), ti >= tj, row by row
@@ -77,7 +139,7 @@ __device__ __forceinline__ void tile_matvec_rhs(const EvalDesc &e, const double 
 __device__ __forceinline__ void acc_matvec_rhs(const double (&acc)[4][4][2], const EvalDesc &e,
                                                const double *zk_base, double *out_base, double *red /*2*64*/)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, ld = e.npad;
+    const int warp = gemm_warp(), lane = threadIdx.x & 31, ld = e.npad;
     const int wm = warp & 1, wn = warp >> 1, r = lane >> 2, kq = lane & 3;
     for (int q = 0; q < e.nrhs; q++) {
         const double *z = zk_base + (size_t)q * ld;
@@ -121,6 +183,10 @@ __device__ __forceinline__ void acc_matvec_rhs(const double (&acc)[4][4][2], con
 //   then the off-diagonal blocks X_IJ = -X_II sum_K L_IK X_KJ, level by level, with DMMA.
 // LAPACK semantics: a non-positive (or NaN) pivot raises *s_fail (potrf info > 0).
 #define MEDGP_DIAG_THREADS 128
+// cycle stamps of the diagonal-block routine for tools/diag_phase.cu (no-op in the library)
+#ifndef MEDGP_PHASE
+#define MEDGP_PHASE(id)
+#endif
 
 // scratch of the diagonal-block routines: d[0] holds 1/L_cc during the factorisation and is the
 // reduction buffer of the forward-solve matvec afterwards
@@ -258,11 +324,13 @@ __device__ __forceinline__ void potf2_inv_blocked(double *sA, double *sX, double
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int lr = lane >> 2, lk = lane & 3;
     for (int i = tid; i < kTileElems; i += MEDGP_DIAG_THREADS) sX[i] = 0.0;
+    MEDGP_PHASE(2)
 #pragma unroll 1
     for (int J = 0; J < 4; J++) {
         const int c0 = 16 * J;
         if (warp == 0) chol16_warp(sA, s_rs, c0, lane, s_fail);
         __syncthreads();
+        MEDGP_PHASE(3 + 3 * J)
         if (J < 3) {
             if (warp < 2) {
                 if (tid >= c0 + 16) panel16_row(sA, s_rs, c0, tid);
@@ -270,12 +338,15 @@ __device__ __forceinline__ void potf2_inv_blocked(double *sA, double *sX, double
                 trinv16_warp(sA, sX, s_rs, c0, lane);
             }
             __syncthreads();
+            MEDGP_PHASE(4 + 3 * J)
             trail16_update(sA, c0, warp, lane);
             __syncthreads();
+            MEDGP_PHASE(5 + 3 * J)
         } else if (warp == 2) {
             trinv16_warp(sA, sX, s_rs, c0, lane);
         }
     }
+    MEDGP_PHASE(13)
     // off-diagonal blocks of X, level d = I - J
 #pragma unroll 1
     for (int d = 1; d < 4; d++) {
@@ -341,6 +412,7 @@ __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, doub
 {
     const int T = e.T, tid = threadIdx.x;
     const double *Kkk = tile_ptr(e.M, T, k, k);
+    MEDGP_PHASE(0)
     // all global loads of this block are issued up front: one memory round trip
     double2 kv[16];
 #pragma unroll
@@ -363,9 +435,12 @@ __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, doub
         *reinterpret_cast<double2 *>(sL + o) = v;
     }
     __syncthreads();  // sD is dead from here on: it receives X
+    MEDGP_PHASE(1)
     potf2_inv_blocked(sL, sD, gjb->d[0], s_fail);
+    MEDGP_PHASE(14)
     // forward solve, block k: z_k = X_kk rhs_k (in place)
     tile_matvec_rhs(e, sD, e.rhs + k * MEDGP_NB, e.rhs + k * MEDGP_NB, true, false, gjb->d[0], true, v0);
+    MEDGP_PHASE(15)
     // write back: L_kk (lower), dinv (X column-major), dinvT (X^T column-major)
     double *Lkk = tile_ptr(e.M, T, k, k);
     double *Xk = e.dinv + (size_t)k * kTileElems;
@@ -385,6 +460,7 @@ __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, doub
             if (*s_fail) fail[e.out_index] = 1;
         }
     }
+    MEDGP_PHASE(16)
 }
 
 // Stand-alone diagonal kernel, one CTA per evaluation: D = K_kk - sum_{l<depth} L_kl L_kl^T.
@@ -416,7 +492,8 @@ k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int depth, int *__restri
                       },
                       smem, &bars, NoStageFn(),
                       // only the lower part of the symmetric product is used
-                      [](int, int wm, int wn) { return wm == 0 && wn == 1; });
+                      [](int, int wm, int wn) { return wm == 0 && wn == 1; },
+                      TileEdge{rows_valid(e, k), rows_valid(e, k), MEDGP_NB});
         __syncthreads();  // all warps are done with the ring before it is reused as sD
         acc_to_smem(acc, sD, 1.0);
     }
@@ -442,6 +519,7 @@ k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_dia
     prefetch_tile_l2(Tik);  // epilogue operands: start them towards L2 now
     prefetch_tile_l2(Xk);
     gemm_bars_init(&bars);
+    const int mv = rows_valid(e, i);  // the last block row is zero from row mv on
     double acc[4][4][2];
     acc_zero(acc);
     gemm_nt_tiles(acc, depth,
@@ -449,7 +527,7 @@ k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_dia
                       A = tile_ptr(M, T, i, l);
                       B = tile_ptr(M, T, k, l);
                   },
-                  smem, &bars);
+                  smem, &bars, NoStageFn(), NoSkipFn(), TileEdge{mv, MEDGP_NB, MEDGP_NB});
     __syncthreads();  // every warp is done with the pipeline buffers
     double *sP = smem, *sX = smem + kTileElems;
     tile_bulk_g2s(sX, Xk, &bars);  // X_kk arrives while P = K_ik - C is formed
@@ -457,7 +535,7 @@ k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_dia
     acc_to_smem(acc, sP, 1.0);
     tile_bulk_wait(&bars);
     __syncthreads();
-    gemm2_smem(acc, sP, sX);
+    gemm2_smem(acc, sP, sX, mv);
     acc_to_global(acc, Tik);
     // forward solve: push the fresh tile into the right-hand sides of block row i
     acc_matvec_rhs(acc, e, e.rhs + k * MEDGP_NB, e.rhs + i * MEDGP_NB, red);
@@ -466,12 +544,9 @@ k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_dia
         // diagonal kernel has a k-tile product to do.  With fold_diag == 2 the CTA of row k+1,
         // whose diagonal block is now complete, factors it on the spot: the next step's
         // diagonal kernel disappears and its latency hides behind the other panel CTAs.
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         acc_to_smem(acc, sP, 1.0);  // (acc_matvec_rhs ended with a block barrier: GEMM2 is done with sP)
         __syncthreads();
-        acc_zero(acc);
-        if (!((warp & 1) == 0 && (warp >> 1) == 1))  // symmetric product: the upper-right quadrant is never used
-            mma_panels(acc, sP, sP, MEDGP_NB / 4, warp & 1, warp >> 1, lane);
+        syrk_smem(acc, sP, mv);
         if (fold_diag == 2 && i == k + 1) {
             __shared__ __align__(16) GjBufs gjb;
             __shared__ int s_fail;
@@ -534,6 +609,7 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, 
     const double *Xk = e.dinv + (size_t)k * kTileElems;
     prefetch_tile_l2(Tik);
     gemm_bars_init(&bars);
+    const int mv = rows_valid(e, i);
     double acc[4][4][2];
     acc_zero(acc);
     gemm_nt_tiles(acc, k,
@@ -541,7 +617,7 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, 
                       A = tile_ptr(M, T, i, l);
                       B = tile_ptr(M, T, k, l);
                   },
-                  smem, &bars);
+                  smem, &bars, NoStageFn(), NoSkipFn(), TileEdge{mv, MEDGP_NB, MEDGP_NB});
     acc_rsub_global(acc, Tik);  // P = K_ik - C (does not depend on the diagonal block)
     __syncthreads();            // every warp is done with the pipeline buffers
     acc_to_smem(acc, sP, 1.0);
@@ -551,16 +627,13 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, 
     tile_bulk_g2s(sX, Xk, &bars);
     tile_bulk_wait(&bars);
     __syncthreads();
-    gemm2_smem(acc, sP, sX);
+    gemm2_smem(acc, sP, sX, mv);
     acc_to_global(acc, Tik);
     acc_matvec_rhs(acc, e, e.rhs + k * MEDGP_NB, e.rhs + i * MEDGP_NB, red);
     // fold into the own diagonal block: K_ii -= L_ik L_ik^T
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     acc_to_smem(acc, sP, 1.0);
     __syncthreads();
-    acc_zero(acc);
-    if (!((warp & 1) == 0 && (warp >> 1) == 1))  // symmetric product: the upper-right quadrant is never used
-        mma_panels(acc, sP, sP, MEDGP_NB / 4, warp & 1, warp >> 1, lane);
+    syrk_smem(acc, sP, mv);
     double *Kii = tile_ptr(M, T, i, i);
     acc_rsub_global(acc, Kii);
     acc_to_global(acc, Kii);
@@ -583,6 +656,9 @@ k_retry_decide(EvalDesc *__restrict__ descs, int count, int *__restrict__ fail, 
     for (int b = threadIdx.x; b < count; b += blockDim.x) {
         EvalDesc &e = descs[b];
         if (e.skip) continue;
+#if defined(MEDGP_X_NODMMA) || defined(MEDGP_X_NOLOAD)
+        fail[e.out_index] = 0;  // timing experiments produce garbage: one pass only
+#endif
         if (fail[e.out_index] != 0 && e.jitter < max_jitter) {
             e.jitter++;
             fail[e.out_index] = 0;
@@ -606,7 +682,7 @@ k_trtri_row(const EvalDesc *__restrict__ descs, int i, int right_looking)
     const EvalDesc &e = descs[blockIdx.y];
     const int j = blockIdx.x;
     if (i >= e.T || j >= i || e.skip) return;
-    const int T = e.T;
+    const int T = e.T, nv = rows_valid(e, i);
     gemm_bars_init(&bars);
     double acc[4][4][2];
     acc_zero(acc);
@@ -624,7 +700,9 @@ k_trtri_row(const EvalDesc *__restrict__ descs, int i, int right_looking)
                       },
                       smem, &bars, NoStageFn(),
                       // U_jj = X_jj^T is upper triangular: rows 32..63 vanish in k-panels 0 and 1
-                      [](int ch, int wm, int) { return ch < 2 && wm == 1; });
+                      [](int ch, int wm, int) { return ch < 2 && wm == 1; },
+                      // block row i of L ends at row nv: columns nv.. of U_ji are zero
+                      TileEdge{MEDGP_NB, nv, MEDGP_NB});
     }
     __syncthreads();
     double *sP = smem, *sX = smem + kTileElems;
@@ -632,7 +710,7 @@ k_trtri_row(const EvalDesc *__restrict__ descs, int i, int right_looking)
     acc_to_smem(acc, sP, -1.0);
     tile_bulk_wait(&bars);
     __syncthreads();
-    gemm2_smem(acc, sP, sX);
+    gemm2_smem(acc, sP, sX, MEDGP_NB, nv);
     acc_to_global(acc, tile_ptr(M, T, j, i));
 }
 
@@ -673,7 +751,8 @@ k_syrk_update(const EvalDesc *__restrict__ descs, int k, int part)
                   },
                   smem, &bars, NoStageFn(),
                   // diagonal tiles: only the lower part of the symmetric update is used
-                  [=](int, int wm, int wn) { return diag && wm == 0 && wn == 1; });
+                  [=](int, int wm, int wn) { return diag && wm == 0 && wn == 1; },
+                  TileEdge{rows_valid(e, i), rows_valid(e, j), MEDGP_NB});
     double *Cij = tile_ptr(M, T, i, j);
     acc_rsub_global(acc, Cij);
     acc_to_global(acc, Cij);
@@ -700,10 +779,11 @@ k_trtri_update(const EvalDesc *__restrict__ descs, int k)
                   },
                   smem, &bars, NoStageFn(),
                   // U_kk is upper triangular: rows 32..63 vanish in k-panels 0 and 1
-                  [=](int ch, int wm, int) { return j == k && ch < 2 && wm == 1; });
+                  [=](int ch, int wm, int) { return j == k && ch < 2 && wm == 1; },
+                  TileEdge{MEDGP_NB, rows_valid(e, i), MEDGP_NB});
     double *Aji = tile_ptr(M, T, j, i);
     if (j != k) {  // first touch (j == k) initialises the accumulator tile
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int warp = gemm_warp(), lane = threadIdx.x & 31;
         const int wm = warp & 1, wn = warp >> 1, r = lane >> 2, kq = lane & 3;
 #pragma unroll
         for (int x = 0; x < 4; x++)
@@ -721,7 +801,14 @@ k_trtri_update(const EvalDesc *__restrict__ descs, int k)
 // grid (lower tiles, evaluations): (K^-1)_ij = sum_{l>=i} U_il U_jl^T  -> written over L_ij.
 // The CTAs of the diagonal tiles stream the whole block row i of U anyway, so they also form
 // alpha_i = (L^-T z)_i = sum_l U_il z_l from the resident panels (no separate pass over U).
-__global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
+#ifndef MEDGP_LAUUM_NST
+// k_lauum has no two-tile epilogue, so its shared memory is the pipeline alone: 3 stages (52 KB)
+// and 128 registers let 4 CTAs share an SM (16 warps) where the other tile kernels run 3
+#define MEDGP_LAUUM_NST 3
+#define MEDGP_LAUUM_OCC 4
+#endif
+constexpr int kLauumSmemBytes = MEDGP_LAUUM_NST * kStageElems * 8;
+__global__ void __launch_bounds__(MEDGP_GEMM_THREADS, MEDGP_LAUUM_OCC)
 k_lauum(const EvalDesc *__restrict__ descs)
 {
     extern __shared__ __align__(128) double smem[];
@@ -741,7 +828,7 @@ k_lauum(const EvalDesc *__restrict__ descs)
     const int m = threadIdx.x & 63, kh = (threadIdx.x >> 6) * (MEDGP_KC / 2);
     const double *z = e.rhs + i * MEDGP_NB + kh;
     double asum = 0.0;
-    gemm_nt_tiles(acc, T - i,
+    gemm_nt_tiles<MEDGP_LAUUM_NST>(acc, T - i,
                   [&](int l0, const double *&A, const double *&B) {
                       const int l = i + l0;
                       A = (l0 == 0) ? XTi : tile_ptr(M, T, i, l);
@@ -761,7 +848,9 @@ k_lauum(const EvalDesc *__restrict__ descs)
                   // upper-right quadrant (rows 0..31, columns 32..63) is not computed at all.
                   [&](int ch, int wm, int wn) {
                       return (diag && wm == 0 && wn == 1) || (ch < 2 && (wm == 1 || (diag && wn == 1)));
-                  });
+                  },
+                  // the last tiles of block rows i, j < T-1 of U are zero from column n - 64 (T-1) on
+                  TileEdge{MEDGP_NB, MEDGP_NB, i < T - 1 ? rows_valid(e, T - 1) : MEDGP_NB});
     acc_to_global(acc, tile_ptr(M, T, i, j));
     if (diag) {
         s_al[threadIdx.x] = asum;
@@ -811,7 +900,12 @@ k_solve(const EvalDesc *__restrict__ descs, ModelDims md, double *__restrict__ o
     block_reduce_sum<2>(v, scratch);
     if (tid == 0) {
         // force_fail (tests of the jitter path): the first attempts count as failed factorisations
+#if defined(MEDGP_X_NODMMA) || defined(MEDGP_X_NOLOAD)
+        const bool bad = false;  // timing experiments produce garbage: no retries
+        fail[e.out_index] = 0;
+#else
         const bool bad = fail[e.out_index] != 0 || e.jitter < force_fail;
+#endif
         if (bad) fail[e.out_index] = 1;
         const double nlml = 0.5 * v[0] + v[1] + e.n * log(2.0 * md.pi) / 2.0;
         out_nlml[e.out_index] = bad ? __longlong_as_double(0x7ff8000000000000LL) : nlml;

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <functional>
 #include <map>
 #include <memory>
@@ -561,7 +562,7 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     }
     if (grad) {
         begin(MEDGP_STAGE_LAUUM);
-        out.push_back([=]() { k_lauum<<<dim3(ntri, ncta), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd); L[MEDGP_STAGE_LAUUM]++; });
+        out.push_back([=]() { k_lauum<<<dim3(ntri, ncta), MEDGP_GEMM_THREADS, kLauumSmemBytes + ctx->gemm_smem_pad, st>>>(dd); L[MEDGP_STAGE_LAUUM]++; });
         end(MEDGP_STAGE_LAUUM);
         begin(MEDGP_STAGE_GRAD);
         const int items = scp->items_max;
@@ -849,8 +850,16 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
         return MEDGP_ERR_NODEVICE;  // the fatbin holds sm_100a code only
     medgp_ctx *ctx = new medgp_ctx();
     ctx->device = device;
+    // The streams that carry a factorisation's critical path (diagonal block -> panel -> first
+    // trailing column) run at the highest priority, the auxiliary streams that carry the bulk of
+    // the look-ahead trailing updates at the lowest: the block scheduler then hands freed SM slots
+    // to a waiting critical kernel before the next wave of a bulk update, also when several
+    // matrices are in flight on different streams.  MEDGP_PRIO=0: all streams alike (experiments).
+    int prio_lo = 0, prio_hi = 0;
+    cudaSetDevice(device);
+    if (!(getenv("MEDGP_PRIO") && atoi(getenv("MEDGP_PRIO")) == 0)) cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaSetDevice(device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
         delete ctx;
         return MEDGP_ERR_CUDA;
     }
@@ -878,8 +887,8 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     if (const char *ev = getenv("MEDGP_FORCE_FAIL")) ctx->force_fail = std::max(0, atoi(ev));  // tests of the jitter path through the executables
     if (const char *ev = getenv("MEDGP_STREAMS")) ctx->max_streams = std::max(1, std::min(8, atoi(ev)));
     for (int i = 0; i < 8; i++) {
-        cudaStreamCreateWithFlags(&ctx->sub_streams[i], cudaStreamNonBlocking);
-        cudaStreamCreateWithFlags(&ctx->aux_streams[i], cudaStreamNonBlocking);
+        cudaStreamCreateWithPriority(&ctx->sub_streams[i], cudaStreamNonBlocking, prio_hi);
+        cudaStreamCreateWithPriority(&ctx->aux_streams[i], cudaStreamNonBlocking, prio_lo);
         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_panel[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_bulk[i], cudaEventDisableTiming);
@@ -1760,6 +1769,28 @@ MEDGP_API int medgp_cuda_scg_run(medgp_scg *g, int super_steps, int *active_left
     const int count = g->S.count;
     std::vector<Request> reqs;
     for (int b : g->launch) reqs.push_back({g->series[b], b, 0, 0, 0});
+    // MEDGP_SCG_TRACE: one line per poll on stderr (launch set, live instances, device time of the
+    // super-steps, host time to enqueue them, wall time of the whole poll)
+    static const bool trace = getenv("MEDGP_SCG_TRACE") != nullptr;
+    static cudaEvent_t tr_a = nullptr, tr_b = nullptr;
+    const auto w0 = std::chrono::steady_clock::now();
+    if (trace) {
+        if (!tr_a) { cudaEventCreate(&tr_a); cudaEventCreate(&tr_b); }
+        cudaEventRecord(tr_a, ctx->stream);
+    }
+    struct TraceEnd {
+        medgp_scg *g; bool on; std::chrono::steady_clock::time_point w0; size_t nreq; int steps;
+        std::chrono::steady_clock::time_point w1;
+        ~TraceEnd() {
+            if (!on) return;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, tr_a, tr_b);
+            const auto w2 = std::chrono::steady_clock::now();
+            fprintf(stderr, "scg poll: launch=%zu live=%zu steps=%d gpu=%.3f ms enqueue=%.3f ms wall=%.3f ms\n", nreq,
+                    g->live.size(), steps, ms, std::chrono::duration<double, std::milli>(w1 - w0).count(),
+                    std::chrono::duration<double, std::milli>(w2 - w0).count());
+        }
+    } trace_end{g, trace, w0, reqs.size(), super_steps, w0};
     for (int step = 0; step < super_steps && !reqs.empty(); step++) {
         int rc = ensure_staging(ctx, count, 0);
         if (rc) return rc;
@@ -1774,6 +1805,10 @@ MEDGP_API int medgp_cuda_scg_run(medgp_scg *g, int super_steps, int *active_left
         if (rc) return rc;
         rc = scg_advance(g);
         if (rc) return rc;
+    }
+    if (trace) {
+        cudaEventRecord(tr_b, ctx->stream);
+        trace_end.w1 = std::chrono::steady_clock::now();
     }
     return scg_count_active(g, active_left);
 }

@@ -2,6 +2,7 @@
 // blocking c_optimizer_scg / c_optimizer_varEM built on them.  Evaluation-for-evaluation the
 // same control flow as medgpc/src/util/c_optimizer_scg.cpp:25-284 and
 // c_optimizer_varEM.cpp:26-163, including the reference's quirks (see comments).
+#include <chrono>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -441,11 +442,16 @@ long medgp_optimize_on_device(medgp_ctx *ctx, const vector<int> &kernel_param, i
             any_prior = any_prior || (it.prior != nullptr && !external);
         }
         medgp_scg *scg = nullptr;
+        const bool trace = getenv("MEDGP_SCG_TRACE") != nullptr;
+        auto tnow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double tr0 = tnow();
         int rc = medgp_cuda_scg_create(ctx, count, &scg);
+        const double tr1 = tnow();
         if (rc != MEDGP_OK) die_opt("medgp_cuda_scg_create", ctx, rc);
         rc = medgp_cuda_scg_start(scg, sids.data(), theta0.data(), budget.data(), any_prior ? ptype.data() : nullptr,
                                   any_prior ? pexp.data() : nullptr, any_prior ? ppar.data() : nullptr);
         if (rc != MEDGP_OK) die_opt("medgp_cuda_scg_start", ctx, rc);
+        const double tr2 = tnow();
         // ---- run the round to completion
         if (!external) {
             int left = count;
@@ -484,7 +490,11 @@ long medgp_optimize_on_device(medgp_ctx *ctx, const vector<int> &kernel_param, i
         std::vector<int> evals(count);
         rc = medgp_cuda_scg_result(scg, best.data(), loss.data(), evals.data());
         if (rc != MEDGP_OK) die_opt("medgp_cuda_scg_result", ctx, rc);
+        const double tr4 = tnow();
         medgp_cuda_scg_destroy(scg);
+        if (trace)
+            std::cerr << "scg round: count=" << count << " create " << tr1 - tr0 << " ms, start " << tr2 - tr1 << " ms, run+result "
+                      << tr4 - tr2 << " ms, destroy " << tnow() - tr4 << " ms" << std::endl;
         for (int b = 0; b < count; b++) {
             medgp_opt_instance &it = inst[who[b]];
             const vector<double> x(best.begin() + (size_t)b * P, best.begin() + (size_t)(b + 1) * P);

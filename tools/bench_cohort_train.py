@@ -22,6 +22,9 @@ cfg = expfiles.write_experiment(top, Q, D, R, list(range(1, D + 1)), pats, prior
                                 top_iteration_num=iters)
 t0 = time.perf_counter()
 out = subprocess.run([os.path.join(ROOT, "medgp_b200", "host", "main_cohort_train"), "--cfg", cfg, "--pans",
-                      os.path.join(top, "data", "cohort.txt")], capture_output=True, text=True, check=True).stdout
+                      os.path.join(top, "data", "cohort.txt")], capture_output=True, text=True, check=True)
+if os.environ.get("MEDGP_SCG_TRACE"):
+    print(out.stderr)
+out = out.stdout
 print("\n".join(l for l in out.splitlines() if "phase" in l or "Finish" in l or "shard" in l))
 print(f"wall {time.perf_counter() - t0:.2f} s")
