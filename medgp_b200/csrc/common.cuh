@@ -119,6 +119,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
         : "memory");
 }
 
+// 1-D bulk copy shared -> global through the TMA engine (bulk async-group completion).  The
+// caller orders its shared-memory writes with fence.proxy.async + a barrier first, commits the
+// group and waits for it (at least for its reads) before the shared source is reused or freed.
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+
 // inter-CTA flag (same kernel): release by the producer CTA, acquire-spin by the consumers
 __device__ __forceinline__ void flag_release(int *flag)
 {

@@ -118,10 +118,15 @@ __device__ __forceinline__ void tile_matvec_rhs(const EvalDesc &e, const double 
     for (int q = 0; q < e.nrhs; q++) {
         if (tid < MEDGP_NB) vs[tid] = (q == 0 && have_v0) ? v0 : vec_base[(size_t)q * ld + tid];
         __syncthreads();
-        double s = 0.0;
         const int cmax = lower_only ? r : MEDGP_NB - 1;
-#pragma unroll 4
-        for (int c = half; c <= cmax; c += 2) s += sTile[c * MEDGP_SLD + r] * vs[c];
+        double s4[4] = {0.0, 0.0, 0.0, 0.0};  // four independent chains
+        int c = half;
+        for (; c + 6 <= cmax; c += 8) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) s4[u] = fma(sTile[(c + 2 * u) * MEDGP_SLD + r], vs[c + 2 * u], s4[u]);
+        }
+        for (; c <= cmax; c += 2) s4[0] = fma(sTile[c * MEDGP_SLD + r], vs[c], s4[0]);
+        const double s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         red[half * MEDGP_NB + r] = s;
         __syncthreads();
         if (half == 0) {
@@ -170,17 +175,21 @@ __device__ __forceinline__ void acc_matvec_rhs(const double (&acc)[4][4][2], con
 
 // ------------------------------------------------------------------ potrf: diagonal block k
 // Cholesky factor L and triangular inverse X = L^-1 of one 64x64 block held in shared memory,
-// 128 threads, blocked by 16 columns so that the only serial chain is the 64 pivots:
-//   for J = 0..3 (column block c0 = 16 J):
-//     (a) warp 0 factors the 16x16 diagonal block in registers (lane = row), exchanging the
-//         pivot column by shuffles; the reciprocal square root of the NEXT pivot is started
-//         before the rest of the rank-1 update is issued, so per pivot the chain is
-//         shuffle -> multiply -> fma -> rsqrt.
-//     (b) warps 0-1 (lane = row) solve the rows below against the block, L_IJ = S_IJ L_JJ^-T,
-//         by right-looking substitution in registers, while warp 2 inverts the diagonal block
-//         (lane = column).
-//     (c) all warps apply the rank-16 update to the trailing lower part with DMMA.
-//   then the off-diagonal blocks X_IJ = -X_II sum_K L_IK X_KJ, level by level, with DMMA.
+// 128 threads, blocked by 16 columns so that the only serial chain is the 64 pivots.  For
+// J = 0..3 (column block c0 = 16 J):
+//   (1) warp 0 factors the 16x16 diagonal block in registers: lanes 0-15 hold its rows, and
+//       lanes 16-31 run the forward substitution L X = I for the block's inverse in the SAME
+//       instruction stream (with v = -e_c as the start vector both recurrences are
+//       v[c] -= w L_cj, w = v[j] / L_jj), so X_JJ costs nothing.  Per pivot the chain is
+//       shuffle -> multiply -> fma -> rsqrt; the reciprocal square root of the next pivot is
+//       started before the rest of the rank-1 update is issued.
+//       Meanwhile warps 1-3 do what is off the critical path: the trailing tiles of the previous
+//       column block that the next step does not need yet, and the off-diagonal blocks of X
+//       whose inputs are complete (X_10 during J = 2; X_20, X_21 during J = 3).
+//   (2) the rows below by substitution against L_JJ, one thread per row;
+//   (3) all warps: rank-16 update of the NEXT column block only (what step J+1 needs).
+// After J = 3 one level is left: X_3J = -X_33 sum_K L_3K X_KJ on warps 0-2 while warp 3 forms the
+// block's log-determinant.
 // LAPACK semantics: a non-positive (or NaN) pivot raises *s_fail (potrf info > 0).
 #define MEDGP_DIAG_THREADS 128
 // cycle stamps of the diagonal-block routine for tools/diag_phase.cu (no-op in the library)
@@ -188,10 +197,11 @@ __device__ __forceinline__ void acc_matvec_rhs(const double (&acc)[4][4][2], con
 #define MEDGP_PHASE(id)
 #endif
 
-// scratch of the diagonal-block routines: d[0] holds 1/L_cc during the factorisation and is the
-// reduction buffer of the forward-solve matvec afterwards
+// scratch of the diagonal-block routines: the reduction buffer of the forward-solve matvec and
+// the block's log-determinant
 struct GjBufs {
     double d[3][MEDGP_NB];
+    double logdet;
 };
 
 // 1/sqrt(d): hardware approximation (about 22 bits) refined by one third-order step,
@@ -206,63 +216,72 @@ __device__ __forceinline__ double rsqrt_fast(double d)
     return fma(y * e, p, y);
 }
 
-// (a) 16x16 diagonal block at (c0, c0): in-place Cholesky (lower part), 1/L_cc -> s_rs[c0 + c].
-// One warp, lane = row (lanes 16..31 mirror lanes 0..15 and store nothing).  The pivot's
-// reciprocal square root travels by shuffle (it is on the serial chain); the pivot column is
-// stored to the tile itself -- its final place -- and read back as broadcasts.
-__device__ __forceinline__ void chol16_warp(double *sA, double *s_rs, int c0, int lane, int *s_fail)
+// (1) 16x16 diagonal block at (c0, c0): in-place Cholesky (lower part of sA) and its inverse
+// (full block of sX, zeros above the diagonal).  One warp: lane r < 16 = row r of the block,
+// lane 16 + c = column c of the inverse.  The pivot's reciprocal square root travels by shuffle
+// (it is on the serial chain); the pivot column is stored to the tile itself -- its final place
+// -- and read back as broadcasts by both halves of the warp.
+__device__ __forceinline__ void chol16_inv_warp(double *sA, double *sX, int c0, int lane, int *s_fail)
 {
     const int r = lane & 15;
-    double a[16];
+    const bool xl = lane >= 16;
+    double v[16];
 #pragma unroll
-    for (int c = 0; c < 16; c++) a[c] = (c <= r) ? sA[(c0 + c) * MEDGP_SLD + c0 + r] : 0.0;
-    __syncwarp();  // the mirror lanes have read the block before its columns are overwritten below
-    double rs = rsqrt_fast(a[0]), rs_mine = rs;
+    for (int c = 0; c < 16; c++)
+        v[c] = xl ? (c == r ? -1.0 : 0.0) : ((c <= r) ? sA[(c0 + c) * MEDGP_SLD + c0 + r] : 0.0);
+    __syncwarp();  // the block has been read before its columns are overwritten below
+    double rs = rsqrt_fast(v[0]);
     bool bad = false;
+    double *dst = xl ? sX + (c0 + r) * MEDGP_SLD + c0 : sA + c0 * MEDGP_SLD + c0 + r;
+    const int stride = xl ? 1 : MEDGP_SLD, sgn = xl ? -1 : 1;
+    const double sign = xl ? -1.0 : 1.0;
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-        bad = bad || (r == j && !(a[j] > 0.0));
-        rs_mine = (r == j) ? rs : rs_mine;
+        bad = bad || (!xl && r == j && !(v[j] > 0.0));
         const double rsj = __shfl_sync(0xffffffffu, rs, j);
-        const double l = a[j] * rsj;  // L_rj for r >= j (r == j: sqrt of the pivot)
+        const double w = v[j] * rsj;  // rows: L_rj (r == j: sqrt of the pivot); X lanes: -X_jc
         double *col = sA + (c0 + j) * MEDGP_SLD + c0;
-        if (lane < 16 && r >= j) col[r] = l;
+        // ONE unconditional store for both halves of the warp (a branch here would split the warp at
+        // every pivot): rows write L_rj down column j (zeros above the diagonal, which is what is
+        // there already), X lanes write X_jc = -w along their own column (zeros above the diagonal)
+        dst[j * stride] = ((r - j) * sgn >= 0) ? sign * w : 0.0;
         if (j < 15) {
-            rs = rsqrt_fast(fma(-l, l, a[j + 1]));  // next pivot: meaningful in lane j + 1
+            rs = rsqrt_fast(fma(-w, w, v[j + 1]));  // next pivot: meaningful in lane j + 1
             __syncwarp();
+            const double p = -w;
             if (j & 1) {  // rows j+1 .. 15 of column j; 16-byte aligned pairs start at an even row
 #pragma unroll
                 for (int c = j + 1; c < 16; c += 2) {
                     const double2 lc = *reinterpret_cast<const double2 *>(col + c);
-                    a[c] = fma(-l, lc.x, a[c]);
-                    a[c + 1] = fma(-l, lc.y, a[c + 1]);
+                    v[c] = fma(p, lc.x, v[c]);
+                    v[c + 1] = fma(p, lc.y, v[c + 1]);
                 }
             } else {
-                a[j + 1] = fma(-l, col[j + 1], a[j + 1]);
+                v[j + 1] = fma(p, col[j + 1], v[j + 1]);
 #pragma unroll
                 for (int c = j + 2; c < 16; c += 2) {
                     const double2 lc = *reinterpret_cast<const double2 *>(col + c);
-                    a[c] = fma(-l, lc.x, a[c]);
-                    a[c + 1] = fma(-l, lc.y, a[c + 1]);
+                    v[c] = fma(p, lc.x, v[c]);
+                    v[c + 1] = fma(p, lc.y, v[c + 1]);
                 }
             }
         }
     }
-    if (lane < 16) {
-        if (bad) *s_fail = 1;
-        s_rs[c0 + r] = rs_mine;
-    }
+    if (!xl && bad) *s_fail = 1;
 }
 
-// (b) one row below the diagonal block: l_rj = (s_rj - sum_{c<j} l_rc L_jc) / L_jj, right-looking
-__device__ __forceinline__ void panel16_row(double *sA, const double *s_rs, int c0, int row)
+// (2) one row below the diagonal block: l_rj = (s_rj - sum_{c<j} l_rc L_jc) / L_jj by right-looking
+// substitution in registers (thread = row).  Substitution, not a product with the explicit inverse
+// X_JJ: on ill-conditioned blocks (condition 1e8 and beyond) the product loses an order of
+// magnitude of accuracy; 1 / L_jj is the diagonal of X_JJ.
+__device__ __forceinline__ void panel16_row(double *sA, const double *sX, int c0, int row)
 {
     double a[16];
 #pragma unroll
     for (int c = 0; c < 16; c++) a[c] = sA[(c0 + c) * MEDGP_SLD + row];
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-        const double l = a[j] * s_rs[c0 + j];
+        const double l = a[j] * sX[(c0 + j) * MEDGP_SLD + c0 + j];
         a[j] = l;
 #pragma unroll
         for (int c = j + 1; c < 16; c++) a[c] = fma(-l, sA[(c0 + j) * MEDGP_SLD + c0 + c], a[c]);
@@ -271,133 +290,142 @@ __device__ __forceinline__ void panel16_row(double *sA, const double *s_rs, int 
     for (int c = 0; c < 16; c++) sA[(c0 + c) * MEDGP_SLD + row] = a[c];
 }
 
-// (b') inverse of the 16x16 diagonal block of L into sX (full block, zeros above the diagonal).
-// One warp, lane = column c: x_cc = 1/L_cc, x_kc = -(sum_{m<k} L_km x_mc) / L_kk.
-__device__ __forceinline__ void trinv16_warp(const double *sA, double *sX, const double *s_rs, int c0, int lane)
-{
-    const int c = lane & 15;
-    double acc[16], x[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) acc[k] = 0.0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const double rk = s_rs[c0 + k];
-        const double xk = (k == c) ? rk : ((k > c) ? -rk * acc[k] : 0.0);
-        x[k] = xk;
-#pragma unroll
-        for (int r = k + 1; r < 16; r++) acc[r] = fma(sA[(c0 + k) * MEDGP_SLD + c0 + r], xk, acc[r]);
-    }
-    if (lane < 16) {
-#pragma unroll
-        for (int r = 0; r < 16; r++) sX[(c0 + c) * MEDGP_SLD + c0 + r] = x[r];
-    }
-}
-
-// (c) trailing update S -= P P^T, P = the 16 columns at c0, rows/columns >= c0 + 16, lower
-// 8x8 tiles dealt round-robin to the 4 warps
-__device__ __forceinline__ void trail16_update(double *sA, int c0, int warp, int lane)
+// (3) trailing update S -= P P^T with P = the 16 columns at c0, restricted to the lower 8x8 tiles
+// of the column tiles ct_lo .. ct_lo+NCT-1 (counted from column c0 + 16).  Row tiles are dealt
+// to nw warps (this one is wi); the tiles of a row are independent DMMA chains.
+template <int NCT>
+__device__ __forceinline__ void trail16_cols(double *sA, int c0, int ct_lo, int wi, int nw, int lane)
 {
     const int c1 = c0 + 16, m = (MEDGP_NB - c1) / 8;
     const int lr = lane >> 2, lk = lane & 3;
-    int cnt = 0;
-    for (int ti = 0; ti < m; ti++)
-        for (int tj = 0; tj <= ti; tj++, cnt++) {
-            if ((cnt & 3) != warp) continue;
-            const int row0 = c1 + 8 * ti, col0 = c1 + 8 * tj;
-            double *pc = sA + (col0 + 2 * lk) * MEDGP_SLD + row0 + lr;
-            double v0 = pc[0], v1 = pc[MEDGP_SLD];
+    for (int rt = ct_lo + wi; rt < m; rt += nw) {
+        const int row0 = c1 + 8 * rt;
+        double v[NCT][2], v2[NCT][2];  // two independent chains per tile (even / odd k-steps)
 #pragma unroll
-            for (int kk = 0; kk < 4; kk++) {
-                const double *pk = sA + (c0 + 4 * kk + lk) * MEDGP_SLD;
-                dmma884(v0, v1, -pk[row0 + lr], pk[col0 + lr]);
+        for (int u = 0; u < NCT; u++)
+            if (ct_lo + u <= rt) {
+                const double *pc = sA + (c1 + 8 * (ct_lo + u) + 2 * lk) * MEDGP_SLD + row0 + lr;
+                v[u][0] = pc[0];
+                v[u][1] = pc[MEDGP_SLD];
+                v2[u][0] = v2[u][1] = 0.0;
             }
-            pc[0] = v0;
-            pc[MEDGP_SLD] = v1;
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const double *pk = sA + (c0 + 4 * kk + lk) * MEDGP_SLD;
+            const double a = -pk[row0 + lr];
+#pragma unroll
+            for (int u = 0; u < NCT; u++)
+                if (ct_lo + u <= rt) {
+                    const double bb = pk[c1 + 8 * (ct_lo + u) + lr];
+                    if (kk & 1) dmma884(v2[u][0], v2[u][1], a, bb);
+                    else dmma884(v[u][0], v[u][1], a, bb);
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < NCT; u++)
+            if (ct_lo + u <= rt) {
+                double *pc = sA + (c1 + 8 * (ct_lo + u) + 2 * lk) * MEDGP_SLD + row0 + lr;
+                pc[0] = v[u][0] + v2[u][0];
+                pc[MEDGP_SLD] = v[u][1] + v2[u][1];
+            }
+    }
+}
+
+// one off-diagonal 16x16 block of the inverse, X_IJ = -X_II sum_{K=J}^{I-1} L_IK X_KJ (I > J): one warp
+__device__ __forceinline__ void xblock16(const double *sA, double *sX, int I, int J, int lane)
+{
+    const int lr = lane >> 2, lk = lane & 3;
+    // two accumulator sets per product (even / odd k-steps): a dependent DMMA costs about 50 cycles
+    double t[2][2][2][2];
+#pragma unroll
+    for (int u = 0; u < 16; u++) (&t[0][0][0][0])[u] = 0.0;
+    for (int K = J; K < I; K++)  // T = sum_K L_IK X_KJ
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const double *pa = sA + (16 * K + 4 * kk + lk) * MEDGP_SLD + 16 * I + lr;
+            const double *pb = sX + (16 * J + lr) * MEDGP_SLD + 16 * K + 4 * kk + lk;
+            const double a0 = pa[0], a1 = pa[8], b0 = pb[0], b1 = pb[8 * MEDGP_SLD];
+            dmma884(t[kk & 1][0][0][0], t[kk & 1][0][0][1], a0, b0);
+            dmma884(t[kk & 1][0][1][0], t[kk & 1][0][1][1], a0, b1);
+            dmma884(t[kk & 1][1][0][0], t[kk & 1][1][0][1], a1, b0);
+            dmma884(t[kk & 1][1][1][0], t[kk & 1][1][1][1], a1, b1);
+        }
+    double *px = sX + (16 * J + 2 * lk) * MEDGP_SLD + 16 * I + lr;  // block (I, J), this lane's C slots
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+            px[8 * nt * MEDGP_SLD + 8 * mt] = t[0][mt][nt][0] + t[1][mt][nt][0];
+            px[(8 * nt + 1) * MEDGP_SLD + 8 * mt] = t[0][mt][nt][1] + t[1][mt][nt][1];
+        }
+    __syncwarp();
+    double x[2][2][2][2];
+#pragma unroll
+    for (int u = 0; u < 16; u++) (&x[0][0][0][0])[u] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {  // X_IJ = -X_II T
+        const double *pa = sX + (16 * I + 4 * kk + lk) * MEDGP_SLD + 16 * I + lr;
+        const double *pb = sX + (16 * J + lr) * MEDGP_SLD + 16 * I + 4 * kk + lk;
+        const double a0 = -pa[0], a1 = -pa[8], b0 = pb[0], b1 = pb[8 * MEDGP_SLD];
+        dmma884(x[kk & 1][0][0][0], x[kk & 1][0][0][1], a0, b0);
+        dmma884(x[kk & 1][0][1][0], x[kk & 1][0][1][1], a0, b1);
+        dmma884(x[kk & 1][1][0][0], x[kk & 1][1][0][1], a1, b0);
+        dmma884(x[kk & 1][1][1][0], x[kk & 1][1][1][1], a1, b1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+            px[8 * nt * MEDGP_SLD + 8 * mt] = x[0][mt][nt][0] + x[1][mt][nt][0];
+            px[(8 * nt + 1) * MEDGP_SLD + 8 * mt] = x[0][mt][nt][1] + x[1][mt][nt][1];
         }
 }
 
 // sA: the SPD block (lower part; element (r, c) at c*SLD + r) -> L in place.  sX -> X = L^-1
-// (full tile, zeros above the diagonal).  Call with all 128 threads after a barrier that makes
-// sA visible; returns after a barrier.
-__device__ __forceinline__ void potf2_inv_blocked(double *sA, double *sX, double *s_rs, int *s_fail)
+// (full tile, zeros above the diagonal; no need to clear it first).  *logdet = sum log L_ii.
+// Call with all 128 threads after a barrier that makes sA visible; returns after a barrier.
+__device__ __forceinline__ void potf2_inv_blocked(double *sA, double *sX, double *logdet, int *s_fail)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int lr = lane >> 2, lk = lane & 3;
-    for (int i = tid; i < kTileElems; i += MEDGP_DIAG_THREADS) sX[i] = 0.0;
-    MEDGP_PHASE(2)
 #pragma unroll 1
     for (int J = 0; J < 4; J++) {
         const int c0 = 16 * J;
-        if (warp == 0) chol16_warp(sA, s_rs, c0, lane, s_fail);
+        if (warp == 0) {
+            chol16_inv_warp(sA, sX, c0, lane, s_fail);
+        } else if (J == 0) {
+            // everything of X outside the four diagonal 16x16 blocks starts as zero (the upper
+            // blocks stay zero, the lower ones are overwritten; rows 64..67 are pitch padding)
+            for (int i = tid - 32; i < kTileElems; i += MEDGP_DIAG_THREADS - 32) {
+                const int c = i / MEDGP_SLD, rr = i - c * MEDGP_SLD;
+                if (rr >= MEDGP_NB || (rr >> 4) != (c >> 4)) sX[i] = 0.0;
+            }
+        } else {
+            trail16_cols<4>(sA, c0 - 16, 2, warp - 1, 3, lane);  // what step J-1 left for later
+            if (J == 2 && warp == 3) xblock16(sA, sX, 1, 0, lane);
+            if (J == 3 && warp == 1) xblock16(sA, sX, 2, 1, lane);
+            if (J == 3 && warp == 2) xblock16(sA, sX, 2, 0, lane);
+        }
         __syncthreads();
         MEDGP_PHASE(3 + 3 * J)
         if (J < 3) {
-            if (warp < 2) {
-                if (tid >= c0 + 16) panel16_row(sA, s_rs, c0, tid);
-            } else if (warp == 2) {
-                trinv16_warp(sA, sX, s_rs, c0, lane);
-            }
+            if (tid >= c0 + 16 && tid < MEDGP_NB) panel16_row(sA, sX, c0, tid);
             __syncthreads();
             MEDGP_PHASE(4 + 3 * J)
-            trail16_update(sA, c0, warp, lane);
+            trail16_cols<2>(sA, c0, 0, warp, 4, lane);
             __syncthreads();
             MEDGP_PHASE(5 + 3 * J)
-        } else if (warp == 2) {
-            trinv16_warp(sA, sX, s_rs, c0, lane);
         }
     }
     MEDGP_PHASE(13)
-    // off-diagonal blocks of X, level d = I - J
-#pragma unroll 1
-    for (int d = 1; d < 4; d++) {
-        __syncthreads();
-        if (warp < 4 - d) {
-            const int J = warp, I = J + d;
-            double t[2][2][2];
+    if (warp < 3) {
+        xblock16(sA, sX, 3, warp, lane);
+    } else {
+        // (diagonal entries of a factor of a covariance block: far from the range where a product of two overflows)
+        double s = log(sA[lane * MEDGP_SLD + lane] * sA[(lane + 32) * MEDGP_SLD + lane + 32]);
 #pragma unroll
-            for (int u = 0; u < 8; u++) (&t[0][0][0])[u] = 0.0;
-            for (int K = J; K < I; K++)  // T = sum_K L_IK X_KJ
-#pragma unroll
-                for (int kk = 0; kk < 4; kk++) {
-                    const double *pa = sA + (16 * K + 4 * kk + lk) * MEDGP_SLD + 16 * I + lr;
-                    const double *pb = sX + (16 * J + lr) * MEDGP_SLD + 16 * K + 4 * kk + lk;
-                    const double a0 = pa[0], a1 = pa[8], b0 = pb[0], b1 = pb[8 * MEDGP_SLD];
-                    dmma884(t[0][0][0], t[0][0][1], a0, b0);
-                    dmma884(t[0][1][0], t[0][1][1], a0, b1);
-                    dmma884(t[1][0][0], t[1][0][1], a1, b0);
-                    dmma884(t[1][1][0], t[1][1][1], a1, b1);
-                }
-            double *px = sX + (16 * J + 2 * lk) * MEDGP_SLD + 16 * I + lr;  // block (I, J), this lane's C slots
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                for (int nt = 0; nt < 2; nt++) {
-                    px[8 * nt * MEDGP_SLD + 8 * mt] = t[mt][nt][0];
-                    px[(8 * nt + 1) * MEDGP_SLD + 8 * mt] = t[mt][nt][1];
-                }
-            __syncwarp();
-            double x[2][2][2];
-#pragma unroll
-            for (int u = 0; u < 8; u++) (&x[0][0][0])[u] = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) {  // X_IJ = -X_II T
-                const double *pa = sX + (16 * I + 4 * kk + lk) * MEDGP_SLD + 16 * I + lr;
-                const double *pb = sX + (16 * J + lr) * MEDGP_SLD + 16 * I + 4 * kk + lk;
-                const double a0 = -pa[0], a1 = -pa[8], b0 = pb[0], b1 = pb[8 * MEDGP_SLD];
-                dmma884(x[0][0][0], x[0][0][1], a0, b0);
-                dmma884(x[0][1][0], x[0][1][1], a0, b1);
-                dmma884(x[1][0][0], x[1][0][1], a1, b0);
-                dmma884(x[1][1][0], x[1][1][1], a1, b1);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                for (int nt = 0; nt < 2; nt++) {
-                    px[8 * nt * MEDGP_SLD + 8 * mt] = x[mt][nt][0];
-                    px[(8 * nt + 1) * MEDGP_SLD + 8 * mt] = x[mt][nt][1];
-                }
-        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) *logdet = s;
     }
     __syncthreads();
 }
@@ -408,7 +436,7 @@ __device__ __forceinline__ void potf2_inv_blocked(double *sA, double *sX, double
 // pivot is not positive.  128 threads; sD / sL are the two halves of the dynamic smem ring.
 __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, double *sD, double *sL,
                                                   GjBufs *gjb, int *s_fail, int *__restrict__ fail,
-                                                  bool have_product = true)
+                                                  bool have_product = true, bool wait_writes = false)
 {
     const int T = e.T, tid = threadIdx.x;
     const double *Kkk = tile_ptr(e.M, T, k, k);
@@ -434,41 +462,59 @@ __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, doub
         if (2 * rp + 1 < c) v.y = 0.0;
         *reinterpret_cast<double2 *>(sL + o) = v;
     }
+    for (int i = tid; i < MEDGP_NB * (MEDGP_SLD - MEDGP_NB); i += MEDGP_DIAG_THREADS)  // pitch padding: defined bytes for the bulk store
+        sL[(i >> 2) * MEDGP_SLD + MEDGP_NB + (i & 3)] = 0.0;
     __syncthreads();  // sD is dead from here on: it receives X
     MEDGP_PHASE(1)
-    potf2_inv_blocked(sL, sD, gjb->d[0], s_fail);
+    potf2_inv_blocked(sL, sD, &gjb->logdet, s_fail);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this thread's tile writes -> the bulk stores below
+    __syncthreads();
+    if (tid == 0) {
+        bulk_s2g(e.dinv + (size_t)k * kTileElems, sD, kTileElems * 8);
+        bulk_s2g(tile_ptr(e.M, T, k, k), sL, kTileElems * 8);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
     MEDGP_PHASE(14)
     // forward solve, block k: z_k = X_kk rhs_k (in place)
     tile_matvec_rhs(e, sD, e.rhs + k * MEDGP_NB, e.rhs + k * MEDGP_NB, true, false, gjb->d[0], true, v0);
     MEDGP_PHASE(15)
-    // write back: L_kk (lower), dinv (X column-major), dinvT (X^T column-major)
-    double *Lkk = tile_ptr(e.M, T, k, k);
-    double *Xk = e.dinv + (size_t)k * kTileElems;
+    // write back: L_kk and dinv (X, column-major) are whole-tile copies and leave through the TMA
+    // engine (one 34816 B bulk store each, issued before the forward solve above); dinvT (X^T)
+    // goes out from registers meanwhile, 16 bytes per store.
     double *XTk = e.dinvT + (size_t)k * kTileElems;
-    for (int idx = tid; idx < MEDGP_NB * MEDGP_NB; idx += blockDim.x) {
-        const int c = idx >> 6, rr = idx & 63;
-        if (rr >= c) Lkk[c * MEDGP_SLD + rr] = sL[c * MEDGP_SLD + rr];
-        Xk[c * MEDGP_SLD + rr] = sD[c * MEDGP_SLD + rr];   // X(rr, c)
-        XTk[c * MEDGP_SLD + rr] = sD[rr * MEDGP_SLD + c];  // X^T(rr, c) = X(c, rr)
+    {
+        // X^T by 2x2 blocks: a warp reads 4 column pairs x 8 row pairs of X (conflict-free 16-byte
+        // loads) and writes 8 column pairs x 64 contiguous bytes of X^T
+        const int lane = tid & 31, warp = tid >> 5, al = lane >> 3, bl = lane & 7;
+        for (int it = warp; it < 32; it += MEDGP_DIAG_THREADS / 32) {
+            const int a = 4 * (it >> 2) + al, b = 8 * (it & 3) + bl;  // X rows 2b, 2b+1; columns 2a, 2a+1
+            const double2 q0 = *reinterpret_cast<const double2 *>(sD + (2 * a) * MEDGP_SLD + 2 * b);
+            const double2 q1 = *reinterpret_cast<const double2 *>(sD + (2 * a + 1) * MEDGP_SLD + 2 * b);
+            *reinterpret_cast<double2 *>(XTk + (2 * b) * MEDGP_SLD + 2 * a) = make_double2(q0.x, q1.x);
+            *reinterpret_cast<double2 *>(XTk + (2 * b + 1) * MEDGP_SLD + 2 * a) = make_double2(q0.y, q1.y);
+        }
     }
-    if (tid < 32) {
-        double s = log(sL[tid * MEDGP_SLD + tid]) + log(sL[(tid + 32) * MEDGP_SLD + tid + 32]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (tid == 0) {
-            e.blk[k] = s;
-            if (*s_fail) fail[e.out_index] = 1;
+    if (tid == 0) {
+        e.blk[k] = gjb->logdet;
+        if (*s_fail) fail[e.out_index] = 1;
+        // The shared tiles must outlive the bulk stores' reads.  wait_writes: a consumer inside the
+        // SAME kernel is about to be released (k_potrf_step), so the stores must have landed and be
+        // ordered before the generic-proxy flag; at a kernel boundary the reads are enough.
+        if (wait_writes) {
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");
+        } else {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
     }
     MEDGP_PHASE(16)
 }
 
-// Stand-alone diagonal kernel, one CTA per evaluation: D = K_kk - sum_{l<depth} L_kl L_kl^T.
-// Used for block 0, for the right-looking path (depth 0: the tile is already updated), and as
-// the general fallback; in the left-looking path blocks k >= 1 are factored inside the panel
-// kernel of step k-1 (see k_potrf_panel).
+// Stand-alone diagonal kernel, one CTA per evaluation: D = K_kk - sum_{l0 <= l < l0+depth} L_kl L_kl^T.
+// Left-looking: l0 = 0, depth = k.  Panel-blocked right-looking: l0 = first block column of the
+// current panel (everything left of it has already been applied by the trailing updates).
 __global__ void __launch_bounds__(MEDGP_DIAG_THREADS, 3)
-k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int depth, int *__restrict__ fail)
+k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int depth, int *__restrict__ fail, int l0 = 0)
 {
     extern __shared__ __align__(128) double smem[];
     __shared__ GemmBars bars;
@@ -487,7 +533,7 @@ k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int depth, int *__restri
         acc_zero(acc);
         gemm_nt_tiles(acc, depth,
                       [&](int l, const double *&A, const double *&B) {
-                          A = tile_ptr(M, T, k, l);
+                          A = tile_ptr(M, T, k, l0 + l);
                           B = A;
                       },
                       smem, &bars, NoStageFn(),
@@ -504,7 +550,7 @@ k_potrf_diag(const EvalDesc *__restrict__ descs, int k, int depth, int *__restri
 // ------------------------------------------------------------------ potrf: panel below block k
 // grid (row tiles i > k, evaluations): L_ik = (K_ik - sum_{l<k} L_il L_kl^T) X_kk^T
 __global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
-k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_diag, int *__restrict__ fail)
+k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_diag, int *__restrict__ fail, int l0 = 0)
 {
     extern __shared__ __align__(128) double smem[];
     __shared__ GemmBars bars;
@@ -524,8 +570,8 @@ k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_dia
     acc_zero(acc);
     gemm_nt_tiles(acc, depth,
                   [&](int l, const double *&A, const double *&B) {
-                      A = tile_ptr(M, T, i, l);
-                      B = tile_ptr(M, T, k, l);
+                      A = tile_ptr(M, T, i, l0 + l);
+                      B = tile_ptr(M, T, k, l0 + l);
                   },
                   smem, &bars, NoStageFn(), NoSkipFn(), TileEdge{mv, MEDGP_NB, MEDGP_NB});
     __syncthreads();  // every warp is done with the pipeline buffers
@@ -597,7 +643,7 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, 
         if (k >= T) return;
         if (threadIdx.x == 0) s_fail = 0;
         __syncthreads();
-        diag_block_factor(e, k, sP, sX, &gjb, &s_fail, fail, false);
+        diag_block_factor(e, k, sP, sX, &gjb, &s_fail, fail, false, true);
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) flag_release(e.flags + k);
@@ -716,38 +762,47 @@ k_trtri_row(const EvalDesc *__restrict__ descs, int i, int right_looking)
 
 // ------------------------------------------------------------------ right-looking variants
 // For few, large matrices the left-looking panel has too few CTAs per launch ((T-k-1) per
-// matrix, each k tiles deep).  The right-looking form exposes (T-k)^2/2 independent one-tile
-// products per step instead, at the price of re-reading the trailing tiles T times:
-//   potrf:  K_ij -= L_ik L_jk^T            for k < j <= i      (k_syrk_update, after step k)
+// matrix, each k tiles deep).  The right-looking form exposes (T-k)^2/2 independent products
+// per step instead, at the price of re-reading the trailing tiles once per update.  With one
+// update per block column those products are one tile deep and the update is bound by HBM / L2
+// traffic (4 tiles moved per tile product) as soon as the matrices in flight outgrow the L2, so
+// the factorisation is PANEL-BLOCKED: W block columns are factored left-looking among
+// themselves (k_potrf_diag / k_potrf_panel with l0 = first column of the panel), then applied
+// to the trailing matrix in one W-tile-deep update:
+//   potrf:  K_ij -= sum_{l in panel} L_il L_jl^T   for panel end <= j <= i   (k_syrk_update)
 //   trtri:  Acc_ji (+)= U_jk L_ik^T        for j <= k < i      (k_trtri_update), then
 //           U_j,k+1 = -Acc_j,k+1 X_k+1^T                       (k_trtri_row, right_looking = 1)
 __global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
-k_syrk_update(const EvalDesc *__restrict__ descs, int k, int part)
+k_syrk_update(const EvalDesc *__restrict__ descs, int k0, int nk, int j0, int ncol)
 {
-    // part 0: every lower tile of the trailing matrix; 1: its first block column only (the tiles
-    // the next step's diagonal and panel kernels need: the critical path of the look-ahead
-    // schedule); 2: everything but the first block column (runs beside the next step)
+    // Trailing update with the nk block columns k0 .. k0+nk-1 of L (a finished panel):
+    //   K_ij -= sum_{l} L_il L_jl^T   for the lower tiles (i, j) of block columns j0 .. j0+ncol-1.
+    // ncol == 0: every block column from j0 on (lower-triangle enumeration); otherwise blockIdx.x
+    // = (row offset) * ncol + (column offset), row offset counted from the tile's own diagonal.
+    // Look-ahead schedule: the block columns of the NEXT panel are updated on the evaluation's
+    // main stream (the critical path), everything right of them on an auxiliary stream beside
+    // the next panel's factorisation.
     extern __shared__ __align__(128) double smem[];
     __shared__ GemmBars bars;
     const EvalDesc &e = descs[blockIdx.y];
     int a, b;
-    if (part == 1) {
-        a = blockIdx.x; b = 0;
-    } else {
+    if (ncol == 0) {
         tri_index(blockIdx.x, a, b);
-        if (part == 2) { a += 1; b += 1; }
+    } else {
+        b = blockIdx.x % ncol;
+        a = b + blockIdx.x / ncol;
     }
-    const int i = k + 1 + a, j = k + 1 + b, T = e.T;
+    const int i = j0 + a, j = j0 + b, T = e.T;
     if (i >= T || e.skip) return;
     gemm_bars_init(&bars);
     double acc[4][4][2];
     acc_zero(acc);
     double *M = e.M;
     const bool diag = (i == j);
-    gemm_nt_tiles(acc, 1,
-                  [&](int, const double *&A, const double *&B) {
-                      A = tile_ptr(M, T, i, k);
-                      B = tile_ptr(M, T, j, k);
+    gemm_nt_tiles(acc, nk,
+                  [&](int l, const double *&A, const double *&B) {
+                      A = tile_ptr(M, T, i, k0 + l);
+                      B = tile_ptr(M, T, j, k0 + l);
                   },
                   smem, &bars, NoStageFn(),
                   // diagonal tiles: only the lower part of the symmetric update is used

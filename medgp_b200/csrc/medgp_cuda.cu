@@ -182,6 +182,7 @@ struct medgp_ctx {
     cudaStream_t aux_streams[8] = {};
     cudaEvent_t ev_panel[8] = {}, ev_bulk[8] = {};
     bool lookahead = true;  // MEDGP_LOOKAHEAD=0 disables it
+    int rl_width = 2;       // block columns per panel of the right-looking factorisation (MEDGP_RL_W); measured at n = 4000: 2 is best for one matrix in flight and ties with 4 for five
     cudaEvent_t ev_t0 = nullptr;      // MEDGP_TIMELINE: origin of the dumped stage intervals
     const char *timeline = nullptr;   // MEDGP_TIMELINE=<file>: with profiling on, keep the sub-streams and dump every stage interval
     // profiling
@@ -488,7 +489,58 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     cudaStream_t st2 = ctx->aux_streams[stagger_slot];
     cudaEvent_t ev_panel = ctx->ev_panel[stagger_slot], ev_bulk = ctx->ev_bulk[stagger_slot];
     bool bulk_pending = false;
-    for (int k = 0; k < Tmax; k++) {
+    // Panel-blocked right-looking schedule (few large matrices): W block columns are factored
+    // left-looking among themselves, then the trailing matrix gets ONE W-tile-deep update.
+    // Look-ahead: the block columns of the next panel are updated on this stream (the critical
+    // path: next diagonal blocks and panels need them), everything right of them on the auxiliary
+    // stream beside the next panel's factorisation.  Orderings that matter: the bulk update of a
+    // panel follows its last panel kernel; the next-panel part of panel p follows the bulk of
+    // panel p-1 (both touch the same block columns); bulks are ordered by their stream.
+    if (rl) {
+        const int W = std::max(1, ctx->rl_width);
+        for (int k0 = 0; k0 < Tmax; k0 += W) {
+            const int k1 = std::min(k0 + W, Tmax);
+            for (int k = k0; k < k1; k++) {
+                const unsigned a0 = sc.act(k), a1 = k + 1 < Tmax ? sc.act(k + 1) : 0;
+                const int rem = Tmax - k - 1, depth = k - k0;
+                begin(MEDGP_STAGE_DIAG);
+                out.push_back([=]() { k_potrf_diag<<<a0, MEDGP_DIAG_THREADS, gemm_smem, st>>>(dd, k, depth, d_fail, k0); L[MEDGP_STAGE_DIAG]++; });
+                end(MEDGP_STAGE_DIAG);
+                if (rem > 0 && a1 > 0) {
+                    begin(MEDGP_STAGE_POTRF);
+                    out.push_back([=]() { k_potrf_panel<<<dim3(rem, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, depth, 0, d_fail, k0); L[MEDGP_STAGE_POTRF]++; });
+                    end(MEDGP_STAGE_POTRF);
+                }
+            }
+            const unsigned at = k1 < Tmax ? sc.act(k1) : 0;
+            if (at == 0) continue;
+            const int nk = k1 - k0, ncolA = std::min(W, Tmax - k1), jB = k1 + ncolA, remB = Tmax - jB;
+            begin(MEDGP_STAGE_POTRF);
+            if (!look) {
+                const int rem = Tmax - k1;
+                out.push_back([=]() { k_syrk_update<<<dim3(rem * (rem + 1) / 2, at), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k0, nk, k1, 0); L[MEDGP_STAGE_POTRF]++; });
+            } else {
+                if (remB > 0) {
+                    out.push_back([=]() {
+                        cudaEventRecord(ev_panel, st);
+                        cudaStreamWaitEvent(st2, ev_panel, 0);
+                        k_syrk_update<<<dim3(remB * (remB + 1) / 2, at), MEDGP_GEMM_THREADS, gemm_smem, st2>>>(dd, k0, nk, jB, 0);
+                        L[MEDGP_STAGE_POTRF]++;
+                    });
+                }
+                if (bulk_pending) out.push_back([=]() { cudaStreamWaitEvent(st, ev_bulk, 0); });
+                out.push_back([=]() { k_syrk_update<<<dim3(ncolA * (Tmax - k1), at), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k0, nk, k1, ncolA); L[MEDGP_STAGE_POTRF]++; });
+                if (remB > 0) {
+                    out.push_back([=]() { cudaEventRecord(ev_bulk, st2); });
+                    bulk_pending = true;
+                } else {
+                    bulk_pending = false;  // the wait above joined the last bulk update
+                }
+            }
+            end(MEDGP_STAGE_POTRF);
+        }
+    }
+    for (int k = 0; k < Tmax && !rl; k++) {
         const unsigned a0 = sc.act(k), a1 = k + 1 < Tmax ? sc.act(k + 1) : 0;
         const int rem = Tmax - k - 1;
         if (step_kernel) {
@@ -500,42 +552,17 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
         // chain_diag: the panel CTA of row k+1 folds its tile into K_{k+1,k+1} and factors that
         // block on the spot, so only block 0 needs a diagonal launch and the 64-pivot chain of
         // block k+1 hides behind the other panel CTAs of step k
-        const bool chain_diag = !rl && ctx->chain_diag;
-        const int depth = (rl || fold || chain_diag) ? 0 : k;
-        const int pdepth = rl ? 0 : k, pfold = chain_diag ? 2 : ((!rl && fold) ? 1 : 0);
+        const bool chain_diag = ctx->chain_diag;
+        const int depth = (fold || chain_diag) ? 0 : k;
+        const int pdepth = k, pfold = chain_diag ? 2 : (fold ? 1 : 0);
         if (!chain_diag || k == 0) {
             begin(MEDGP_STAGE_DIAG);
-            out.push_back([=]() { k_potrf_diag<<<a0, MEDGP_DIAG_THREADS, gemm_smem, st>>>(dd, k, depth, d_fail); L[MEDGP_STAGE_DIAG]++; });
+            out.push_back([=]() { k_potrf_diag<<<a0, MEDGP_DIAG_THREADS, gemm_smem, st>>>(dd, k, depth, d_fail, 0); L[MEDGP_STAGE_DIAG]++; });
             end(MEDGP_STAGE_DIAG);
         }
         if (rem > 0) {
             begin(MEDGP_STAGE_POTRF);
-            out.push_back([=]() { k_potrf_panel<<<dim3(rem, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, pdepth, pfold, d_fail); L[MEDGP_STAGE_POTRF]++; });
-            if (rl && !look)
-                out.push_back([=]() { k_syrk_update<<<dim3(rem * (rem + 1) / 2, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, 0); L[MEDGP_STAGE_POTRF]++; });
-            if (rl && look) {
-                // look-ahead: the first block column of the trailing update stays on this stream
-                // (the next diagonal block and panel need it); the rest goes to the auxiliary
-                // stream and overlaps the next step.  Orderings that matter: the bulk of step k
-                // follows the panel of step k; the column part of step k follows the bulk of step
-                // k-1 (both update the tiles of column k+1).
-                if (rem > 1) {
-                    out.push_back([=]() {
-                        cudaEventRecord(ev_panel, st);
-                        cudaStreamWaitEvent(st2, ev_panel, 0);
-                        k_syrk_update<<<dim3((rem - 1) * rem / 2, a1), MEDGP_GEMM_THREADS, gemm_smem, st2>>>(dd, k, 2);
-                        L[MEDGP_STAGE_POTRF]++;
-                    });
-                }
-                if (bulk_pending) out.push_back([=]() { cudaStreamWaitEvent(st, ev_bulk, 0); });
-                out.push_back([=]() { k_syrk_update<<<dim3(rem, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, 1); L[MEDGP_STAGE_POTRF]++; });
-                if (rem > 1) {
-                    out.push_back([=]() { cudaEventRecord(ev_bulk, st2); });
-                    bulk_pending = true;
-                } else {
-                    bulk_pending = false;  // the wait above joined the last bulk update
-                }
-            }
+            out.push_back([=]() { k_potrf_panel<<<dim3(rem, a1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, pdepth, pfold, d_fail, 0); L[MEDGP_STAGE_POTRF]++; });
             end(MEDGP_STAGE_POTRF);
         }
     }
@@ -737,7 +764,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         } else {
             uint64_t key = 1469598103934665603ULL;
             auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ULL; };
-            mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)ctx->stagger_us); mix(ctx->chain_diag); mix(ctx->lookahead); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
+            mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)ctx->stagger_us); mix(ctx->chain_diag); mix(ctx->lookahead); mix((uint64_t)ctx->rl_width); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
             mix((uint64_t)(uintptr_t)d_theta); mix((uint64_t)(uintptr_t)d_nlml); mix((uint64_t)(uintptr_t)d_grad);
             mix((uint64_t)(uintptr_t)d_status); mix((uint64_t)(uintptr_t)d_mean); mix((uint64_t)(uintptr_t)d_var);
             mix((uint64_t)(uintptr_t)ctx->d_fail); mix((uint64_t)(uintptr_t)ctx->ext_skip);
@@ -884,6 +911,7 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     if (const char *ev = getenv("MEDGP_GRAPHS")) ctx->use_graphs = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_DEVICE_RETRY")) ctx->device_retry = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_LOOKAHEAD")) ctx->lookahead = atoi(ev) != 0;
+    if (const char *ev = getenv("MEDGP_RL_W")) ctx->rl_width = std::max(1, atoi(ev));
     if (const char *ev = getenv("MEDGP_FORCE_FAIL")) ctx->force_fail = std::max(0, atoi(ev));  // tests of the jitter path through the executables
     if (const char *ev = getenv("MEDGP_STREAMS")) ctx->max_streams = std::max(1, std::min(8, atoi(ev)));
     for (int i = 0; i < 8; i++) {

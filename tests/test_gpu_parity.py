@@ -412,6 +412,10 @@ def test_long_stay_patient(api):
 @pytest.mark.parametrize("env,batch", [
     ({"MEDGP_RL": "1"}, 6),                                 # right-looking potrf / trtri, look-ahead on a second stream
     ({"MEDGP_RL": "1", "MEDGP_LOOKAHEAD": "0"}, 6),         # right-looking, one stream
+    ({"MEDGP_RL": "1", "MEDGP_RL_W": "1"}, 6),              # panels of 1, 2, 3 block columns (T = 6: ragged last panel)
+    ({"MEDGP_RL": "1", "MEDGP_RL_W": "2"}, 6),
+    ({"MEDGP_RL": "1", "MEDGP_RL_W": "3", "MEDGP_LOOKAHEAD": "0"}, 6),
+    ({"MEDGP_RL": "1", "MEDGP_RL_W": "8"}, 6),              # one panel: left-looking inside, no trailing update
     ({"MEDGP_RL": "0"}, 6),                                 # left-looking, one launch per step (k_potrf_step)
     ({"MEDGP_RL": "0", "MEDGP_FUSE_DIAG": "0"}, 6),         # left-looking, separate kernels, folded diagonal update
     ({"MEDGP_RL": "0"}, 140),                               # left-looking, separate kernels, large batch

@@ -50,10 +50,12 @@ int main()
         cudaDeviceSynchronize();
         cudaMemcpyFromSymbol(clk, g_clk, sizeof(clk));
     }
-    const char *names[] = {"entry", "tile loaded into smem", "X zeroed", "J0 chol16", "J0 rows below + inverse16", "J0 trailing update",
-                           "J1 chol16", "J1 rows+inv", "J1 trailing", "J2 chol16", "J2 rows+inv", "J2 trailing", "J3 chol16", "J3 inverse16",
-                           "X off-diagonal levels", "forward-solve block", "write-back + logdet"};
-    for (int i = 1; i <= 16; i++) printf("%-28s %7lld cycles\n", names[i], clk[i] - clk[i - 1]);
+    const int ids[] = {0, 1, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+    const char *names[] = {"entry", "tile loaded into smem", "J0 chol16+inverse16 (others: zero X)", "J0 rows below (DMMA)", "J0 next column block",
+                           "J1 chol16+inv (others: deferred trailing)", "J1 rows below", "J1 next column block",
+                           "J2 chol16+inv (others: deferred, X_10)", "J2 rows below", "J2 next column block",
+                           "J3 chol16+inv (others: X_20, X_21)", "-", "X_3J level + logdet", "forward-solve block", "write-back"};
+    for (int i = 1; i < 16; i++) printf("%-44s %7lld cycles\n", names[i], clk[ids[i]] - clk[ids[i - 1]]);
     printf("total %lld cycles = %.2f us at 1.965 GHz; status %s\n", clk[16] - clk[0], (clk[16] - clk[0]) / 1965.0, cudaGetErrorString(cudaGetLastError()));
     int f; cudaMemcpy(&f, dfail, 4, cudaMemcpyDeviceToHost);
     printf("fail flag %d\n", f);
