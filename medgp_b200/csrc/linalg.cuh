@@ -622,8 +622,13 @@ k_potrf_panel(const EvalDesc *__restrict__ descs, int k, int depth, int fold_dia
 // factorisation hides behind the tensor-core work of the panel roles.
 // *ticket must be 0 at launch (k_prep zeroes the sub-chunk's counters).
 __global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
-k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, int *__restrict__ ticket)
+k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, int *__restrict__ ticket,
+             int l0 = 0, int fold = 1)
 {
+    // fold = 1 (left-looking, l0 = 0): every panel role folds its tile into its own diagonal block,
+    // so the diagonal role has no product to do.  fold = 0 (panel-blocked right-looking, l0 = first
+    // block column of the current panel): the diagonal role forms the k - l0 products of its block
+    // itself (at most W - 1), the trailing update takes care of everything right of the panel.
     extern __shared__ __align__(128) double smem[];
     __shared__ GemmBars bars;
     __shared__ __align__(16) GjBufs gjb;
@@ -642,8 +647,25 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, 
     if (row == 0) {
         if (k >= T) return;
         if (threadIdx.x == 0) s_fail = 0;
+        const bool products = !fold && k > l0;
+        if (products) {
+            prefetch_tile_l2(tile_ptr(M, T, k, k));
+            gemm_bars_init(&bars);
+            double acc[4][4][2];
+            acc_zero(acc);
+            gemm_nt_tiles(acc, k - l0,
+                          [&](int l, const double *&A, const double *&B) {
+                              A = tile_ptr(M, T, k, l0 + l);
+                              B = A;
+                          },
+                          smem, &bars, NoStageFn(),
+                          [](int, int wm, int wn) { return wm == 0 && wn == 1; },  // lower part only
+                          TileEdge{rows_valid(e, k), rows_valid(e, k), MEDGP_NB});
+            __syncthreads();  // all warps are done with the ring before it is reused as sP
+            acc_to_smem(acc, sP, 1.0);
+        }
         __syncthreads();
-        diag_block_factor(e, k, sP, sX, &gjb, &s_fail, fail, false, true);
+        diag_block_factor(e, k, sP, sX, &gjb, &s_fail, fail, products, true);
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) flag_release(e.flags + k);
@@ -658,10 +680,10 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, 
     const int mv = rows_valid(e, i);
     double acc[4][4][2];
     acc_zero(acc);
-    gemm_nt_tiles(acc, k,
+    gemm_nt_tiles(acc, k - l0,
                   [&](int l, const double *&A, const double *&B) {
-                      A = tile_ptr(M, T, i, l);
-                      B = tile_ptr(M, T, k, l);
+                      A = tile_ptr(M, T, i, l0 + l);
+                      B = tile_ptr(M, T, k, l0 + l);
                   },
                   smem, &bars, NoStageFn(), NoSkipFn(), TileEdge{mv, MEDGP_NB, MEDGP_NB});
     acc_rsub_global(acc, Tik);  // P = K_ik - C (does not depend on the diagonal block)
@@ -676,6 +698,7 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, 
     gemm2_smem(acc, sP, sX, mv);
     acc_to_global(acc, Tik);
     acc_matvec_rhs(acc, e, e.rhs + k * MEDGP_NB, e.rhs + i * MEDGP_NB, red);
+    if (!fold) return;
     // fold into the own diagonal block: K_ii -= L_ik L_ik^T
     acc_to_smem(acc, sP, 1.0);
     __syncthreads();

@@ -182,7 +182,9 @@ struct medgp_ctx {
     cudaStream_t aux_streams[8] = {};
     cudaEvent_t ev_panel[8] = {}, ev_bulk[8] = {};
     bool lookahead = true;  // MEDGP_LOOKAHEAD=0 disables it
-    int rl_width = 2;       // block columns per panel of the right-looking factorisation (MEDGP_RL_W); measured at n = 4000: 2 is best for one matrix in flight and ties with 4 for five
+    int rl_width = 0;       // block columns per panel of the right-looking factorisation (MEDGP_RL_W); 0 = by the number
+                            // of matrices in the chunk: 2 for one or two (shortest critical path), 4 beyond (measured at n = 4000)
+    int rl_width_now = 2;   // the width of the chunk being issued
     cudaEvent_t ev_t0 = nullptr;      // MEDGP_TIMELINE: origin of the dumped stage intervals
     const char *timeline = nullptr;   // MEDGP_TIMELINE=<file>: with profiling on, keep the sub-streams and dump every stage interval
     // profiling
@@ -497,12 +499,19 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     // panel follows its last panel kernel; the next-panel part of panel p follows the bulk of
     // panel p-1 (both touch the same block columns); bulks are ordered by their stream.
     if (rl) {
-        const int W = std::max(1, ctx->rl_width);
+        const int W = std::max(1, ctx->rl_width_now);
+        const bool rl_step = ctx->fuse_diag && Tmax <= kTicketsPerSub;
         for (int k0 = 0; k0 < Tmax; k0 += W) {
             const int k1 = std::min(k0 + W, Tmax);
             for (int k = k0; k < k1; k++) {
                 const unsigned a0 = sc.act(k), a1 = k + 1 < Tmax ? sc.act(k + 1) : 0;
                 const int rem = Tmax - k - 1, depth = k - k0;
+                if (rl_step) {  // one launch per block column: the panel roles wait for the diagonal role's flag
+                    begin(MEDGP_STAGE_POTRF);
+                    out.push_back([=]() { k_potrf_step<<<dim3(a0, rem + 1), MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, k, d_fail, tickets + k, k0, 0); L[MEDGP_STAGE_POTRF]++; });
+                    end(MEDGP_STAGE_POTRF);
+                    continue;
+                }
                 begin(MEDGP_STAGE_DIAG);
                 out.push_back([=]() { k_potrf_diag<<<a0, MEDGP_DIAG_THREADS, gemm_smem, st>>>(dd, k, depth, d_fail, k0); L[MEDGP_STAGE_DIAG]++; });
                 end(MEDGP_STAGE_DIAG);
@@ -664,6 +673,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         // ones -> left-looking (less traffic).  Decided on the whole chunk, not per stream.
         bool rl = Tbig >= 8 && cnt * (size_t)Tbig < 600;
         if (ctx->force_rl >= 0) rl = ctx->force_rl != 0;
+        ctx->rl_width_now = ctx->rl_width > 0 ? ctx->rl_width : (cnt <= 2 ? 2 : 4);
         // left-looking with few matrices: the diagonal kernel (one CTA per matrix) must not carry
         // a k-tile product; the panel CTAs fold their tile into the diagonal block instead
         const bool fold = !rl && cnt < ctx->fold_max;
@@ -764,7 +774,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         } else {
             uint64_t key = 1469598103934665603ULL;
             auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ULL; };
-            mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)ctx->stagger_us); mix(ctx->chain_diag); mix(ctx->lookahead); mix((uint64_t)ctx->rl_width); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
+            mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)ctx->stagger_us); mix(ctx->chain_diag); mix(ctx->lookahead); mix((uint64_t)ctx->rl_width_now); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
             mix((uint64_t)(uintptr_t)d_theta); mix((uint64_t)(uintptr_t)d_nlml); mix((uint64_t)(uintptr_t)d_grad);
             mix((uint64_t)(uintptr_t)d_status); mix((uint64_t)(uintptr_t)d_mean); mix((uint64_t)(uintptr_t)d_var);
             mix((uint64_t)(uintptr_t)ctx->d_fail); mix((uint64_t)(uintptr_t)ctx->ext_skip);
@@ -911,7 +921,7 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     if (const char *ev = getenv("MEDGP_GRAPHS")) ctx->use_graphs = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_DEVICE_RETRY")) ctx->device_retry = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_LOOKAHEAD")) ctx->lookahead = atoi(ev) != 0;
-    if (const char *ev = getenv("MEDGP_RL_W")) ctx->rl_width = std::max(1, atoi(ev));
+    if (const char *ev = getenv("MEDGP_RL_W")) ctx->rl_width = std::max(0, atoi(ev));
     if (const char *ev = getenv("MEDGP_FORCE_FAIL")) ctx->force_fail = std::max(0, atoi(ev));  // tests of the jitter path through the executables
     if (const char *ev = getenv("MEDGP_STREAMS")) ctx->max_streams = std::max(1, std::min(8, atoi(ev)));
     for (int i = 0; i < 8; i++) {

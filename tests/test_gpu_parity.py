@@ -416,6 +416,8 @@ def test_long_stay_patient(api):
     ({"MEDGP_RL": "1", "MEDGP_RL_W": "2"}, 6),
     ({"MEDGP_RL": "1", "MEDGP_RL_W": "3", "MEDGP_LOOKAHEAD": "0"}, 6),
     ({"MEDGP_RL": "1", "MEDGP_RL_W": "8"}, 6),              # one panel: left-looking inside, no trailing update
+    ({"MEDGP_RL": "1", "MEDGP_FUSE_DIAG": "0"}, 6),         # right-looking with separate diagonal / panel kernels
+    ({"MEDGP_RL": "1", "MEDGP_STREAMS": "1"}, 40),          # right-looking step kernel, 40 matrices on one stream
     ({"MEDGP_RL": "0"}, 6),                                 # left-looking, one launch per step (k_potrf_step)
     ({"MEDGP_RL": "0", "MEDGP_FUSE_DIAG": "0"}, 6),         # left-looking, separate kernels, folded diagonal update
     ({"MEDGP_RL": "0"}, 140),                               # left-looking, separate kernels, large batch
