@@ -75,6 +75,36 @@ k_prep(const EvalDesc *__restrict__ descs, ModelDims md, const double *__restric
 #ifndef MEDGP_AOCC
 #define MEDGP_AOCC 4
 #endif
+// The 16 columns of one thread in a tile with no special cases: an off-diagonal tile that does not
+// touch the ragged end of the matrix (every pair is a real pair below the diagonal) -- all but
+// O(T) of the T^2/2 tiles.  No per-element predicates, running pointers instead of index
+// arithmetic, the B_q entries of a feature pair side by side (one address per column).
+template <int QT, bool FAST>
+__device__ __forceinline__ void assemble_interior(double *__restrict__ po, const double tr, const double2 (&arow)[QT],
+                                                  const double (&cq)[QT], const double *__restrict__ brow /* + mc*QT + q */,
+                                                  const double *__restrict__ ptc, const int *__restrict__ pmc,
+                                                  const double2 *__restrict__ pcs /* [q*64 + column] */,
+                                                  const double *__restrict__ s_tab)
+{
+#pragma unroll 2
+    for (int u = 0; u < 16; u++) {
+        const double tau = tr - ptc[u], tau2 = tau * tau;
+        const double *bq = brow + pmc[u] * QT;
+        double xarg[QT], ex[QT];
+#pragma unroll
+        for (int q = 0; q < QT; q++) xarg[q] = -cq[q] * tau2;
+        exp_nonpos<QT, !FAST>(xarg, ex, s_tab);
+        double val = 0.0;
+#pragma unroll
+        for (int q = 0; q < QT; q++) {
+            const double2 b = pcs[q * MEDGP_NB + u];
+            const double cosphi = arow[q].x * b.x + arow[q].y * b.y;
+            val = fma(bq[q] * cosphi, ex[q], val);
+        }
+        po[u * MEDGP_SLD] = val;
+    }
+}
+
 template <int QT>
 __global__ void __launch_bounds__(256, QT <= 5 ? MEDGP_AOCC : 2)
 k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
@@ -93,12 +123,13 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
     double *sB = sm, *sC = sm + Q * D * D;
     // Only the block of every B_q that the tile's features select is staged: with points in
     // feature order a 64 x 64 tile touches a few of the D features, so this is a few hundred
-    // bytes instead of all Q D^2 doubles per CTA.  sB[(q nr + (f_i - r0)) nc + (f_j - c0)].  The
-    // feature range of every 64-point block comes with the series (no dependent round of loads).
+    // bytes instead of all Q D^2 doubles per CTA.  sB[((f_i - r0) nc + (f_j - c0)) Q + q]: the Q
+    // entries of a feature pair are adjacent.  The feature range of every 64-point block comes
+    // with the series (no dependent round of loads).
     const int2 fr_r = e.frange[ti], fr_c = e.frange[tj];
     const int r0 = fr_r.x, c0 = fr_c.x, nr = fr_r.y - fr_r.x + 1, nc = fr_c.y - fr_c.x + 1;
     for (int i = tid; i < Q * nr * nc; i += blockDim.x) {
-        const int q = i / (nr * nc), rem = i - q * nr * nc, fr = rem / nc, fc = rem - fr * nc;
+        const int q = i % Q, rem = i / Q, fr = rem / nc, fc = rem - fr * nc;
         sB[i] = e.par[md.oB + (q * D + r0 + fr) * D + c0 + fc];
     }
     if (tid < Q) sC[tid] = e.par[md.oC + tid];
@@ -122,19 +153,28 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
     const int gi = ti * MEDGP_NB + r;
     const double tr = s_tr[r];
     const int mr = s_mr[r];
-    const double jit = 1.0 + (double)e.jitter;
     double *out = e.M + tile_off(e.T, ti, tj) + r;
     // row-side data stays in registers for the 16 columns this thread produces
     double2 arow[QT];
-#pragma unroll
-    for (int q = 0; q < QT; q++) arow[q] = s_csr[q][r];
-    const double *brow = sB + (mr - r0) * nc - c0;  // + q*nr*nc + mc
+    double cq[QT];
     double cmax = 0.0;
 #pragma unroll
-    for (int q = 0; q < QT; q++) cmax = fmax(cmax, sC[q]);
+    for (int q = 0; q < QT; q++) {
+        arow[q] = s_csr[q][r];
+        cq[q] = sC[q];
+        cmax = fmax(cmax, cq[q]);
+    }
+    const double *brow = sB + ((mr - r0) * nc - c0) * QT;  // + mc * QT + q
     const bool fastexp = cmax * e.trange2 < MEDGP_EXP_UNCHECKED_MAX;  // uniform per evaluation
-    const int DD = nr * nc;
-#pragma unroll 2
+    if (ti != tj && ti < e.T - 1) {  // uniform per CTA: the tile has no diagonal and no padding
+        if (fastexp)
+            assemble_interior<QT, true>(out + g * 16 * MEDGP_SLD, tr, arow, cq, brow, s_tc + g * 16, s_mc + g * 16, &s_csc[0][g * 16], s_tab);
+        else
+            assemble_interior<QT, false>(out + g * 16 * MEDGP_SLD, tr, arow, cq, brow, s_tc + g * 16, s_mc + g * 16, &s_csc[0][g * 16], s_tab);
+        return;
+    }
+    const double jit = 1.0 + (double)e.jitter;
+#pragma unroll 1
     for (int u = 0; u < 16; u++) {
         const int c = g * 16 + u, gj = tj * MEDGP_NB + c;
         if (gj > gi) {  // strictly upper part of a diagonal tile: never used as data, kept defined
@@ -146,10 +186,10 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
             val = (gi == gj) ? 1.0 : 0.0;
         } else {
             const double tau = tr - s_tc[c], tau2 = tau * tau;
-            const double *bq = brow + s_mc[c];
+            const double *bq = brow + s_mc[c] * QT;
             double xarg[QT], ex[QT];
 #pragma unroll
-            for (int q = 0; q < QT; q++) xarg[q] = -sC[q] * tau2;
+            for (int q = 0; q < QT; q++) xarg[q] = -cq[q] * tau2;
             if (fastexp) exp_nonpos<QT, false>(xarg, ex, s_tab);
             else exp_nonpos<QT, true>(xarg, ex, s_tab);
             val = 0.0;
@@ -157,7 +197,7 @@ k_assemble(const EvalDesc *__restrict__ descs, ModelDims md)
             for (int q = 0; q < QT; q++) {
                 const double2 b = s_csc[q][c];
                 const double cosphi = arow[q].x * b.x + arow[q].y * b.y;
-                val += bq[q * DD] * cosphi * ex[q];
+                val = fma(bq[q] * cosphi, ex[q], val);
             }
             if (gi == gj) val += jit * e.par[md.oSig2 + mr];
         }

@@ -686,10 +686,34 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
             return r;
         };
         size_t dcur = dpos;
+        // Which evaluations go to which sub-chunk.  Large chunks: CONTIGUOUS ranges of the
+        // size-sorted chunk with equal shares of the n^3 work, so that the matrices of a sub-chunk
+        // have (nearly) the same number of block rows: its launch grids -- sized for its largest
+        // matrix -- then hold few CTAs that find nothing to do, and the CTAs of a launch are equally
+        // deep.  Small chunks: round-robin (one or two matrices per stream).  MEDGP_DEAL=0: always round-robin.
+        std::vector<std::vector<size_t> > members(S);
+        static const bool deal_ranges = !(getenv("MEDGP_DEAL") && atoi(getenv("MEDGP_DEAL")) == 0);
+        if (deal_ranges && S > 1 && cnt >= (size_t)(4 * S)) {
+            std::vector<double> cum(cnt + 1, 0.0);
+            for (size_t c = 0; c < cnt; c++) {
+                const double t = ctx->series[reqs[first + c].series].T;
+                cum[c + 1] = cum[c] + t * t * t;
+            }
+            size_t c = 0;
+            for (int sidx = 0; sidx < S; sidx++) {
+                const double upto = cum[cnt] * (double)(sidx + 1) / (double)S;
+                const size_t keep = (size_t)(S - 1 - sidx);  // leave at least one evaluation for every later sub-chunk
+                do members[sidx].push_back(c++);
+                while (c + keep < cnt && (sidx == S - 1 || cum[c + 1] <= upto));
+            }
+        } else {
+            for (int sidx = 0; sidx < S; sidx++)
+                for (size_t c = sidx; c < cnt; c += S) members[sidx].push_back(c);
+        }
         for (int sidx = 0; sidx < S; sidx++) {
             SubChunk &sc = subs[sidx];
             sc.base = dcur;
-            for (size_t c = sidx; c < cnt; c += S) {
+            for (size_t c : members[sidx]) {
                 const Request &rq = reqs[first + c];
                 const Series &s = ctx->series[rq.series];
                 EvalDesc &e = ctx->h_descs[dcur++];
