@@ -70,10 +70,10 @@ k_prep(const EvalDesc *__restrict__ descs, ModelDims md, const double *__restric
 // grid (lower tiles, evaluations), 256 threads, one 64x64 tile of K + noise per CTA, written
 // column-major (lanes along rows: coalesced 512 B column segments).  Rows/cols >= n are the
 // identity.  dynamic smem: B (Q*D*D) + c (Q) doubles.
-// resident CTAs per SM the register budget of k_assemble is set for: 4 (64 registers, no
-// spills) up to Q = 5, 2 for wider kernels
+// resident CTAs per SM the register budget of k_assemble is set for: 3 (80 registers, no spills;
+// measured faster than 4 CTAs at 64 registers with spills) up to Q = 5, 2 for wider kernels
 #ifndef MEDGP_AOCC
-#define MEDGP_AOCC 4
+#define MEDGP_AOCC 3
 #endif
 // The 16 columns of one thread in a tile with no special cases: an off-diagonal tile that does not
 // touch the ragged end of the matrix (every pair is a real pair below the diagonal) -- all but

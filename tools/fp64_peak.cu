@@ -52,5 +52,40 @@ int main()
             printf("%s warps/block=%2d blocks=%d : %.2f TFLOP/s (%.3f ms)\n", which ? "DMMA" : "DFMA", warps, blocks, fl / best / 1e9, best);
         }
     }
+    // Do DFMA and DMMA run on the same datapath?  Both kernels at once (two streams, one 8-warp
+    // CTA of each per SM): separate pipes would add up to about 71 TFLOP/s, one shared pipe stays at
+    // about 35-37 in total.
+    {
+        cudaStream_t sa, sb;
+        cudaStreamCreateWithFlags(&sa, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking);
+        const int threads = 256, blocks = 148, iters = 40000;
+        double *out2; cudaMalloc(&out2, 148 * 8 * 1024 * 8);
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {
+            cudaDeviceSynchronize();
+            cudaEventRecord(e0, sa);
+            cudaStreamWaitEvent(sb, e0, 0);
+            k_dfma<<<blocks, threads, 0, sa>>>(out, iters, 1.0000001, 1e-9);
+            k_dmma<<<blocks, threads, 0, sb>>>(out2, iters, 1.0000001, 1e-9);
+            cudaEventRecord(e1, sb);
+            cudaStreamWaitEvent(sa, e1, 0);
+            cudaEventRecord(e1, sa);
+            cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+        }
+        const double f_dfma = 2.0 * 16 * iters * (double)threads * blocks, f_dmma = 2.0 * 256 * 16 * iters * 8.0 * blocks;
+        printf("DFMA + DMMA concurrently (one 8-warp CTA of each per SM): %.3f ms, %.2f + %.2f = %.2f TFLOP/s in total\n", best,
+               f_dfma / best / 1e9, f_dmma / best / 1e9, (f_dfma + f_dmma) / best / 1e9);
+        for (int which = 0; which < 2; which++) {
+            cudaDeviceSynchronize();
+            cudaEventRecord(e0, sa);
+            if (which == 0) k_dfma<<<blocks, threads, 0, sa>>>(out, iters, 1.0000001, 1e-9);
+            else k_dmma<<<blocks, threads, 0, sa>>>(out2, iters, 1.0000001, 1e-9);
+            cudaEventRecord(e1, sa); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            printf("  alone, same shape: %s %.3f ms = %.2f TFLOP/s\n", which ? "DMMA" : "DFMA", ms, (which ? f_dmma : f_dfma) / ms / 1e9);
+        }
+    }
     return 0;
 }
