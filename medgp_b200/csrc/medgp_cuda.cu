@@ -18,6 +18,7 @@
 #include <map>
 #include <memory>
 #include <numeric>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -168,6 +169,9 @@ struct medgp_ctx {
     // sub-chunk streams (fork/join around the context's stream)
     int max_streams = 1;
     bool use_graphs = true;  // MEDGP_GRAPHS=0 disables CUDA-graph replay of chunk launch sequences
+    bool allow_direct = false;          // set by the host-buffer entry points around run_batch (capture on second sighting)
+    bool lazy_capture = true;           // MEDGP_LAZY_CAPTURE=0: capture at first sighting everywhere
+    std::set<uint64_t> seen_keys;       // chunk structures issued directly once
     std::map<uint64_t, GraphEntry> graphs;
     bool fuse_diag = true;   // MEDGP_FUSE_DIAG=0: separate diagonal kernels in the left-looking path
     bool chain_diag = false; // MEDGP_CHAIN_DIAG=1: diagonal blocks k >= 1 are factored inside the panel kernel of step k-1
@@ -789,14 +793,10 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         // jitter of the failed evaluations, retires the others, and keeps the loop alive while
         // any evaluation is left.  The common case (nothing fails) is one pass plus that kernel.
         const int max_jitter = (mode == 3) ? 0 : kMaxJitter;  // online imputation never retries (see the header)
-        const bool graph_mode = !ctx->profile && ctx->use_graphs;
-        const bool loop = graph_mode && ctx->device_retry && max_jitter > 0;
-        ctx->retry_on_device = loop;
-        if (!graph_mode) {
-            const int rc = issue_all();
-            if (rc) return rc;
-        } else {
-            uint64_t key = 1469598103934665603ULL;
+        bool graph_mode = !ctx->profile && ctx->use_graphs;
+        bool loop = graph_mode && ctx->device_retry && max_jitter > 0;
+        uint64_t key = 1469598103934665603ULL;
+        if (graph_mode) {
             auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ULL; };
             mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)ctx->stagger_us); mix(ctx->chain_diag); mix(ctx->lookahead); mix((uint64_t)ctx->rl_width_now); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
             mix((uint64_t)(uintptr_t)d_theta); mix((uint64_t)(uintptr_t)d_nlml); mix((uint64_t)(uintptr_t)d_grad);
@@ -810,6 +810,25 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
                 mix(sc.cnt); mix((uint64_t)sc.items_max); mix((uint64_t)sc.nstar_max); mix((uint64_t)sc.groups_max);
                 for (int t : sc.T) mix((uint64_t)t);
             }
+            // Capture on the SECOND sighting (host-buffer entry points only, which synchronise anyway):
+            // capturing and instantiating a sequence costs about as much as several direct issues, and
+            // callers like the with-update imputation (a new set of history windows at every time stamp)
+            // never show the same chunk structure twice.  The device-resident entry points always
+            // replay graphs -- their contract is "no host synchronisation inside the call", and
+            // without the graph's WHILE node the jitter rounds are driven by the host.
+            if (ctx->allow_direct && ctx->graphs.find(key) == ctx->graphs.end()) {
+                if (ctx->seen_keys.size() > 8192) ctx->seen_keys.clear();
+                if (ctx->seen_keys.insert(key).second) {
+                    graph_mode = false;
+                    loop = false;
+                }
+            }
+        }
+        ctx->retry_on_device = loop;
+        if (!graph_mode) {
+            const int rc = issue_all();
+            if (rc) return rc;
+        } else {
             auto it = ctx->graphs.find(key);
             if (it == ctx->graphs.end()) {
                 long long before[MEDGP_STAGE_COUNT];
@@ -943,6 +962,7 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     ctx->timeline = getenv("MEDGP_TIMELINE");
     if (const char *ev = getenv("MEDGP_FUSE_DIAG")) ctx->fuse_diag = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_GRAPHS")) ctx->use_graphs = atoi(ev) != 0;
+    if (const char *ev = getenv("MEDGP_LAZY_CAPTURE")) ctx->lazy_capture = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_DEVICE_RETRY")) ctx->device_retry = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_LOOKAHEAD")) ctx->lookahead = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_RL_W")) ctx->rl_width = std::max(0, atoi(ev));
@@ -1471,7 +1491,9 @@ MEDGP_API int medgp_cuda_nlml_grad(medgp_ctx *ctx, int batch, const int *series_
     std::vector<Request> reqs(batch);
     for (int b = 0; b < batch; b++) reqs[b] = {series_id[b], b, 0, 0, 0};
     CU(cudaMemsetAsync(ctx->d_fail, 0, batch * sizeof(int), st));
+    ctx->allow_direct = ctx->lazy_capture;  // a chunk structure seen for the first time is issued directly
     rc = run_batch(ctx, reqs, ctx->d_theta, want_grad ? 1 : 0, d_nlml, d_grad, ctx->d_status, nullptr, nullptr, 0);
+    ctx->allow_direct = false;
     if (rc) return rc;
     // jitter retries happened inside the launch sequence (graph WHILE node); without it the
     // host drives them
@@ -1533,7 +1555,9 @@ MEDGP_API int medgp_cuda_predict(medgp_ctx *ctx, int batch, const int *series_id
     for (int b = 0; b < batch; b++)
         reqs[b] = {series_id[b], b, 0, star_offset[b + 1] - star_offset[b], star_offset[b]};
     CU(cudaMemsetAsync(ctx->d_fail, 0, batch * sizeof(int), st));
+    ctx->allow_direct = ctx->lazy_capture;  // a chunk structure seen for the first time is issued directly
     rc = run_batch(ctx, reqs, ctx->d_theta, 2, d_nlml, nullptr, ctx->d_status, d_mean, d_var, 0);
+    ctx->allow_direct = false;
     if (rc) return rc;
     if (!ctx->retry_on_device) {
         rc = host_retry_rounds(ctx, std::move(reqs), batch, ctx->d_theta, 2, d_nlml, nullptr, ctx->d_status, d_mean, d_var);
@@ -1582,7 +1606,9 @@ MEDGP_API int medgp_cuda_predict_online(medgp_ctx *ctx, int batch, const int *se
     CU(cudaMemcpyAsync(ctx->d_theta, ctx->h_theta, (size_t)batch * P * 8, cudaMemcpyHostToDevice, st));
     double *d_nlml = ctx->d_out, *d_mean = ctx->d_out + batch, *d_var = d_mean + ntot;
     CU(cudaMemsetAsync(ctx->d_fail, 0, batch * sizeof(int), st));
+    ctx->allow_direct = ctx->lazy_capture;  // a chunk structure seen for the first time is issued directly
     rc = run_batch(ctx, reqs, ctx->d_theta, 3, d_nlml, nullptr, ctx->d_status, d_mean, d_var, 0);
+    ctx->allow_direct = false;
     if (rc) return rc;
     rc = release_desc_slot(ctx);
     if (rc) return rc;
