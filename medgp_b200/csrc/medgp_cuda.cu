@@ -169,6 +169,11 @@ struct medgp_ctx {
     // sub-chunk streams (fork/join around the context's stream)
     int max_streams = 1;
     bool use_graphs = true;  // MEDGP_GRAPHS=0 disables CUDA-graph replay of chunk launch sequences
+    // device + pinned blocks of finished optimiser sessions, kept for the next session: cudaFree /
+    // cudaMalloc were observed to take up to 0.7 s each on a busy context, and a new session at the
+    // old addresses also finds its launch sequences in the graph cache
+    struct ScgBlock { char *dev = nullptr; size_t dev_bytes = 0; int *host = nullptr; size_t host_bytes = 0; bool busy = false; };
+    std::vector<ScgBlock> scg_blocks;
     bool allow_direct = false;          // set by the host-buffer entry points around run_batch (capture on second sighting)
     bool lazy_capture = true;           // MEDGP_LAZY_CAPTURE=0: capture at first sighting everywhere
     std::set<uint64_t> seen_keys;       // chunk structures issued directly once
@@ -1012,6 +1017,10 @@ MEDGP_API void medgp_cuda_destroy(medgp_ctx *ctx)
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     ctx->blob_pool.clear();
+    for (auto &blk : ctx->scg_blocks) {
+        cudaFree(blk.dev);
+        cudaFreeHost(blk.host);
+    }
     if (ctx->h_upload) cudaFreeHost(ctx->h_upload);
     cudaFree(ctx->arena);
     cudaFree(ctx->d_tickets);
@@ -1711,6 +1720,9 @@ struct medgp_scg {
     signed char *d_ptype = nullptr, *d_pexp = nullptr;
     float *d_ppar = nullptr;
     int *h_active = nullptr;  // pinned: [0] = live count, [1 + b] = skip flag of instance b
+    double *d_theta0 = nullptr;  // staging of scg_start
+    int *d_len = nullptr;
+    int block = -1;              // index of the session's block in ctx->scg_blocks
     std::vector<int> live;    // instances that wanted an evaluation at the last poll
     std::vector<int> launch;  // instances the super-steps are launched for (a superset of live)
     bool started = false;
@@ -1723,24 +1735,60 @@ MEDGP_API int medgp_cuda_scg_create(medgp_ctx *ctx, int count, medgp_scg **out)
         return MEDGP_ERR_ARG;
     }
     cudaSetDevice(ctx->device);
+    const size_t P = ctx->md.P, n = (size_t)count;
+    // one device block per session, carved below; the last two pieces stage theta0 / budgets of scg_start
+    const size_t sizes[] = {n * sizeof(ScgScalars), n * SCG_NVEC * P * 8, n * P * 8, n * 8, n * P * 8, n * sizeof(int),
+                            n * sizeof(int), sizeof(int), n * P, n * P, n * P * 2 * sizeof(float), n * P * 8, n * sizeof(int)};
+    size_t total = 0;
+    for (size_t b : sizes) total += align_up(b, 256);
+    const size_t host_bytes = (n + 1) * sizeof(int);
+    int slot = -1;
+    for (size_t k = 0; k < ctx->scg_blocks.size(); k++) {
+        const auto &blk = ctx->scg_blocks[k];
+        if (!blk.busy && blk.dev_bytes >= total && blk.host_bytes >= host_bytes &&
+            (slot < 0 || blk.dev_bytes < ctx->scg_blocks[slot].dev_bytes))
+            slot = (int)k;
+    }
+    if (slot < 0) {
+        medgp_ctx::ScgBlock blk;
+        if (cudaMalloc(&blk.dev, total) != cudaSuccess || cudaMallocHost(&blk.host, host_bytes) != cudaSuccess) {
+            if (blk.dev) cudaFree(blk.dev);
+            cudaGetLastError();
+            ctx->err = "scg_create: out of memory";
+            return MEDGP_ERR_NOMEM;
+        }
+        blk.dev_bytes = total;
+        blk.host_bytes = host_bytes;
+        ctx->scg_blocks.push_back(blk);
+        slot = (int)ctx->scg_blocks.size() - 1;
+    }
+    ctx->scg_blocks[slot].busy = true;
     medgp_scg *g = new medgp_scg();
     g->ctx = ctx;
-    const size_t P = ctx->md.P, n = (size_t)count;
+    g->block = slot;
     g->S.count = count;
     g->S.P = (int)P;
-    bool ok = cudaMalloc(&g->S.sc, n * sizeof(ScgScalars)) == cudaSuccess &&
-              cudaMalloc(&g->S.vec, n * SCG_NVEC * P * 8) == cudaSuccess &&
-              cudaMalloc(&g->S.theta, n * P * 8) == cudaSuccess && cudaMalloc(&g->S.nlml, n * 8) == cudaSuccess &&
-              cudaMalloc(&g->S.grad, n * P * 8) == cudaSuccess && cudaMalloc(&g->S.status, n * sizeof(int)) == cudaSuccess &&
-              cudaMalloc(&g->S.skip, n * sizeof(int)) == cudaSuccess && cudaMalloc(&g->S.active, sizeof(int)) == cudaSuccess &&
-              cudaMalloc(&g->d_ptype, n * P) == cudaSuccess && cudaMalloc(&g->d_pexp, n * P) == cudaSuccess &&
-              cudaMalloc(&g->d_ppar, n * P * 2 * sizeof(float)) == cudaSuccess &&
-              cudaMallocHost(&g->h_active, (n + 1) * sizeof(int)) == cudaSuccess;
-    if (!ok) {
-        ctx->err = "scg_create: out of memory";
-        medgp_cuda_scg_destroy(g);
-        return MEDGP_ERR_NOMEM;
-    }
+    char *p = ctx->scg_blocks[slot].dev;
+    int piece = 0;
+    auto take = [&]() {
+        char *r = p;
+        p += align_up(sizes[piece++], 256);
+        return r;
+    };
+    g->S.sc = (ScgScalars *)take();
+    g->S.vec = (double *)take();
+    g->S.theta = (double *)take();
+    g->S.nlml = (double *)take();
+    g->S.grad = (double *)take();
+    g->S.status = (int *)take();
+    g->S.skip = (int *)take();
+    g->S.active = (int *)take();
+    g->d_ptype = (signed char *)take();
+    g->d_pexp = (signed char *)take();
+    g->d_ppar = (float *)take();
+    g->d_theta0 = (double *)take();
+    g->d_len = (int *)take();
+    g->h_active = ctx->scg_blocks[slot].host;
     *out = g;
     return MEDGP_OK;
 }
@@ -1749,11 +1797,8 @@ MEDGP_API void medgp_cuda_scg_destroy(medgp_scg *g)
 {
     if (!g) return;
     cudaSetDevice(g->ctx->device);
-    cudaStreamSynchronize(g->ctx->stream);
-    cudaFree(g->S.sc); cudaFree(g->S.vec); cudaFree(g->S.theta); cudaFree(g->S.nlml); cudaFree(g->S.grad);
-    cudaFree(g->S.status); cudaFree(g->S.skip); cudaFree(g->S.active);
-    cudaFree(g->d_ptype); cudaFree(g->d_pexp); cudaFree(g->d_ppar);
-    if (g->h_active) cudaFreeHost(g->h_active);
+    cudaStreamSynchronize(g->ctx->stream);  // nothing enqueued for the session is still running
+    if (g->block >= 0 && g->block < (int)g->ctx->scg_blocks.size()) g->ctx->scg_blocks[g->block].busy = false;
     delete g;
 }
 
@@ -1790,10 +1835,8 @@ MEDGP_API int medgp_cuda_scg_start(medgp_scg *g, const int *series_id, const dou
     cudaStream_t st = ctx->stream;
     CU(cudaStreamSynchronize(st));  // the staging buffers below are plain temporaries
     g->series.assign(series_id, series_id + count);
-    double *d_theta0 = nullptr;
-    int *d_len = nullptr;
-    CU(cudaMalloc(&d_theta0, (size_t)count * P * 8));
-    CU(cudaMalloc(&d_len, (size_t)count * sizeof(int)));
+    double *d_theta0 = g->d_theta0;
+    int *d_len = g->d_len;
     CU(cudaMemcpyAsync(d_theta0, theta0, (size_t)count * P * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_len, max_iteration, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, st));
     if (prior_type) {
@@ -1806,9 +1849,7 @@ MEDGP_API int medgp_cuda_scg_start(medgp_scg *g, const int *series_id, const dou
     }
     k_scg_start<<<count, MEDGP_SCG_THREADS, 0, st>>>(g->S, d_theta0, d_len);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(st));
-    cudaFree(d_theta0);
-    cudaFree(d_len);
+    CU(cudaStreamSynchronize(st));  // the caller's host arrays have been consumed
     g->started = true;
     g->launch.clear();
     return scg_count_active(g, nullptr);

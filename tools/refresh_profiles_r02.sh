@@ -31,3 +31,10 @@ python tools/bench_latency.py 2> /dev/null | tail -1 > "gpurun_out/${TAG}_latenc
 python tools/bench_cohort_train.py 256 500 20 300 > "gpurun_out/${TAG}_cohort_train.txt" 2>&1
 python tools/bench_predict.py 16 500 > "gpurun_out/${TAG}_online_imputation.json" 2> /dev/null
 ls -la gpurun_out | tail -30
+# 5. summarise on the box (the raw .ncu-rep files together exceed what gpurun copies back) and
+#    hand the committed-evidence files over in gpurun_out/profiles_out/
+python tools/refresh_profiles_post_r02.py "${TAG}" > "gpurun_out/${TAG}_post.log" 2>&1
+mkdir -p gpurun_out/profiles_out
+cp profiles/${TAG}_* profiles/traffic.json gpurun_out/profiles_out/ 2>/dev/null
+rm -f gpurun_out/${TAG}_ncu_*.ncu-rep
+du -sh gpurun_out
