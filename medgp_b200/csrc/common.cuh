@@ -140,14 +140,14 @@ __device__ __forceinline__ int flag_acquire(const int *flag)
     return v;
 }
 
-// Warp -> quadrant assignment of the tile GEMM kernels.  The hardware places warp w of a CTA on
-// SM sub-partition w % 4, each with its own FP64 tensor pipe.  Wherever a quadrant of a tile
-// product is skipped (zero blocks of triangular operands, the unused part of symmetric results,
-// rows beyond the end of a ragged matrix) the same sub-partitions would idle in EVERY resident
-// CTA while the others stay the bottleneck; rotating the assignment by the block index spreads
-// the skipped quadrants over all four pipes.
+// Warp -> quadrant assignment of the tile GEMM kernels.  Wherever a quadrant of a tile product is
+// skipped (zero blocks of triangular operands, the unused part of symmetric results, rows beyond
+// the end of a ragged matrix) the same warp indices idle in every CTA.  If warp w of every CTA sat
+// on SM sub-partition w, rotating the assignment by the block index would spread the skipped
+// quadrants over the four FP64 pipes; measured on B200 (MEDGP_WARP_ROT=1 against 0 on the C3
+// cohort): no difference, so the plain assignment is the default and the switch stays for experiments.
 #ifndef MEDGP_WARP_ROT
-#define MEDGP_WARP_ROT 1
+#define MEDGP_WARP_ROT 0
 #endif
 __device__ __forceinline__ int gemm_warp()
 {

@@ -20,8 +20,7 @@ __device__ __forceinline__ double *tile_ptr(double *M, int T, int ti, int tj)
 // second product of the panel kernels: acc = sP * X^T with sP, sX pitch-SLD tiles in smem,
 // sP[c][m] (column-major), sX[c][n] = X(n,c), X LOWER triangular: X(n, c) = 0 for c > n, so the
 // 8-column sub-tile starting at column n0 only needs the k-steps (of 4) below (n0 + 8) / 4 --
-// 288 DMMAs per tile instead of 512 (the warp rotation of gemm_warp() evens the two column
-// halves out over the SM's four pipes).  RAGGED: the tile touches the end of the matrix -- only
+// 288 DMMAs per tile instead of 512.  RAGGED: the tile touches the end of the matrix -- only
 // mx / ny sub-tiles of this warp hold rows / columns below n and P is zero from column 4 k4max on.
 template <int WN, bool RAGGED>
 __device__ __forceinline__ void gemm2_tri_half(double (&acc)[4][4][2], const double *sP, const double *sX,
@@ -387,6 +386,8 @@ __device__ __forceinline__ void xblock16(const double *sA, double *sX, int I, in
 // Call with all 128 threads after a barrier that makes sA visible; returns after a barrier.
 __device__ __forceinline__ void potf2_inv_blocked(double *sA, double *sX, double *logdet, int *s_fail)
 {
+    // (rotating these warp roles by the block index, so that the factoring warps of the CTAs resident
+    // on one SM would not share a sub-partition, was measured: no difference)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #pragma unroll 1
     for (int J = 0; J < 4; J++) {
