@@ -505,7 +505,9 @@ def run_ours(args):
             "note": "sum n^3 of the cohort / step time / GPUs: the tensor-core work against the DGEMM yardstick with the "
                     "FP64-pipe-bound assembly and gradient kernels inside the same time"}
         roofline["note"] = ("assembly and gradient kernels are FP64-pipe bound at Q=5 (about 19 FMA per byte against a "
-                            "2.6 FMA/B machine balance), so their HBM fraction is low by construction; DESIGN.md section 4")
+                            "2.6 FMA/B machine balance), so their HBM fraction is low by construction; DFMA and DMMA share one "
+                            "datapath on B200 (profiles/r02_fp64_peak.txt: run concurrently they take the sum of their separate "
+                            "times), so that work adds to the factorisation's instead of hiding behind it; DESIGN.md section 4")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,

@@ -276,7 +276,7 @@ def test_changing_the_model_on_a_live_context(api, oracle):
         ctx.set_model(Q, D, R)
         sids = [ctx.add_series(meta, x, y) for _ in range(3)]
         thetas = synth.init_hyp_lmc_sm(Q, D, R, 3, seed=8)
-        for _ in range(2):  # the second call replays what the first one captured
+        for _ in range(3):  # first sighting: plain launches; second: captured; third: replayed
             f, g, st = ctx.nlml_grad(sids, thetas, True)
         for b in range(3):
             f0, g0, _ = oracle.nlml_grad(Q, D, R, meta, x, y, thetas[b])
@@ -284,6 +284,35 @@ def test_changing_the_model_on_a_live_context(api, oracle):
     with pytest.raises(api.MedgpError):
         ctx.set_model(2, 2, 2)   # series still uploaded
     ctx.close()
+
+
+def test_direct_captured_and_replayed_sequences_agree(api, monkeypatch):
+    """A batch structure is issued as plain launches at its first sighting, captured into a CUDA graph
+    at the second and replayed from the third call on (host-buffer entry points); MEDGP_LAZY_CAPTURE=0
+    captures at once.  All of them must return the same bits, jitter rounds included."""
+    Q, D, R = 3, 4, 2
+    sizes = [70, 200, 333, 64, 129]
+    series = [synth.make_patient(D, n, seed=700 + n) for n in sizes]
+    thetas = synth.init_hyp_lmc_sm(Q, D, R, len(sizes), seed=3)
+    results = []
+    for lazy in ("1", "0"):
+        monkeypatch.setenv("MEDGP_LAZY_CAPTURE", lazy)
+        ctx = api.Context(Q, D, R, workspace_bytes=1 << 30)
+        ctx.force_fail(1)  # every evaluation needs one jitter round: host-driven when direct, in-graph otherwise
+        sids = [ctx.add_series(*s) for s in series]
+        for _ in range(3):
+            f, g, st = ctx.nlml_grad(sids, thetas, True)
+            results.append((f.copy(), g.copy(), st.copy()))
+        mean, var, _ = ctx.predict(sids[:2], thetas[:2], [0, 1, 2], series[0][0][:2], series[0][1][:2] + 0.5)
+        results.append((mean.copy(), var.copy(), np.zeros(1)))
+        ctx.close()
+    for k in range(1, 3):
+        for a, b in zip(results[0], results[k]):
+            assert np.array_equal(a, b)
+    for a, b in zip(results[0], results[4]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(results[3][0], results[7][0]) and np.array_equal(results[3][1], results[7][1])
+    assert (results[0][2] == 1).all()
 
 
 def test_argument_checks(api):
