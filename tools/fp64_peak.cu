@@ -52,6 +52,19 @@ int main()
             printf("%s warps/block=%2d blocks=%d : %.2f TFLOP/s (%.3f ms)\n", which ? "DMMA" : "DFMA", warps, blocks, fl / best / 1e9, best);
         }
     }
+    // How many warps per SM sub-partition does the DMMA pipe need?  One CTA per SM, 1/2/3/4 warps per sub-partition
+    // (16 independent accumulators per warp).
+    for (int wps = 1; wps <= 4; wps++) {
+        const int threads = 128 * wps, blocks = 148, iters = 20000;
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {
+            cudaEventRecord(e0);
+            k_dmma<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+        }
+        printf("DMMA %d warp(s) per sub-partition: %.2f TFLOP/s\n", wps, 2.0 * 256 * 16 * iters * (double)(threads / 32) * blocks / best / 1e9);
+    }
     // Do DFMA and DMMA run on the same datapath?  Both kernels at once (two streams, one 8-warp
     // CTA of each per SM): separate pipes would add up to about 71 TFLOP/s, one shared pipe stays at
     // about 35-37 in total.
