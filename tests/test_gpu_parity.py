@@ -85,6 +85,29 @@ def test_ragged_batch_and_order_invariance(api, oracle):
     ctx.close()
 
 
+@pytest.mark.parametrize("rl", ["0", "1"])
+def test_ragged_last_block_row(api, oracle, monkeypatch, rl):
+    """The tile kernels do not issue the DMMAs of rows / columns beyond n in the last block row
+    (8-row, 8-column, 4-deep granularity): every residue class that changes which sub-tiles are
+    skipped, in both factorisation schedules, against the oracle -- NLML, gradient, and K^-1 itself."""
+    monkeypatch.setenv("MEDGP_RL", rl)
+    Q, D, R = 2, 3, 2
+    sizes = [128 + r for r in (1, 4, 7, 8, 9, 31, 32, 33, 57, 63)] + [64 + 5, 3 * 64 + 40]
+    series = [synth.make_patient(D, n, seed=300 + n) for n in sizes]
+    thetas = synth.init_hyp_lmc_sm(Q, D, R, len(sizes), seed=21)
+    ctx = api.Context(Q, D, R, workspace_bytes=1 << 30)
+    sids = [ctx.add_series(*s) for s in series]
+    f, g, st = ctx.nlml_grad(sids, thetas, True)
+    for k, n in enumerate(sizes):
+        f0, g0, _ = oracle.nlml_grad(Q, D, R, *series[k], thetas[k])
+        assert st[k] == 0 and abs(f[k] - f0) <= RTOL * abs(f0) and rel(g[k], g0) <= RTOL, n
+    for k in (2, 5, 9):
+        dbg = ctx.debug_matrices(sids[k], thetas[k], sizes[k])
+        K = oracle.gram(Q, D, R, series[k][0], series[k][1], thetas[k])
+        assert rel(dbg["Kinv"], np.linalg.inv(K)) <= RTOL
+    ctx.close()
+
+
 def test_duplicate_timestamps_and_two_point_features(api, oracle):
     Q, D, R = 2, 3, 2
     meta = np.array([0, 0, 1, 1, 1, 2, 2], dtype=np.int32)
