@@ -35,7 +35,8 @@ struct ModelDims {
 
 struct __align__(16) EvalDesc {
     double *M, *dinv, *dinvT, *rhs, *alpha, *cs, *par, *part, *blk;
-    int *flags;              // T ints: flags[k] = 1 once diagonal block k is factored (k_potrf_step)
+    int *flags;              // T x T ints: flags[i*T + j] = 1 once tile (i, j) is final (lower: L, upper: U = L^-T).
+                             // k_potrf_step uses the diagonal entries only, the dataflow kernels all of them
     const double *t, *y;
     const int *meta, *off;
     const int4 *items;

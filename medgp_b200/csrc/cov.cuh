@@ -57,7 +57,7 @@ k_prep(const EvalDesc *__restrict__ descs, ModelDims md, const double *__restric
     }
     const int npad = e.npad;
     for (int i = tid; i < npad; i += blockDim.x) e.rhs[i] = (i < e.n) ? e.y[i] : 0.0;  // rhs row 0 = y
-    for (int k = tid; k < e.T; k += blockDim.x) e.flags[k] = 0;
+    for (int k = tid; k < e.T * e.T; k += blockDim.x) e.flags[k] = 0;  // one per tile
     for (int idx = tid; idx < Q * npad; idx += blockDim.x) {
         const int q = idx / npad, i = idx - q * npad;
         double sn = 0.0, cs = 1.0;

@@ -115,7 +115,7 @@ __device__ __forceinline__ void tile_matvec_rhs(const EvalDesc &e, const double 
     const int tid = threadIdx.x, r = tid & 63, half = tid >> 6, ld = e.npad;
     double *vs = red + 2 * MEDGP_NB;
     for (int q = 0; q < e.nrhs; q++) {
-        if (tid < MEDGP_NB) vs[tid] = (q == 0 && have_v0) ? v0 : vec_base[(size_t)q * ld + tid];
+        if (tid < MEDGP_NB) vs[tid] = (q == 0 && have_v0) ? v0 : __ldcg(vec_base + (size_t)q * ld + tid);
         __syncthreads();
         const int cmax = lower_only ? r : MEDGP_NB - 1;
         double s4[4] = {0.0, 0.0, 0.0, 0.0};  // four independent chains
@@ -165,8 +165,9 @@ __device__ __forceinline__ void acc_matvec_rhs(const double (&acc)[4][4][2], con
             for (int a = 0; a < 4; a++) red[wn * MEDGP_NB + wm * 32 + 8 * a + r] = ps[a];
         __syncthreads();
         if (threadIdx.x < MEDGP_NB) {
-            double *o = out_base + (size_t)q * ld;
-            o[threadIdx.x] -= red[threadIdx.x] + red[MEDGP_NB + threadIdx.x];
+            // through L2: in the dataflow kernels the previous update of this block came from another CTA of the same launch
+            double *o = out_base + (size_t)q * ld + threadIdx.x;
+            __stcg(o, __ldcg(o) - (red[threadIdx.x] + red[MEDGP_NB + threadIdx.x]));
         }
         __syncthreads();
     }
@@ -449,7 +450,7 @@ __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, doub
         const int idx = tid + MEDGP_DIAG_THREADS * u, c = idx >> 5, rp = idx & 31;
         kv[u] = *reinterpret_cast<const double2 *>(Kkk + c * MEDGP_SLD + 2 * rp);
     }
-    const double v0 = (tid < MEDGP_NB) ? e.rhs[k * MEDGP_NB + tid] : 0.0;
+    const double v0 = (tid < MEDGP_NB) ? __ldcg(e.rhs + k * MEDGP_NB + tid) : 0.0;
 #pragma unroll
     for (int u = 0; u < 16; u++) {
         const int idx = tid + MEDGP_DIAG_THREADS * u, c = idx >> 5, rp = idx & 31, o = c * MEDGP_SLD + 2 * rp;
@@ -669,7 +670,7 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, 
         diag_block_factor(e, k, sP, sX, &gjb, &s_fail, fail, products, true);
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) flag_release(e.flags + k);
+        if (threadIdx.x == 0) flag_release(e.flags + k * T + k);
         return;
     }
     const int i = k + row;
@@ -691,7 +692,7 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, 
     __syncthreads();            // every warp is done with the pipeline buffers
     acc_to_smem(acc, sP, 1.0);
     if (threadIdx.x == 0)
-        while (flag_acquire(e.flags + k) == 0) __nanosleep(64);
+        while (flag_acquire(e.flags + k * T + k) == 0) __nanosleep(64);
     __syncthreads();
     tile_bulk_g2s(sX, Xk, &bars);
     tile_bulk_wait(&bars);
@@ -707,6 +708,179 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, 
     double *Kii = tile_ptr(M, T, i, i);
     acc_rsub_global(acc, Kii);
     acc_to_global(acc, Kii);
+}
+
+// ------------------------------------------------------------------ dataflow factorisation
+// ONE launch for the whole factorisation of every matrix of a sub-chunk (k_potrf_flow) and one for
+// the whole triangular inverse (k_trtri_flow).  Every tile is a role; a role streams its tile
+// products in order and waits, tile pair by tile pair, for the per-tile flags of its operands, so
+// block columns overlap as far as the data dependencies allow: for ONE large matrix the critical
+// path shrinks from "every launch of every block column" to diagonal block -> last product ->
+// second product per column, while all other products run ahead; for many small matrices the
+// launch boundaries (2 per block column) and their tails disappear.
+// Roles are tickets drawn from a counter when a CTA starts running, in an order that is a
+// topological order of the dependency graph (potrf: by block column, diagonal roles of a column
+// first; trtri: by block row of L^-1).  A role only ever waits for roles with smaller tickets, and
+// a ticket is only ever held by a CTA that is already running, so forward progress does not depend
+// on dispatch order, grid size or what else shares the GPU.
+// FlowMap: act[t] = evaluations of the sub-chunk with more than t block rows (the descriptors are
+// sorted by size, so these are prefixes), base[k] = first ticket of block column / row k.
+#define MEDGP_FLOW_TMAX 64
+struct FlowMap {
+    int Tmax, total;
+    int act[MEDGP_FLOW_TMAX + 1];
+    int base[MEDGP_FLOW_TMAX + 1];
+};
+
+__device__ __forceinline__ void flag_wait(const int *flag)
+{
+    while (flag_acquire(flag) == 0) __nanosleep(40);
+}
+
+// publish a finished tile: every thread's stores, then the flag (call with all threads)
+__device__ __forceinline__ void tile_publish(int *flag)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) flag_release(flag);
+}
+
+__global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
+k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap map, int *__restrict__ fail,
+             int *__restrict__ ticket)
+{
+    extern __shared__ __align__(128) double smem[];
+    __shared__ GemmBars bars;
+    __shared__ __align__(16) GjBufs gjb;
+    __shared__ double red[2 * MEDGP_NB];
+    __shared__ int s_fail, s_role[3];
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        int k = 0;
+        while (k + 1 < map.Tmax && map.base[k + 1] <= t) k++;
+        int rem = t - map.base[k], r = 0;
+        while (k + r < map.Tmax && rem >= map.act[k + r]) rem -= map.act[k + r++];  // row offset r: act[k + r] evaluations have that row
+        s_role[0] = k; s_role[1] = r; s_role[2] = rem;
+        s_fail = 0;
+    }
+    __syncthreads();
+    const int k = s_role[0], r = s_role[1];
+    const EvalDesc &e = descs[s_role[2]];
+    if (e.skip) return;  // (every role of this evaluation returns: nobody waits for it)
+    const int T = e.T, i = k + r;
+    double *M = e.M;
+    int *flags = e.flags;
+    double *sP = smem, *sX = smem + kTileElems;
+    gemm_bars_init(&bars);
+    double acc[4][4][2];
+    acc_zero(acc);
+    int waited = -1;  // (lane 0 of the producer warp) last tile pair whose flags have been seen
+    if (r == 0) {
+        // ---- diagonal block k: D = K_kk - sum_{l<k} L_kl L_kl^T, factor, invert, forward-solve block
+        if (k > 0) prefetch_tile_l2(tile_ptr(M, T, k, k));
+        gemm_nt_tiles(acc, k,
+                      [&](int l, const double *&A, const double *&B) {
+                          if (l > waited) {
+                              flag_wait(flags + k * T + l);
+                              asm volatile("fence.proxy.async;" ::: "memory");  // the tile's generic-proxy writes -> our bulk copies
+                              waited = l;
+                          }
+                          A = tile_ptr(M, T, k, l);
+                          B = A;
+                      },
+                      smem, &bars, NoStageFn(), [](int, int wm, int wn) { return wm == 0 && wn == 1; },
+                      TileEdge{rows_valid(e, k), rows_valid(e, k), MEDGP_NB});
+        __syncthreads();  // all warps are done with the ring before it is reused as sP
+        if (k > 0) acc_to_smem(acc, sP, 1.0);
+        __syncthreads();
+        diag_block_factor(e, k, sP, sX, &gjb, &s_fail, fail, k > 0, true);
+        tile_publish(flags + k * T + k);
+        return;
+    }
+    // ---- panel tile (i, k): L_ik = (K_ik - sum_{l<k} L_il L_kl^T) X_kk^T
+    double *Tik = tile_ptr(M, T, i, k);
+    const double *Xk = e.dinv + (size_t)k * kTileElems;
+    prefetch_tile_l2(Tik);
+    const int mv = rows_valid(e, i);
+    gemm_nt_tiles(acc, k,
+                  [&](int l, const double *&A, const double *&B) {
+                      if (l > waited) {
+                          flag_wait(flags + i * T + l);
+                          flag_wait(flags + k * T + l);
+                          asm volatile("fence.proxy.async;" ::: "memory");
+                          waited = l;
+                      }
+                      A = tile_ptr(M, T, i, l);
+                      B = tile_ptr(M, T, k, l);
+                  },
+                  smem, &bars, NoStageFn(), NoSkipFn(), TileEdge{mv, MEDGP_NB, MEDGP_NB});
+    acc_rsub_global(acc, Tik);  // P = K_ik - C (K_ik comes from the assembly kernel: complete at launch)
+    __syncthreads();            // every warp is done with the pipeline buffers
+    acc_to_smem(acc, sP, 1.0);
+    if (threadIdx.x == 0) flag_wait(flags + k * T + k);
+    __syncthreads();
+    tile_bulk_g2s(sX, Xk, &bars);
+    tile_bulk_wait(&bars);
+    __syncthreads();
+    gemm2_smem(acc, sP, sX, mv);
+    acc_to_global(acc, Tik);
+    // forward solve: rhs_i -= L_ik z_k.  The roles (i, k') of one block row run in the order of k'
+    // (role (i, k) has waited for tile (i, k-1), published after ITS update), so the updates of rhs_i
+    // are applied in a fixed order: bit-reproducible, no atomics
+    acc_matvec_rhs(acc, e, e.rhs + k * MEDGP_NB, e.rhs + i * MEDGP_NB, red);
+    tile_publish(flags + i * T + k);
+}
+
+// the triangular inverse the same way: role (j, i), j < i: U_ji = -(sum_{l=j}^{i-1} U_jl L_il^T) X_ii^T with
+// U_jj = X_jj^T; it waits for U_jl, j < l < i (tiles of earlier block rows: smaller tickets).
+// base[i] = first ticket of block row i (i >= 1), act[i] evaluations have it, i roles each.
+__global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
+k_trtri_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap map, int *__restrict__ ticket)
+{
+    extern __shared__ __align__(128) double smem[];
+    __shared__ GemmBars bars;
+    __shared__ int s_role[3];
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        int i = 1;
+        while (i + 1 < map.Tmax && map.base[i + 1] <= t) i++;
+        const int rem = t - map.base[i];
+        s_role[0] = i; s_role[1] = rem / map.act[i]; s_role[2] = rem % map.act[i];
+    }
+    __syncthreads();
+    const int i = s_role[0], j = s_role[1];
+    const EvalDesc &e = descs[s_role[2]];
+    if (e.skip) return;
+    const int T = e.T, nv = rows_valid(e, i);
+    double *M = e.M;
+    int *flags = e.flags;
+    gemm_bars_init(&bars);
+    double acc[4][4][2];
+    acc_zero(acc);
+    const double *XTj = e.dinvT + (size_t)j * kTileElems;
+    int waited = 0;  // (lane 0 of the producer warp) the first operand is X_jj^T, final since the factorisation
+    gemm_nt_tiles(acc, i - j,
+                  [&](int l0, const double *&A, const double *&B) {
+                      const int l = j + l0;
+                      if (l0 > waited) {
+                          flag_wait(flags + j * T + l);
+                          asm volatile("fence.proxy.async;" ::: "memory");
+                          waited = l0;
+                      }
+                      A = (l0 == 0) ? XTj : tile_ptr(M, T, j, l);
+                      B = tile_ptr(M, T, i, l);
+                  },
+                  smem, &bars, NoStageFn(), [](int ch, int wm, int) { return ch < 2 && wm == 1; },
+                  TileEdge{MEDGP_NB, nv, MEDGP_NB});
+    __syncthreads();
+    double *sP = smem, *sX = smem + kTileElems;
+    tile_bulk_g2s(sX, e.dinv + (size_t)i * kTileElems, &bars);
+    acc_to_smem(acc, sP, -1.0);
+    tile_bulk_wait(&bars);
+    __syncthreads();
+    gemm2_smem(acc, sP, sX, MEDGP_NB, nv);
+    acc_to_global(acc, tile_ptr(M, T, j, i));
+    tile_publish(flags + j * T + i);
 }
 
 // ------------------------------------------------------------------ device-side jitter loop

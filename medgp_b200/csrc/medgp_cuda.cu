@@ -191,6 +191,9 @@ struct medgp_ctx {
     cudaStream_t aux_streams[8] = {};
     cudaEvent_t ev_panel[8] = {}, ev_bulk[8] = {};
     bool lookahead = true;  // MEDGP_LOOKAHEAD=0 disables it
+    int flow = -1;          // MEDGP_FLOW bits: 1 = dataflow factorisation, 2 = dataflow triangular inverse (one launch each,
+                            // per-tile flags); -1 = chosen per chunk
+    size_t rl_count_now = 0; // evaluations in the chunk being issued
     int rl_width = 0;       // block columns per panel of the right-looking factorisation (MEDGP_RL_W); 0 = by the number
                             // of matrices in the chunk: 2 for one or two (shortest critical path), 4 beyond (measured at n = 4000)
     int rl_width_now = 2;   // the width of the chunk being issued
@@ -243,7 +246,7 @@ size_t eval_bytes(const ModelDims &md, const Series &s, int nrhs, bool grad)
     b += align_up(np * (size_t)md.Q * 16, 256);            // cs
     b += align_up((size_t)md.parLen * 8, 256);             // par
     b += align_up((size_t)s.T * 8, 256);                   // blk
-    b += align_up((size_t)s.T * 4, 256);                   // flags
+    b += align_up((size_t)s.T * s.T * 4, 256);             // flags (one per tile)
     if (grad) b += align_up((size_t)s.nseg * md.D * (3 * md.Q + 1) * 8, 256);
     return b;
 }
@@ -507,7 +510,40 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     // stream beside the next panel's factorisation.  Orderings that matter: the bulk update of a
     // panel follows its last panel kernel; the next-panel part of panel p follows the bulk of
     // panel p-1 (both touch the same block columns); bulks are ordered by their stream.
-    if (rl) {
+    // Dataflow path: ONE launch for the factorisation, ONE for the triangular inverse (linalg.cuh)
+    // Measured (n = 4000 with 1 / 5 / 32 matrices in flight, C2, C3): the dataflow inverse wins for few
+    // large matrices (-10 % / -7 % on NLML+gradient with 1 / 5 in flight) and loses 1-3 % for many small
+    // ones; the dataflow factorisation wins only for one or two matrices in flight (its resident roles
+    // advance one tile product per finished block column, so it is latency-, not throughput-oriented).
+    const int flow_bits = ctx->flow >= 0 ? ctx->flow : (rl ? (ctx->rl_count_now <= 2 ? 3 : 2) : 0);
+    const bool flow = (flow_bits & 1) != 0 && Tmax <= MEDGP_FLOW_TMAX;        // bit 0: factorisation
+    const bool flow_trtri = (flow_bits & 2) != 0 && Tmax <= MEDGP_FLOW_TMAX;  // bit 1: triangular inverse
+    FlowMap fm_potrf{}, fm_trtri{};
+    if (flow || flow_trtri) {
+        fm_potrf.Tmax = fm_trtri.Tmax = Tmax;
+        for (int t = 0; t <= Tmax; t++) fm_potrf.act[t] = fm_trtri.act[t] = (int)sc.act(t);
+        int tot = 0;
+        for (int k = 0; k < Tmax; k++) {  // block column k: one role per (evaluation, block row >= k)
+            fm_potrf.base[k] = tot;
+            for (int r = 0; k + r < Tmax; r++) tot += fm_potrf.act[k + r];
+        }
+        fm_potrf.base[Tmax] = fm_potrf.total = tot;
+        tot = 0;
+        fm_trtri.base[0] = 0;
+        for (int i = 1; i < Tmax; i++) {  // block row i of L^-1: i roles per evaluation that has it
+            fm_trtri.base[i] = tot;
+            tot += i * fm_trtri.act[i];
+        }
+        fm_trtri.base[Tmax] = fm_trtri.total = tot;
+    }
+    // (ticket counters: the last two of the sub-chunk's block; the first Tmax belong to k_potrf_step)
+    if (flow) {
+        const FlowMap fm = fm_potrf;
+        begin(MEDGP_STAGE_POTRF);
+        out.push_back([=]() { k_potrf_flow<<<fm.total, MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, fm, d_fail, tickets + kTicketsPerSub - 2); L[MEDGP_STAGE_POTRF]++; });
+        end(MEDGP_STAGE_POTRF);
+    }
+    if (rl && !flow) {
         const int W = std::max(1, ctx->rl_width_now);
         const bool rl_step = ctx->fuse_diag && Tmax <= kTicketsPerSub;
         for (int k0 = 0; k0 < Tmax; k0 += W) {
@@ -558,7 +594,7 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
             end(MEDGP_STAGE_POTRF);
         }
     }
-    for (int k = 0; k < Tmax && !rl; k++) {
+    for (int k = 0; k < Tmax && !rl && !flow; k++) {
         const unsigned a0 = sc.act(k), a1 = k + 1 < Tmax ? sc.act(k + 1) : 0;
         const int rem = Tmax - k - 1;
         if (step_kernel) {
@@ -590,7 +626,11 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     end(MEDGP_STAGE_SOLVE);
     if (grad || mode == 4) {
         begin(MEDGP_STAGE_TRTRI);
-        for (int i = 1; i < Tmax; i++) {
+        if (flow_trtri && fm_trtri.total > 0) {
+            const FlowMap fm = fm_trtri;
+            out.push_back([=]() { k_trtri_flow<<<fm.total, MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, fm, tickets + kTicketsPerSub - 1); L[MEDGP_STAGE_TRTRI]++; });
+        }
+        for (int i = 1; i < Tmax && !flow_trtri; i++) {
             const unsigned ai = sc.act(i);
             if (rl) {
                 const int k = i - 1;  // rows 0..k of U are final: push them into rows i > k
@@ -683,6 +723,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         bool rl = Tbig >= 8 && cnt * (size_t)Tbig < 600;
         if (ctx->force_rl >= 0) rl = ctx->force_rl != 0;
         ctx->rl_width_now = ctx->rl_width > 0 ? ctx->rl_width : (cnt <= 2 ? 2 : 4);
+        ctx->rl_count_now = cnt;
         // left-looking with few matrices: the diagonal kernel (one CTA per matrix) must not carry
         // a k-tile product; the panel CTAs fold their tile into the diagonal block instead
         const bool fold = !rl && cnt < ctx->fold_max;
@@ -735,7 +776,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
                 e.cs = (double *)take(np * (size_t)md.Q * 16);
                 e.par = (double *)take((size_t)md.parLen * 8);
                 e.blk = (double *)take((size_t)s.T * 8);
-                e.flags = (int *)take((size_t)s.T * 4);
+                e.flags = (int *)take((size_t)s.T * s.T * 4);
                 e.part = grad ? (double *)take((size_t)s.nseg * md.D * (3 * md.Q + 1) * 8) : nullptr;
                 e.t = s.d_t; e.y = s.d_y; e.meta = s.d_meta; e.off = s.d_off;
                 e.items = s.d_items; e.seg_start = s.d_seg_start;
@@ -803,7 +844,7 @@ int run_batch(medgp_ctx *ctx, std::vector<Request> reqs, const double *d_theta, 
         uint64_t key = 1469598103934665603ULL;
         if (graph_mode) {
             auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ULL; };
-            mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)ctx->stagger_us); mix(ctx->chain_diag); mix(ctx->lookahead); mix((uint64_t)ctx->rl_width_now); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
+            mix((uint64_t)mode); mix(rl); mix(fold); mix(ctx->fuse_diag); mix((uint64_t)ctx->stagger_us); mix(ctx->chain_diag); mix(ctx->lookahead); mix((uint64_t)(ctx->flow + 1)); mix((uint64_t)ctx->rl_width_now); mix((uint64_t)S); mix((uint64_t)dpos); mix((uint64_t)(uintptr_t)ctx->d_descs);
             mix((uint64_t)(uintptr_t)d_theta); mix((uint64_t)(uintptr_t)d_nlml); mix((uint64_t)(uintptr_t)d_grad);
             mix((uint64_t)(uintptr_t)d_status); mix((uint64_t)(uintptr_t)d_mean); mix((uint64_t)(uintptr_t)d_var);
             mix((uint64_t)(uintptr_t)ctx->d_fail); mix((uint64_t)(uintptr_t)ctx->ext_skip);
@@ -970,6 +1011,7 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     if (const char *ev = getenv("MEDGP_LAZY_CAPTURE")) ctx->lazy_capture = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_DEVICE_RETRY")) ctx->device_retry = atoi(ev) != 0;
     if (const char *ev = getenv("MEDGP_LOOKAHEAD")) ctx->lookahead = atoi(ev) != 0;
+    if (const char *ev = getenv("MEDGP_FLOW")) ctx->flow = atoi(ev);
     if (const char *ev = getenv("MEDGP_RL_W")) ctx->rl_width = std::max(0, atoi(ev));
     if (const char *ev = getenv("MEDGP_FORCE_FAIL")) ctx->force_fail = std::max(0, atoi(ev));  // tests of the jitter path through the executables
     if (const char *ev = getenv("MEDGP_STREAMS")) ctx->max_streams = std::max(1, std::min(8, atoi(ev)));
@@ -993,6 +1035,8 @@ MEDGP_API int medgp_cuda_create(medgp_ctx **out, int device, size_t workspace_by
     cudaFuncSetAttribute(k_lauum, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
     cudaFuncSetAttribute(k_potrf_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
     cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
+    cudaFuncSetAttribute(k_potrf_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
+    cudaFuncSetAttribute(k_trtri_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
     cudaFuncSetAttribute(k_trtri_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes + ctx->gemm_smem_pad);
     *out = ctx;
     return MEDGP_OK;

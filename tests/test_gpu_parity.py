@@ -471,6 +471,12 @@ def test_long_stay_patient(api):
     ({"MEDGP_RL": "1", "MEDGP_FUSE_DIAG": "0"}, 6),         # right-looking with separate diagonal / panel kernels
     ({"MEDGP_RL": "1", "MEDGP_STREAMS": "1"}, 40),          # right-looking step kernel, 40 matrices on one stream
     ({"MEDGP_RL": "0"}, 6),                                 # left-looking, one launch per step (k_potrf_step)
+    ({"MEDGP_FLOW": "3"}, 6),                               # dataflow kernels: one launch per factorisation / inverse, per-tile flags
+    ({"MEDGP_FLOW": "3"}, 140),
+    ({"MEDGP_FLOW": "3", "MEDGP_STREAMS": "1"}, 120),       # 120 matrices x 21 tile roles on ONE stream: several waves of waiting roles
+    ({"MEDGP_FLOW": "1", "MEDGP_GRAPHS": "0"}, 40),         # dataflow factorisation only
+    ({"MEDGP_FLOW": "2", "MEDGP_RL": "1"}, 6),              # right-looking factorisation + dataflow inverse (the default for few large matrices)
+    ({"MEDGP_FLOW": "0", "MEDGP_RL": "1"}, 6),              # no dataflow kernels
     ({"MEDGP_RL": "0", "MEDGP_FUSE_DIAG": "0"}, 6),         # left-looking, separate kernels, folded diagonal update
     ({"MEDGP_RL": "0"}, 140),                               # left-looking, separate kernels, large batch
     ({"MEDGP_RL": "0", "MEDGP_STREAMS": "1", "MEDGP_GRAPHS": "0"}, 140),   # single stream, no CUDA graph
