@@ -23,6 +23,9 @@ cap lauum 'k_lauum' 0 tools/profile_c3.py 1
 cap panel10 'k_potrf_panel' 10 tools/profile_c3.py 1
 cap diag10 'k_potrf_diag' 10 tools/profile_c3.py 1
 cap trtri12 'k_trtri_row' 12 tools/profile_c3.py 1
+# 3b. the dataflow kernels on one n = 4000 matrix in flight
+cap flow_potrf_n4000 'k_potrf_flow' 1 tools/longstay_one.py 1 4000 2
+cap flow_trtri_n4000 'k_trtri_flow' 1 tools/longstay_one.py 1 4000 2 1
 # 4. the bench lines themselves (never under a profiler)
 python bench.py --impl reference --steps 4 --warmup 1 > "gpurun_out/${TAG}_bench_reference_arm.json" 2> /dev/null
 python bench.py > "gpurun_out/${TAG}_bench_n1.json" 2> "gpurun_out/${TAG}_bench_n1.err"
