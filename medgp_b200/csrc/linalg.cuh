@@ -438,7 +438,7 @@ __device__ __forceinline__ void potf2_inv_blocked(double *sA, double *sX, double
 // pivot is not positive.  128 threads; sD / sL are the two halves of the dynamic smem ring.
 __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, double *sD, double *sL,
                                                   GjBufs *gjb, int *s_fail, int *__restrict__ fail,
-                                                  bool have_product = true, bool wait_writes = false)
+                                                  bool have_product = true, int *publish = nullptr)
 {
     const int T = e.T, tid = threadIdx.x;
     const double *Kkk = tile_ptr(e.M, T, k, k);
@@ -471,8 +471,9 @@ __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, doub
     potf2_inv_blocked(sL, sD, &gjb->logdet, s_fail);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this thread's tile writes -> the bulk stores below
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0) {  // two groups: X_kk (what waiting panel roles need) and L_kk
         bulk_s2g(e.dinv + (size_t)k * kTileElems, sD, kTileElems * 8);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         bulk_s2g(tile_ptr(e.M, T, k, k), sL, kTileElems * 8);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
@@ -480,6 +481,18 @@ __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, doub
     // forward solve, block k: z_k = X_kk rhs_k (in place)
     tile_matvec_rhs(e, sD, e.rhs + k * MEDGP_NB, e.rhs + k * MEDGP_NB, true, false, gjb->d[0], true, v0);
     MEDGP_PHASE(15)
+    if (publish) {
+        // A consumer inside the SAME kernel waits for this flag (panel roles of k_potrf_step /
+        // k_potrf_flow): it needs X_kk landed and ordered before the generic-proxy flag, and z_k.
+        // X_kk^T and L_kk, which nobody needs before the next kernel, go out afterwards.
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");  // the X_kk store has completed
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        __threadfence();  // z_k
+        __syncthreads();
+        if (tid == 0) flag_release(publish);
+    }
     // write back: L_kk and dinv (X, column-major) are whole-tile copies and leave through the TMA
     // engine (one 34816 B bulk store each, issued before the forward solve above); dinvT (X^T)
     // goes out from registers meanwhile, 16 bytes per store.
@@ -499,15 +512,8 @@ __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, doub
     if (tid == 0) {
         e.blk[k] = gjb->logdet;
         if (*s_fail) fail[e.out_index] = 1;
-        // The shared tiles must outlive the bulk stores' reads.  wait_writes: a consumer inside the
-        // SAME kernel is about to be released (k_potrf_step), so the stores must have landed and be
-        // ordered before the generic-proxy flag; at a kernel boundary the reads are enough.
-        if (wait_writes) {
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            asm volatile("fence.proxy.async;" ::: "memory");
-        } else {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
+        // the shared tiles must outlive the bulk stores' reads (at the kernel boundary that is enough)
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     MEDGP_PHASE(16)
 }
@@ -667,10 +673,7 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, 
             acc_to_smem(acc, sP, 1.0);
         }
         __syncthreads();
-        diag_block_factor(e, k, sP, sX, &gjb, &s_fail, fail, products, true);
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) flag_release(e.flags + k * T + k);
+        diag_block_factor(e, k, sP, sX, &gjb, &s_fail, fail, products, e.flags + k * T + k);
         return;
     }
     const int i = k + row;
@@ -793,8 +796,7 @@ k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap
         __syncthreads();  // all warps are done with the ring before it is reused as sP
         if (k > 0) acc_to_smem(acc, sP, 1.0);
         __syncthreads();
-        diag_block_factor(e, k, sP, sX, &gjb, &s_fail, fail, k > 0, true);
-        tile_publish(flags + k * T + k);
+        diag_block_factor(e, k, sP, sX, &gjb, &s_fail, fail, k > 0, flags + k * T + k);
         return;
     }
     // ---- panel tile (i, k): L_ik = (K_ik - sum_{l<k} L_il L_kl^T) X_kk^T
