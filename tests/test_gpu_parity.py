@@ -58,7 +58,13 @@ def test_matrices_nlml_grad(api, oracle, Q, D, R, n, seed):
     ctx.close()
 
 
-def test_ragged_batch_and_order_invariance(api, oracle):
+@pytest.mark.parametrize("flow", [None, "3", "0"])
+def test_ragged_batch_and_order_invariance(api, oracle, monkeypatch, flow):
+    """sizes from 12 to 500 points in one call: 1 to 8 block rows in the same sub-chunk (the default
+    schedule for such a chunk is right-looking with the dataflow inverse; flow = 3: dataflow
+    factorisation too, whose ticket map must cope with the ragged block-row counts; 0: neither)"""
+    if flow is not None:
+        monkeypatch.setenv("MEDGP_FLOW", flow)
     Q, D, R = 3, 5, 2
     ctx = api.Context(Q, D, R, workspace_bytes=1 << 30)
     rng = np.random.default_rng(0)
