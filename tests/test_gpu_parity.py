@@ -344,6 +344,19 @@ def test_direct_captured_and_replayed_sequences_agree(api, monkeypatch):
     assert (results[0][2] == 1).all()
 
 
+def test_randomised_schedules_short_soak():
+    """tools/fuzz_parity.py for a few seconds: random shapes, ragged batches, forced jitter rounds and
+    random combinations of every scheduling switch, against the oracle at 1e-9 (own process: the
+    switches are environment variables read when a context is created)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "8", "7"], capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0 and "fuzz ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_argument_checks(api):
     Q, D, R = 2, 2, 1
     ctx = api.Context(Q, D, R, workspace_bytes=1 << 28)
