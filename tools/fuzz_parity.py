@@ -60,6 +60,21 @@ while time.time() < t_end:
                                    status=(int(st[b]), int(st0)), f=(float(f[b]), float(f0)), grel=rel(g[b], g0)))
             sys.exit(1)
         evals += 1
+    # predictions (cross-covariance columns ride along the factorisation as extra right-hand sides)
+    npred = min(npat, 3)
+    nstar = rng.integers(1, 4, npred)
+    offs = np.concatenate([[0], np.cumsum(nstar)]).astype(np.int32)
+    mstar = rng.integers(0, D, int(offs[-1])).astype(np.int32)
+    xstar = rng.uniform(0.0, 250.0, int(offs[-1])).astype(np.float32)
+    mean, var, stp = ctx.predict(sids[:npred], thetas[:npred], offs, mstar, xstar)
+    for b in range(npred):
+        sl = slice(offs[b], offs[b + 1])
+        m0, v0, sp0 = oracle.predict(Q, D, R, *pats[b], thetas[b], mstar[sl], xstar[sl])
+        ok = stp[b] == force and np.abs(mean[sl] - m0).max() <= 1e-9 * max(1.0, np.abs(m0).max()) and rel(var[sl], v0) <= 1e-9
+        if not ok:
+            print("PREDICTION MISMATCH", dict(env=env, Q=Q, D=D, R=R, n=int(len(pats[b][1])), status=int(stp[b]), mean=(mean[sl], m0), var=(var[sl], v0)))
+            sys.exit(1)
+        evals += 1
     if force:
         oracle.force_fail(0)
     ctx.close()
