@@ -729,6 +729,20 @@ k_potrf_step(const EvalDesc *__restrict__ descs, int k, int *__restrict__ fail, 
 // FlowMap: act[t] = evaluations of the sub-chunk with more than t block rows (the descriptors are
 // sorted by size, so these are prefixes), base[k] = first ticket of block column / row k.
 #define MEDGP_FLOW_TMAX 64
+#ifdef MEDGP_X_TRACE  // timing experiment: globaltimer stamps of the critical roles of evaluation 0 (tools/flow_trace.py)
+__device__ unsigned long long g_flow_trace[MEDGP_FLOW_TMAX][16];
+__device__ __forceinline__ void flow_stamp(int k, int slot)
+{
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_flow_trace[k][slot] = t;
+    }
+}
+#define FLOW_STAMP(cond, k, slot) { if (cond) flow_stamp(k, slot); }
+#else
+#define FLOW_STAMP(cond, k, slot)
+#endif
 struct FlowMap {
     int Tmax, total;
     int act[MEDGP_FLOW_TMAX + 1];
@@ -778,6 +792,8 @@ k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap
     double acc[4][4][2];
     acc_zero(acc);
     int waited = -1;  // (lane 0 of the producer warp) last tile pair whose flags have been seen
+    const bool tr = (s_role[2] == 0);
+    FLOW_STAMP(tr && r <= 1, k, r == 0 ? 0 : 8)  // role started
     if (r == 0) {
         // ---- diagonal block k: D = K_kk - sum_{l<k} L_kl L_kl^T, factor, invert, forward-solve block
         if (k > 0) prefetch_tile_l2(tile_ptr(M, T, k, k));
@@ -785,6 +801,9 @@ k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap
                       [&](int l, const double *&A, const double *&B) {
                           if (l > waited) {
                               flag_wait(flags + k * T + l);
+#ifdef MEDGP_X_TRACE
+                              if (tr && l == k - 1) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_flow_trace[k][1] = t; }
+#endif
                               asm volatile("fence.proxy.async;" ::: "memory");  // the tile's generic-proxy writes -> our bulk copies
                               waited = l;
                           }
@@ -794,9 +813,11 @@ k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap
                       smem, &bars, NoStageFn(), [](int, int wm, int wn) { return wm == 0 && wn == 1; },
                       TileEdge{rows_valid(e, k), rows_valid(e, k), MEDGP_NB});
         __syncthreads();  // all warps are done with the ring before it is reused as sP
+        FLOW_STAMP(tr, k, 2)  // products done
         if (k > 0) acc_to_smem(acc, sP, 1.0);
         __syncthreads();
         diag_block_factor(e, k, sP, sX, &gjb, &s_fail, fail, k > 0, flags + k * T + k);
+        FLOW_STAMP(tr, k, 3)  // factor done, flag published, remaining stores issued
         return;
     }
     // ---- panel tile (i, k): L_ik = (K_ik - sum_{l<k} L_il L_kl^T) X_kk^T
@@ -819,18 +840,24 @@ k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap
     acc_rsub_global(acc, Tik);  // P = K_ik - C (K_ik comes from the assembly kernel: complete at launch)
     __syncthreads();            // every warp is done with the pipeline buffers
     acc_to_smem(acc, sP, 1.0);
+    FLOW_STAMP(tr && r == 1, k, 9)   // products done, waiting for X_kk
     if (threadIdx.x == 0) flag_wait(flags + k * T + k);
+    FLOW_STAMP(tr && r == 1, k, 10)  // flag seen
     __syncthreads();
     tile_bulk_g2s(sX, Xk, &bars);
     tile_bulk_wait(&bars);
     __syncthreads();
+    FLOW_STAMP(tr && r == 1, k, 11)  // X_kk in shared memory
     gemm2_smem(acc, sP, sX, mv);
     acc_to_global(acc, Tik);
+    FLOW_STAMP(tr && r == 1, k, 12)  // second product done, tile stored
     // forward solve: rhs_i -= L_ik z_k.  The roles (i, k') of one block row run in the order of k'
     // (role (i, k) has waited for tile (i, k-1), published after ITS update), so the updates of rhs_i
     // are applied in a fixed order: bit-reproducible, no atomics
     acc_matvec_rhs(acc, e, e.rhs + k * MEDGP_NB, e.rhs + i * MEDGP_NB, red);
+    FLOW_STAMP(tr && r == 1, k, 13)  // right-hand sides updated
     tile_publish(flags + i * T + k);
+    FLOW_STAMP(tr && r == 1, k, 14)  // published
 }
 
 // the triangular inverse the same way: role (j, i), j < i: U_ji = -(sum_{l=j}^{i-1} U_jl L_il^T) X_ii^T with

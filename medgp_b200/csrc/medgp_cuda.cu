@@ -2039,6 +2039,13 @@ MEDGP_API int medgp_cuda_scg_feed(medgp_scg *g, const double *f, const double *g
     return scg_count_active(g, nullptr);
 }
 
+#ifdef MEDGP_X_TRACE
+MEDGP_API int medgp_cuda_debug_flow_trace(unsigned long long *out /* 64 x 16 */)
+{
+    return cudaMemcpyFromSymbol(out, g_flow_trace, sizeof(unsigned long long) * MEDGP_FLOW_TMAX * 16) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 // ======================================================================= mode-kernel KDE
 MEDGP_API int medgp_cuda_kde_mode(medgp_ctx *ctx, int n_sets, const int *offsets, const double *data,
                                   const double *bandwidth, double *mode, double *density)
