@@ -130,9 +130,9 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t by
 }
 
 // inter-CTA flag (same kernel): release by the producer CTA, acquire-spin by the consumers
-__device__ __forceinline__ void flag_release(int *flag)
+__device__ __forceinline__ void flag_release(int *flag, int value = 1)
 {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
 }
 __device__ __forceinline__ int flag_acquire(const int *flag)
 {

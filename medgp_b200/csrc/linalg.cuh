@@ -438,7 +438,7 @@ __device__ __forceinline__ void potf2_inv_blocked(double *sA, double *sX, double
 // pivot is not positive.  128 threads; sD / sL are the two halves of the dynamic smem ring.
 __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, double *sD, double *sL,
                                                   GjBufs *gjb, int *s_fail, int *__restrict__ fail,
-                                                  bool have_product = true, int *publish = nullptr)
+                                                  bool have_product = true, int *publish = nullptr, int publish_value = 1)
 {
     const int T = e.T, tid = threadIdx.x;
     const double *Kkk = tile_ptr(e.M, T, k, k);
@@ -448,7 +448,7 @@ __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, doub
 #pragma unroll
     for (int u = 0; u < 16; u++) {
         const int idx = tid + MEDGP_DIAG_THREADS * u, c = idx >> 5, rp = idx & 31;
-        kv[u] = *reinterpret_cast<const double2 *>(Kkk + c * MEDGP_SLD + 2 * rp);
+        kv[u] = __ldcg(reinterpret_cast<const double2 *>(Kkk + c * MEDGP_SLD + 2 * rp));  // (through L2: k_potrf_flow's chained roles read a tile another CTA of the launch wrote)
     }
     const double v0 = (tid < MEDGP_NB) ? __ldcg(e.rhs + k * MEDGP_NB + tid) : 0.0;
 #pragma unroll
@@ -491,7 +491,7 @@ __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, doub
         }
         __threadfence();  // z_k
         __syncthreads();
-        if (tid == 0) flag_release(publish);
+        if (tid == 0) flag_release(publish, publish_value);
     }
     // write back: L_kk and dinv (X, column-major) are whole-tile copies and leave through the TMA
     // engine (one 34816 B bulk store each, issued before the forward solve above); dinvT (X^T)
@@ -749,9 +749,9 @@ struct FlowMap {
     int base[MEDGP_FLOW_TMAX + 1];
 };
 
-__device__ __forceinline__ void flag_wait(const int *flag)
+__device__ __forceinline__ void flag_wait(const int *flag, int at_least = 1)
 {
-    while (flag_acquire(flag) == 0) __nanosleep(40);
+    while (flag_acquire(flag) < at_least) __nanosleep(40);
 }
 
 // publish a finished tile: every thread's stores, then the flag (call with all threads)
@@ -762,6 +762,17 @@ __device__ __forceinline__ void tile_publish(int *flag)
     if (threadIdx.x == 0) flag_release(flag);
 }
 
+// Roles of k_potrf_flow, in ticket order, for block column c = 0, 1, ...:
+//   (c == 0)  DIAG0: factor block 0;
+//   (c >= 1)  PRE(c+1): D' = K_{c+1,c+1} - sum_{l<c} L_{c+1,l} L_{c+1,l}^T, everything of the next diagonal
+//             block but its last term, written back into the tile (diagonal flag value 1);
+//   PANEL(i, c), i > c: L_ic; the role of tile (c+1, c) CONTINUES: it still holds L_{c+1,c} on chip, forms the
+//             last term from shared memory, subtracts it from D' and factors block c+1 (diagonal flag value 2).
+// Without the chaining the next diagonal block would fetch tile (c+1, c) back through L2 for that last
+// product: 8.5 us of the 28 us a block column takes (tools/flow_trace.py, profiles/r02_flow_trace.txt).
+// Every role waits for smaller tickets only: PRE(c+1) needs block columns < c, PANEL(i, c) needs block
+// columns < c and the factor of block c (chained to a PANEL role of column c-1, or DIAG0), the chained
+// factorisation needs PRE(c+1), the first ticket(s) of its own column.
 __global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
 k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap map, int *__restrict__ fail,
              int *__restrict__ ticket)
@@ -773,18 +784,23 @@ k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap
     __shared__ int s_fail, s_role[3];
     if (threadIdx.x == 0) {
         const int t = atomicAdd(ticket, 1);
-        int k = 0;
-        while (k + 1 < map.Tmax && map.base[k + 1] <= t) k++;
-        int rem = t - map.base[k], r = 0;
-        while (k + r < map.Tmax && rem >= map.act[k + r]) rem -= map.act[k + r++];  // row offset r: act[k + r] evaluations have that row
-        s_role[0] = k; s_role[1] = r; s_role[2] = rem;
+        int c = 0;
+        while (c + 1 < map.Tmax && map.base[c + 1] <= t) c++;
+        int rem = t - map.base[c], r = -1;  // r = -1: DIAG0 / PRE(c+1); r >= 1: PANEL(c + r, c)
+        const int nfirst = c == 0 ? map.act[0] : (c + 1 < map.Tmax ? map.act[c + 1] : 0);
+        if (rem >= nfirst) {
+            rem -= nfirst;
+            r = 1;
+            while (c + r < map.Tmax && rem >= map.act[c + r]) rem -= map.act[c + r++];
+        }
+        s_role[0] = c; s_role[1] = r; s_role[2] = rem;
         s_fail = 0;
     }
     __syncthreads();
-    const int k = s_role[0], r = s_role[1];
+    const int c = s_role[0], r = s_role[1];
     const EvalDesc &e = descs[s_role[2]];
     if (e.skip) return;  // (every role of this evaluation returns: nobody waits for it)
-    const int T = e.T, i = k + r;
+    const int T = e.T;
     double *M = e.M;
     int *flags = e.flags;
     double *sP = smem, *sX = smem + kTileElems;
@@ -793,17 +809,18 @@ k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap
     acc_zero(acc);
     int waited = -1;  // (lane 0 of the producer warp) last tile pair whose flags have been seen
     const bool tr = (s_role[2] == 0);
-    FLOW_STAMP(tr && r <= 1, k, r == 0 ? 0 : 8)  // role started
-    if (r == 0) {
-        // ---- diagonal block k: D = K_kk - sum_{l<k} L_kl L_kl^T, factor, invert, forward-solve block
-        if (k > 0) prefetch_tile_l2(tile_ptr(M, T, k, k));
-        gemm_nt_tiles(acc, k,
+    if (r < 0 && c == 0) {  // ---- DIAG0
+        diag_block_factor(e, 0, sP, sX, &gjb, &s_fail, fail, false, flags, 2);
+        return;
+    }
+    if (r < 0) {  // ---- PRE(k), k = c + 1: all but the last term of the diagonal block
+        const int k = c + 1;
+        double *Kkk = tile_ptr(M, T, k, k);
+        prefetch_tile_l2(Kkk);
+        gemm_nt_tiles(acc, k - 1,
                       [&](int l, const double *&A, const double *&B) {
                           if (l > waited) {
                               flag_wait(flags + k * T + l);
-#ifdef MEDGP_X_TRACE
-                              if (tr && l == k - 1) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_flow_trace[k][1] = t; }
-#endif
                               asm volatile("fence.proxy.async;" ::: "memory");  // the tile's generic-proxy writes -> our bulk copies
                               waited = l;
                           }
@@ -812,15 +829,14 @@ k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap
                       },
                       smem, &bars, NoStageFn(), [](int, int wm, int wn) { return wm == 0 && wn == 1; },
                       TileEdge{rows_valid(e, k), rows_valid(e, k), MEDGP_NB});
-        __syncthreads();  // all warps are done with the ring before it is reused as sP
-        FLOW_STAMP(tr, k, 2)  // products done
-        if (k > 0) acc_to_smem(acc, sP, 1.0);
-        __syncthreads();
-        diag_block_factor(e, k, sP, sX, &gjb, &s_fail, fail, k > 0, flags + k * T + k);
-        FLOW_STAMP(tr, k, 3)  // factor done, flag published, remaining stores issued
+        acc_rsub_global(acc, Kkk);  // (the skipped upper-right quadrant keeps K: it is masked when the block is factored)
+        acc_to_global(acc, Kkk);
+        tile_publish(flags + k * T + k);  // value 1: D' is in place
         return;
     }
-    // ---- panel tile (i, k): L_ik = (K_ik - sum_{l<k} L_il L_kl^T) X_kk^T
+    // ---- PANEL(i, k): L_ik = (K_ik - sum_{l<k} L_il L_kl^T) X_kk^T
+    const int k = c, i = c + r;
+    FLOW_STAMP(tr && r == 1, k, 8)  // role started
     double *Tik = tile_ptr(M, T, i, k);
     const double *Xk = e.dinv + (size_t)k * kTileElems;
     prefetch_tile_l2(Tik);
@@ -841,7 +857,7 @@ k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap
     __syncthreads();            // every warp is done with the pipeline buffers
     acc_to_smem(acc, sP, 1.0);
     FLOW_STAMP(tr && r == 1, k, 9)   // products done, waiting for X_kk
-    if (threadIdx.x == 0) flag_wait(flags + k * T + k);
+    if (threadIdx.x == 0) flag_wait(flags + k * T + k, 2);
     FLOW_STAMP(tr && r == 1, k, 10)  // flag seen
     __syncthreads();
     tile_bulk_g2s(sX, Xk, &bars);
@@ -858,6 +874,18 @@ k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap
     FLOW_STAMP(tr && r == 1, k, 13)  // right-hand sides updated
     tile_publish(flags + i * T + k);
     FLOW_STAMP(tr && r == 1, k, 14)  // published
+    if (r != 1) return;
+    // ---- chained: block i = k + 1.  Last term L_ik L_ik^T from the tile still on chip, D' from PRE(i)
+    acc_to_smem(acc, sP, 1.0);  // (tile_publish ended with a block barrier: the second product is done with sP)
+    __syncthreads();
+    syrk_smem(acc, sP, mv);
+    __syncthreads();  // everyone is done reading sP
+    acc_to_smem(acc, sP, 1.0);
+    if (k >= 1 && threadIdx.x == 0) flag_wait(flags + i * T + i, 1);  // (block 1 has no earlier term: its tile is K_11)
+    __syncthreads();
+    FLOW_STAMP(tr, i, 2)  // last term formed, D' available
+    diag_block_factor(e, i, sP, sX, &gjb, &s_fail, fail, true, flags + i * T + i, 2);
+    FLOW_STAMP(tr, i, 3)  // factor done, flag published, remaining stores issued
 }
 
 // the triangular inverse the same way: role (j, i), j < i: U_ji = -(sum_{l=j}^{i-1} U_jl L_il^T) X_ii^T with

@@ -523,9 +523,10 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
         fm_potrf.Tmax = fm_trtri.Tmax = Tmax;
         for (int t = 0; t <= Tmax; t++) fm_potrf.act[t] = fm_trtri.act[t] = (int)sc.act(t);
         int tot = 0;
-        for (int k = 0; k < Tmax; k++) {  // block column k: one role per (evaluation, block row >= k)
-            fm_potrf.base[k] = tot;
-            for (int r = 0; k + r < Tmax; r++) tot += fm_potrf.act[k + r];
+        for (int c = 0; c < Tmax; c++) {  // block column c (roles: see k_potrf_flow)
+            fm_potrf.base[c] = tot;
+            tot += c == 0 ? fm_potrf.act[0] : (c + 1 < Tmax ? fm_potrf.act[c + 1] : 0);  // DIAG0 / PRE(c+1)
+            for (int r = 1; c + r < Tmax; r++) tot += fm_potrf.act[c + r];               // PANEL(c + r, c)
         }
         fm_potrf.base[Tmax] = fm_potrf.total = tot;
         tot = 0;

@@ -20,15 +20,14 @@ for _ in range(3):
 buf = np.zeros((64, 16), dtype=np.uint64)
 assert ctx.lib.medgp_cuda_debug_flow_trace(buf.ctypes.data_as(ctypes.c_void_p)) == 0
 t = buf.astype(np.float64) / 1e3  # us
-names = ["diag: last operand flag seen -> products done", "diag: products done -> factor done + published",
-         "panel(k+1,k): X flag seen after diag publish", "panel: flag seen -> X in smem", "panel: second product + store",
-         "panel: rhs update", "panel: publish", "next diag: sees flag(k+1,k) after panel publish"]
+names = ["panel(k+1,k): flag of block k seen -> X_kk in smem", "panel: second product + tile stored", "panel: rhs update",
+         "panel: publish tile", "chained: last term from smem (+ wait for D')", "chained: factor block k+1, publish",
+         "panel(k+2,k+1): sees the flag"]
 rows = []
-for k in range(2, 61):
-    d, p, dn = t[k], t[k], t[k + 1]
-    rows.append([d[2] - d[1], d[3] - d[2], p[10] - d[3], p[11] - p[10], p[12] - p[11], p[13] - p[12], p[14] - p[13], dn[1] - p[14],
-                 dn[1] - d[1]])
+for k in range(2, 60):
+    p, d, pn = t[k], t[k + 1], t[k + 1]
+    rows.append([p[11] - p[10], p[12] - p[11], p[13] - p[12], p[14] - p[13], d[2] - p[14], d[3] - d[2], pn[10] - d[3], pn[10] - p[10]])
 rows = np.array(rows)
 for i, nm in enumerate(names):
     print(f"{nm:55s} median {np.median(rows[:, i]):6.2f} us   mean {rows[:, i].mean():6.2f}")
-print(f"{'column period (flag(k,k-1) seen -> flag(k+1,k) seen)':55s} median {np.median(rows[:, 8]):6.2f} us   mean {rows[:, 8].mean():6.2f}")
+print(f"{'column period (flag of block k seen -> flag of block k+1 seen)':55s} median {np.median(rows[:, 7]):6.2f} us   mean {rows[:, 7].mean():6.2f}")
