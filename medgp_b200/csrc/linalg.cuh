@@ -515,6 +515,16 @@ __device__ __forceinline__ void diag_block_factor(const EvalDesc &e, int k, doub
         // the shared tiles must outlive the bulk stores' reads (at the kernel boundary that is enough)
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
+    if (publish) {
+        // second signal (value + 1): X_kk^T and L_kk are in place too (the dataflow kernel's inverse roles read X_kk^T)
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) flag_release(publish, publish_value + 1);
+    }
     MEDGP_PHASE(16)
 }
 
@@ -775,8 +785,13 @@ __device__ __forceinline__ void tile_publish(int *flag)
 // factorisation needs PRE(c+1), the first ticket(s) of its own column.
 __global__ void __launch_bounds__(MEDGP_GEMM_THREADS, 3)
 k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap map, int *__restrict__ fail,
-             int *__restrict__ ticket)
+             int *__restrict__ ticket, int with_inverse)
 {
+    // with_inverse: block column c also carries the roles INV(j, c), j < c, of the triangular inverse
+    // (U_jc, as in k_trtri_flow), after its PANEL roles: they need block row c of L (columns < c), X_cc
+    // (chained to column c-1), X_jj^T (diagonal flag value 3: stored) and U_jl, l < c (INV roles of
+    // earlier columns) -- smaller tickets all.  The factorisation's critical chain leaves most of the
+    // SMs idle; the inverse fills them instead of running afterwards.
     extern __shared__ __align__(128) double smem[];
     __shared__ GemmBars bars;
     __shared__ __align__(16) GjBufs gjb;
@@ -792,6 +807,10 @@ k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap
             rem -= nfirst;
             r = 1;
             while (c + r < map.Tmax && rem >= map.act[c + r]) rem -= map.act[c + r++];
+            if (c + r >= map.Tmax) {  // past the PANEL roles: INV(j, c), r = -2 - j
+                r = -2 - rem / map.act[c];
+                rem = rem % map.act[c];
+            }
         }
         s_role[0] = c; s_role[1] = r; s_role[2] = rem;
         s_fail = 0;
@@ -809,6 +828,36 @@ k_potrf_flow(const EvalDesc *__restrict__ descs, const __grid_constant__ FlowMap
     acc_zero(acc);
     int waited = -1;  // (lane 0 of the producer warp) last tile pair whose flags have been seen
     const bool tr = (s_role[2] == 0);
+    if (r <= -2) {  // ---- INV(j, i): U_ji = -(sum_{l=j}^{i-1} U_jl L_il^T) X_ii^T, U_jj = X_jj^T
+        const int i = c, j = -2 - r, nv = rows_valid(e, i);
+        const double *XTj = e.dinvT + (size_t)j * kTileElems;
+        gemm_nt_tiles(acc, i - j,
+                      [&](int l0, const double *&A, const double *&B) {
+                          const int l = j + l0;
+                          if (l0 > waited) {
+                              if (l0 == 0) flag_wait(flags + j * T + j, 3);  // X_jj^T stored
+                              else flag_wait(flags + j * T + l);             // U_jl
+                              flag_wait(flags + i * T + l);                  // L_il
+                              asm volatile("fence.proxy.async;" ::: "memory");
+                              waited = l0;
+                          }
+                          A = (l0 == 0) ? XTj : tile_ptr(M, T, j, l);
+                          B = tile_ptr(M, T, i, l);
+                      },
+                      smem, &bars, NoStageFn(), [](int ch, int wm, int) { return ch < 2 && wm == 1; },
+                      TileEdge{MEDGP_NB, nv, MEDGP_NB});
+        __syncthreads();
+        if (threadIdx.x == 0) flag_wait(flags + i * T + i, 2);  // X_ii
+        __syncthreads();
+        tile_bulk_g2s(sX, e.dinv + (size_t)i * kTileElems, &bars);
+        acc_to_smem(acc, sP, -1.0);
+        tile_bulk_wait(&bars);
+        __syncthreads();
+        gemm2_smem(acc, sP, sX, MEDGP_NB, nv);
+        acc_to_global(acc, tile_ptr(M, T, j, i));
+        tile_publish(flags + j * T + i);
+        return;
+    }
     if (r < 0 && c == 0) {  // ---- DIAG0
         diag_block_factor(e, 0, sP, sX, &gjb, &s_fail, fail, false, flags, 2);
         return;

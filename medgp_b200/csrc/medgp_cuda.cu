@@ -519,6 +519,8 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     const bool flow = (flow_bits & 1) != 0 && Tmax <= MEDGP_FLOW_TMAX;        // bit 0: factorisation
     const bool flow_trtri = (flow_bits & 2) != 0 && Tmax <= MEDGP_FLOW_TMAX;  // bit 1: triangular inverse
     FlowMap fm_potrf{}, fm_trtri{};
+    // both: the inverse's roles ride in the factorisation's launch (k_potrf_flow with_inverse)
+    const bool flow_both = flow && flow_trtri && (grad || mode == 4);
     if (flow || flow_trtri) {
         fm_potrf.Tmax = fm_trtri.Tmax = Tmax;
         for (int t = 0; t <= Tmax; t++) fm_potrf.act[t] = fm_trtri.act[t] = (int)sc.act(t);
@@ -527,6 +529,7 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
             fm_potrf.base[c] = tot;
             tot += c == 0 ? fm_potrf.act[0] : (c + 1 < Tmax ? fm_potrf.act[c + 1] : 0);  // DIAG0 / PRE(c+1)
             for (int r = 1; c + r < Tmax; r++) tot += fm_potrf.act[c + r];               // PANEL(c + r, c)
+            if (flow_both) tot += c * fm_potrf.act[c];                                   // INV(j, c), j < c
         }
         fm_potrf.base[Tmax] = fm_potrf.total = tot;
         tot = 0;
@@ -541,7 +544,7 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     if (flow) {
         const FlowMap fm = fm_potrf;
         begin(MEDGP_STAGE_POTRF);
-        out.push_back([=]() { k_potrf_flow<<<fm.total, MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, fm, d_fail, tickets + kTicketsPerSub - 2); L[MEDGP_STAGE_POTRF]++; });
+        out.push_back([=]() { k_potrf_flow<<<fm.total, MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, fm, d_fail, tickets + kTicketsPerSub - 2, flow_both ? 1 : 0); L[MEDGP_STAGE_POTRF]++; });
         end(MEDGP_STAGE_POTRF);
     }
     if (rl && !flow) {
@@ -627,7 +630,7 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     end(MEDGP_STAGE_SOLVE);
     if (grad || mode == 4) {
         begin(MEDGP_STAGE_TRTRI);
-        if (flow_trtri && fm_trtri.total > 0) {
+        if (flow_trtri && !flow_both && fm_trtri.total > 0) {
             const FlowMap fm = fm_trtri;
             out.push_back([=]() { k_trtri_flow<<<fm.total, MEDGP_GEMM_THREADS, gemm_smem, st>>>(dd, fm, tickets + kTicketsPerSub - 1); L[MEDGP_STAGE_TRTRI]++; });
         }
