@@ -511,11 +511,14 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     // panel follows its last panel kernel; the next-panel part of panel p follows the bulk of
     // panel p-1 (both touch the same block columns); bulks are ordered by their stream.
     // Dataflow path: ONE launch for the factorisation, ONE for the triangular inverse (linalg.cuh)
-    // Measured (n = 4000 with 1 / 5 / 32 matrices in flight, C2, C3): the dataflow inverse wins for few
-    // large matrices (-10 % / -7 % on NLML+gradient with 1 / 5 in flight) and loses 1-3 % for many small
-    // ones; the dataflow factorisation wins only for one or two matrices in flight (its resident roles
+    // Measured (n = 4000 with 1 / 5 / 32 matrices in flight, C2, C3, batch-1 latencies): the dataflow inverse
+    // wins for few large matrices (-10 % / -7 % on NLML+gradient with 1 / 5 in flight) and loses 1-3 % for
+    // many small ones; the dataflow factorisation wins only where little is in flight (its resident roles
     // advance one tile product per finished block column, so it is latency-, not throughput-oriented).
-    const int flow_bits = ctx->flow >= 0 ? ctx->flow : (rl ? (ctx->rl_count_now <= 2 ? 3 : 2) : 0);
+    // Small chunks (one or two matrices of any size, or a handful of small ones: the batch-1 shape of
+    // main_one_train's line searches) take both: n = 300 / 500 with 1-5 evaluations per call -20 % latency.
+    const bool small_chunk = ctx->rl_count_now <= 2 || ctx->rl_count_now * (size_t)Tmax <= 48;
+    const int flow_bits = ctx->flow >= 0 ? ctx->flow : (small_chunk ? 3 : (rl ? 2 : 0));
     const bool flow = (flow_bits & 1) != 0 && Tmax <= MEDGP_FLOW_TMAX;        // bit 0: factorisation
     const bool flow_trtri = (flow_bits & 2) != 0 && Tmax <= MEDGP_FLOW_TMAX;  // bit 1: triangular inverse
     FlowMap fm_potrf{}, fm_trtri{};
