@@ -517,7 +517,11 @@ void build_sub(medgp_ctx *ctx, const SubChunk &sc, bool rl, bool fold, cudaStrea
     // advance one tile product per finished block column, so it is latency-, not throughput-oriented).
     // Small chunks (one or two matrices of any size, or a handful of small ones: the batch-1 shape of
     // main_one_train's line searches) take both: n = 300 / 500 with 1-5 evaluations per call -20 % latency.
-    const bool small_chunk = ctx->rl_count_now <= 2 || ctx->rl_count_now * (size_t)Tmax <= 48;
+    // (tools/sweep_small.py, tools/sweep_mid.py: up to 16 block rows the dataflow pair wins by 15-30 % until
+    // count x block rows reaches about 700 -- 48 matrices of n = 900 -- and loses beyond; with more block rows
+    // it only wins for one or two matrices, the right-looking schedule takes over from three)
+    const size_t cnt_now = ctx->rl_count_now;
+    const bool small_chunk = cnt_now <= 2 || cnt_now * (size_t)Tmax <= 48 || (Tmax <= 16 && cnt_now * (size_t)Tmax <= 720);
     const int flow_bits = ctx->flow >= 0 ? ctx->flow : (small_chunk ? 3 : (rl ? 2 : 0));
     const bool flow = (flow_bits & 1) != 0 && Tmax <= MEDGP_FLOW_TMAX;        // bit 0: factorisation
     const bool flow_trtri = (flow_bits & 2) != 0 && Tmax <= MEDGP_FLOW_TMAX;  // bit 1: triangular inverse
