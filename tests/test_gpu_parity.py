@@ -461,6 +461,17 @@ def test_cohort_sweep_sizes(api):
     ctx.close()
 
 
+def test_block_row_limit_of_the_dataflow_kernels():
+    """n = 4096 (64 block rows: the dataflow kernels' limit) and n = 4097 / 4160 (beyond it: right-looking
+    schedule) against the numpy oracle"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "edge_tmax.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "edge ok" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
+
+
 def test_long_stay_patient(api):
     """C4: n = 4000, 24 features, Q = 5, several initialisations of the same series in flight
     (right-looking blocked Cholesky path) against the numpy/LAPACK oracle."""
